@@ -1,0 +1,105 @@
+"""ctypes binding of libcommu_b200.so (the C-ABI declared in include/commu_b200.h).
+
+There is no fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_PKG_ROOT, "lib", "libcommu_b200.so")
+
+_lib = None
+_lock = threading.Lock()
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_int64 = ctypes.c_int64
+c_float = ctypes.c_float
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("a", c_void_p), ("lda", c_int64), ("a_mn_major", c_int),
+        ("b", c_void_p), ("ldb", c_int64), ("b_mn_major", c_int),
+        ("m", c_int), ("n", c_int), ("k", c_int),
+        ("split_k", c_int), ("alpha", c_float),
+        ("bias", c_void_p), ("relu", c_int),
+        ("relu_mask", c_void_p), ("ld_mask", c_int64),
+        ("add_f32", c_void_p), ("ld_add", c_int64),
+        ("out_bf16", c_void_p), ("ld_out_bf16", c_int64),
+        ("out_f32", c_void_p), ("ld_out_f32", c_int64),
+        ("f32_atomic", c_int), ("impl", c_int),
+    ]
+
+
+def build_if_needed():
+    """(Re)build the shared library in-tree when nvcc is available and sources are newer."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("commu_b200_build", os.path.join(_PKG_ROOT, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build()
+
+
+def lib():
+    """Loads the shared library (once)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "commu_b200: %s is missing. Build it with `python commu-code_b200/build.py` "
+                "(needs nvcc). There is no CPU or PyTorch fallback for the hot path." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        L.commu_last_error.restype = ctypes.c_char_p
+        L.commu_launch_count.restype = ctypes.c_longlong
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().commu_last_error()
+        raise RuntimeError("commu_b200 native call failed (%d): %s" % (rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def gemm(a, b, *, m, n, k, lda=None, ldb=None, a_mn=False, b_mn=False, split_k=1, alpha=1.0,
+         bias=None, relu=False, relu_mask=None, ld_mask=0, add_f32=None, ld_add=0,
+         out_bf16=None, ld_out_bf16=0, out_f32=None, ld_out_f32=0, f32_atomic=False, impl=0):
+    """C[m,n] = alpha * sum_k A[m,k] B[n,k] with the fused epilogue of commu_gemm_bf16."""
+    args = GemmArgs()
+    args.a = a.data_ptr(); args.lda = lda if lda is not None else a.stride(0); args.a_mn_major = int(a_mn)
+    args.b = b.data_ptr(); args.ldb = ldb if ldb is not None else b.stride(0); args.b_mn_major = int(b_mn)
+    args.m, args.n, args.k = m, n, k
+    args.split_k = split_k
+    args.alpha = alpha
+    args.bias = bias.data_ptr() if bias is not None else None
+    args.relu = int(relu)
+    args.relu_mask = relu_mask.data_ptr() if relu_mask is not None else None
+    args.ld_mask = ld_mask or (relu_mask.stride(0) if relu_mask is not None else 0)
+    args.add_f32 = add_f32.data_ptr() if add_f32 is not None else None
+    args.ld_add = ld_add or (add_f32.stride(0) if add_f32 is not None else 0)
+    args.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+    args.ld_out_bf16 = ld_out_bf16 or (out_bf16.stride(0) if out_bf16 is not None else 0)
+    args.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+    args.ld_out_f32 = ld_out_f32 or (out_f32.stride(0) if out_f32 is not None else 0)
+    args.f32_atomic = int(f32_atomic)
+    args.impl = impl
+    check(lib().commu_gemm_bf16(ctypes.byref(args), stream_ptr()))

@@ -1,0 +1,477 @@
+// tcgen05 / TMA / TMEM dense contraction for sm_100a.
+//
+//   C[m,n] = alpha * sum_k A[m,k] * B[n,k]      bf16 operands, fp32 accumulation in TMEM
+//
+// Persistent, warp-specialised kernel (one CTA per SM, 256 threads):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
+//   warp 1   : MMA issuer     (one elected lane issues tcgen05.mma, tcgen05.commit frees slots)
+//   warp 2   : TMEM allocator (2 accumulator buffers so the epilogue overlaps the next tile)
+//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//
+// Both operand majors are supported so forward (K-major x K-major), dgrad (K-major x K-major on a
+// transposed weight shadow) and wgrad (MN-major x MN-major: reduction over tokens) all run here.
+// Replaces the nn.Linear calls of the reference (commu/model/model.py:285-286, 348, 163-169, 46)
+// and their autograd backward.
+#include "api_common.h"
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+struct GemmKernelParams {
+  int M, N, K;
+  int a_mn, b_mn;
+  int split_k;
+  float alpha;
+  const float* bias;
+  int relu;
+  const bf16* relu_mask;
+  long long ld_mask;
+  const float* add_f32;
+  long long ld_add;
+  bf16* out_bf16;
+  long long ld_out_bf16;
+  float* out_f32;
+  long long ld_out_f32;
+  int f32_atomic;
+  int vec_ok;  // all leading dims / bases allow 16-byte vector stores
+};
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ void epilogue_store(const GemmKernelParams& p, const uint32_t (&r)[32],
+                                               int row, int n0) {
+  if (row >= p.M) return;
+  const bool full = (n0 + 32 <= p.N) && p.vec_ok;
+  float v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+  if (p.bias) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (p.relu_mask) {
+    const bf16* mrow = p.relu_mask + (long long)row * p.ld_mask + n0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 q = __ldg(reinterpret_cast<const uint4*>(mrow) + i);
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!(cb::bf16_lo(w[j]) > 0.f)) v[i * 8 + j * 2] = 0.f;
+          if (!(cb::bf16_hi(w[j]) > 0.f)) v[i * 8 + j * 2 + 1] = 0.f;
+        }
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
+    }
+  }
+  if (p.add_f32) {
+    const float* arow = p.add_f32 + (long long)row * p.ld_add + n0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(arow) + i);
+        v[i * 4 + 0] += q.x;
+        v[i * 4 + 1] += q.y;
+        v[i * 4 + 2] += q.z;
+        v[i * 4 + 3] += q.w;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) v[i] += arow[i];
+    }
+  }
+  if (p.out_bf16) {
+    bf16* orow = p.out_bf16 + (long long)row * p.ld_out_bf16 + n0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 q;
+        q.x = cb::pack_bf16(v[i * 8 + 0], v[i * 8 + 1]);
+        q.y = cb::pack_bf16(v[i * 8 + 2], v[i * 8 + 3]);
+        q.z = cb::pack_bf16(v[i * 8 + 4], v[i * 8 + 5]);
+        q.w = cb::pack_bf16(v[i * 8 + 6], v[i * 8 + 7]);
+        reinterpret_cast<uint4*>(orow)[i] = q;
+      }
+    } else {
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) orow[i] = __float2bfloat16_rn(v[i]);
+    }
+  }
+  if (p.out_f32) {
+    float* orow = p.out_f32 + (long long)row * p.ld_out_f32 + n0;
+    if (p.f32_atomic) {
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          cb::red_add_v4(orow + i * 4, v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (n0 + i < p.N) atomicAdd(orow + i, v[i]);
+      }
+    } else {
+      if (full) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<float4*>(orow)[i] =
+              make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
+      } else {
+        for (int i = 0; i < 32; ++i)
+          if (n0 + i < p.N) orow[i] = v[i];
+      }
+    }
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                    const __grid_constant__ CUtensorMap tmap_b, const GemmKernelParams p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per = (kb_total + p.split_k - 1) / p.split_k;
+  const int num_items = m_tiles * n_tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    cb::tma_prefetch_desc(&tmap_a);
+    cb::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      cb::mbar_init(&full_bar[s], 1);
+      cb::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      cb::mbar_init(&tmem_full[b], 1);
+      cb::mbar_init(&tmem_empty[b], 128);
+    }
+    cb::fence_barrier_init();
+  }
+  if (warp == 2) {
+    cb::tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    cb::tmem_relinquish();
+  }
+  cb::tc_fence_before();
+  __syncthreads();
+  cb::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (cb::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int n_blk = item % n_tiles;
+        const int m_blk = (item / n_tiles) % m_tiles;
+        const int ks = item / (n_tiles * m_tiles);
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(kb_total, kb0 + kb_per);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          cb::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          cb::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if (!p.a_mn) {
+            cb::tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / 64; ++a)
+              cb::tma_load_2d(sa + a * (64 * BLOCK_K * 2), &tmap_a, &full_bar[stage],
+                              m_blk * BLOCK_M + a * 64, kb * BLOCK_K);
+          }
+          if (!p.b_mn) {
+            cb::tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 64; ++a)
+              cb::tma_load_2d(sb + a * (64 * BLOCK_K * 2), &tmap_b, &full_bar[stage],
+                              n_blk * BLOCK_N + a * 64, kb * BLOCK_K);
+          }
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (cb::elect_one()) {
+      const uint32_t idesc = cb::umma_idesc_bf16(BLOCK_M, BLOCK_N, p.a_mn, p.b_mn);
+      // K-major: SBO = 8 rows * 128 B, LBO unused. MN-major: SBO = 8 k-rows * 128 B,
+      // LBO = one 64-wide MN atom = BLOCK_K rows * 128 B.
+      const uint32_t a_lbo = p.a_mn ? (BLOCK_K * 128) : 16;
+      const uint32_t b_lbo = p.b_mn ? (BLOCK_K * 128) : 16;
+      const uint32_t a_kstep = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      const uint32_t b_kstep = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int buf = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int ks = item / (n_tiles * m_tiles);
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(kb_total, kb0 + kb_per);
+        if (kb0 >= kb1) continue;
+        cb::mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+        cb::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          cb::mbar_wait(&full_bar[stage], phase);
+          cb::tc_fence_after();
+          const uint32_t sa = cb::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          uint64_t adesc = cb::umma_smem_desc(sa, a_lbo, 1024);
+          uint64_t bdesc = cb::umma_smem_desc(sb, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            cb::umma_bf16_ss(tmem_d, adesc + (uint64_t)(k * a_kstep),
+                             bdesc + (uint64_t)(k * b_kstep), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          cb::umma_commit(&empty_bar[stage]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        cb::umma_commit(&tmem_full[buf]);
+        buf ^= 1;
+        if (buf == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int q = warp - 4;
+    int buf = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int n_blk = item % n_tiles;
+      const int m_blk = (item / n_tiles) % m_tiles;
+      const int ks = item / (n_tiles * m_tiles);
+      const int kb0 = ks * kb_per;
+      const int kb1 = min(kb_total, kb0 + kb_per);
+      if (kb0 >= kb1) continue;
+      cb::mbar_wait(&tmem_full[buf], acc_phase);
+      cb::tc_fence_after();
+      const int row = m_blk * BLOCK_M + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int n0 = n_blk * BLOCK_N + c * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        cb::tmem_ld_32x32b_x32(taddr + c * 32, r);
+        cb::tmem_ld_wait();
+        epilogue_store(p, r, row, n0);
+      }
+      cb::tc_fence_before();
+      cb::mbar_arrive(&tmem_empty[buf]);
+      buf ^= 1;
+      if (buf == 0) acc_phase ^= 1;
+    }
+  }
+
+  cb::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    cb::tc_fence_after();
+    cb::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// Naive SIMT cross-check kernel: same contract, one thread per output element.
+__global__ void gemm_simt_kernel(const bf16* __restrict__ A, long long lda, const bf16* __restrict__ B,
+                                 long long ldb, GemmKernelParams p) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  const int ks = blockIdx.z;
+  if (n >= p.N || m >= p.M) return;
+  const int kper = (p.K + p.split_k - 1) / p.split_k;
+  const int k0 = ks * kper, k1 = min(p.K, k0 + kper);
+  float acc = 0.f;
+  for (int k = k0; k < k1; ++k) {
+    float a = __bfloat162float(p.a_mn ? A[(long long)k * lda + m] : A[(long long)m * lda + k]);
+    float b = __bfloat162float(p.b_mn ? B[(long long)k * ldb + n] : B[(long long)n * ldb + k]);
+    acc = fmaf(a, b, acc);
+  }
+  float v = acc * p.alpha;
+  if (p.split_k > 1 && ks > 0) {
+    atomicAdd(p.out_f32 + (long long)m * p.ld_out_f32 + n, v);
+    return;
+  }
+  if (p.bias) v += p.bias[n];
+  if (p.relu) v = fmaxf(v, 0.f);
+  if (p.relu_mask && !(__bfloat162float(p.relu_mask[(long long)m * p.ld_mask + n]) > 0.f)) v = 0.f;
+  if (p.add_f32) v += p.add_f32[(long long)m * p.ld_add + n];
+  if (p.out_bf16) p.out_bf16[(long long)m * p.ld_out_bf16 + n] = __float2bfloat16_rn(v);
+  if (p.out_f32) {
+    if (p.f32_atomic)
+      atomicAdd(p.out_f32 + (long long)m * p.ld_out_f32 + n, v);
+    else
+      p.out_f32[(long long)m * p.ld_out_f32 + n] = v;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace
+
+namespace cb_host {
+// 2D bf16 tensor map with 128B swizzle: inner (contiguous) extent `inner`, outer extent `outer`,
+// row stride `ld` elements, box {box_inner (=64), box_outer}.
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer,
+                      uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(COMMU_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(COMMU_ERR_CUDA,
+                "cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu", (int)r,
+                ptr, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld);
+  return 0;
+}
+}  // namespace cb_host
+
+template <int BLOCK_N>
+static int launch_tc(const commu_gemm_args* a, const GemmKernelParams& p, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a->a_mn_major)
+    rc = cb_host::make_tmap_bf16_2d(&ta, a->a, a->k, a->m, a->lda, 64, BLOCK_M);
+  else
+    rc = cb_host::make_tmap_bf16_2d(&ta, a->a, a->m, a->k, a->lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!a->b_mn_major)
+    rc = cb_host::make_tmap_bf16_2d(&tb, a->b, a->k, a->n, a->ldb, 64, BLOCK_N);
+  else
+    rc = cb_host::make_tmap_bf16_2d(&tb, a->b, a->n, a->k, a->ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_tiles = cb_host::ceil_div(a->m, BLOCK_M), n_tiles = cb_host::ceil_div(a->n, BLOCK_N);
+  const int items = m_tiles * n_tiles * p.split_k;
+  const int grid = items < cb_host::num_sms() ? items : cb_host::num_sms();
+  cb_host::ProfScope prof(cb_host::PROF_GEMM, stream);
+  gemm_tcgen05_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  cb_host::count_launch();
+  CB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int commu_gemm_bf16(const commu_gemm_args* a, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  CB_REQUIRE(a && a->a && a->b, "gemm: null operand");
+  CB_REQUIRE(a->m > 0 && a->n > 0 && a->k > 0, "gemm: bad shape m=%d n=%d k=%d", a->m, a->n, a->k);
+  CB_REQUIRE(a->out_bf16 || a->out_f32, "gemm: no output");
+  int split = a->split_k < 1 ? 1 : a->split_k;
+  const int kb_total = cb_host::ceil_div(a->k, BLOCK_K);
+  if (split > kb_total) split = kb_total;
+  if (split > 1) {
+    CB_REQUIRE(a->out_f32 && a->f32_atomic && !a->out_bf16 && !a->bias && !a->relu &&
+                   !a->relu_mask && !a->add_f32,
+               "gemm: split_k>1 needs a pure atomic fp32 epilogue");
+    // make every split non-empty
+    const int per = cb_host::ceil_div(kb_total, split);
+    split = cb_host::ceil_div(kb_total, per);
+  }
+  GemmKernelParams p;
+  p.M = a->m; p.N = a->n; p.K = a->k;
+  p.a_mn = a->a_mn_major ? 1 : 0;
+  p.b_mn = a->b_mn_major ? 1 : 0;
+  p.split_k = split;
+  p.alpha = a->alpha;
+  p.bias = a->bias;
+  p.relu = a->relu;
+  p.relu_mask = static_cast<const bf16*>(a->relu_mask);
+  p.ld_mask = a->ld_mask;
+  p.add_f32 = a->add_f32;
+  p.ld_add = a->ld_add;
+  p.out_bf16 = static_cast<bf16*>(a->out_bf16);
+  p.ld_out_bf16 = a->ld_out_bf16;
+  p.out_f32 = a->out_f32;
+  p.ld_out_f32 = a->ld_out_f32;
+  p.f32_atomic = a->f32_atomic;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  p.vec_ok = 1;
+  if (p.out_bf16 && (!al16(p.out_bf16) || (p.ld_out_bf16 % 8))) p.vec_ok = 0;
+  if (p.out_f32 && (!al16(p.out_f32) || (p.ld_out_f32 % 4))) p.vec_ok = 0;
+  if (p.relu_mask && (!al16(p.relu_mask) || (p.ld_mask % 8))) p.vec_ok = 0;
+  if (p.add_f32 && (!al16(p.add_f32) || (p.ld_add % 4))) p.vec_ok = 0;
+
+  if (a->impl == 1) {
+    dim3 grid(cb_host::ceil_div(a->n, 128), a->m, split);
+    gemm_simt_kernel<<<grid, 128, 0, stream>>>(static_cast<const bf16*>(a->a), a->lda,
+                                               static_cast<const bf16*>(a->b), a->ldb, p);
+    cb_host::count_launch();
+    CB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  CB_REQUIRE(al16(a->a) && al16(a->b) && (a->lda % 8 == 0) && (a->ldb % 8 == 0),
+             "gemm: TMA needs 16-byte aligned operands and leading dims that are multiples of 8 "
+             "(lda=%lld ldb=%lld)", (long long)a->lda, (long long)a->ldb);
+  if (a->n > 128) return launch_tc<256>(a, p, stream);
+  return launch_tc<128>(a, p, stream);
+}
