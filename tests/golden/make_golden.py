@@ -1,0 +1,240 @@
+"""Generates tests/golden/*.npz by importing the UNMODIFIED reference (POZAlabs/ComMU-code) from
+/root/reference in the build container.  The reference cannot travel to the GPU box, so the
+outputs are frozen here; this script is committed so the fixtures are reproducible.
+
+    python tests/golden/make_golden.py            # rewrites every fixture
+
+Third-party modules the reference imports at module scope but that are absent from this image
+(yacs, miditoolkit, parmap, pretty_midi) are stubbed in sys.modules ONLY to make the import of
+commu.midi_generator.midi_inferrer succeed; none of them is on the arithmetic path.
+"""
+import os
+import sys
+import types
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+REF = os.environ.get("COMMU_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _stub_modules():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _CfgNode(dict):
+        pass
+
+    mod("yacs")
+    mod("yacs.config", CfgNode=_CfgNode)
+    sys.modules["yacs"].config = sys.modules["yacs.config"]
+    mod("miditoolkit", MidiFile=object, Instrument=object, TempoChange=object, Note=object,
+        Marker=object, TimeSignature=object)
+    mod("miditoolkit.midi")
+    mod("miditoolkit.midi.parser", MidiFile=object)
+    mod("miditoolkit.midi.containers", Marker=object, TimeSignature=object, TempoChange=object,
+        Instrument=object, Note=object)
+    mod("parmap")
+    mod("pretty_midi")
+    mod("splitfolders")
+
+
+def ref_cfg(n_layer, n_head, d_model, d_inner, tgt_len, mem_len, same_length, clamp_len):
+    return SimpleNamespace(
+        MODEL=SimpleNamespace(num_layers=n_layer, num_heads=n_head, units=d_model,
+                              inner_size=d_inner, dropout=0.0, attention_dropout=0.0,
+                              same_length=same_length, clamp_len=clamp_len),
+        TRAIN=SimpleNamespace(tgt_length=tgt_len, mem_length=mem_len))
+
+
+class Vocab:
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+
+def build_ref_model(cfgd, n_token, seed, std):
+    """Reference model + the init recipe of train.py:291-342 (restated; train.py itself is not
+    importable because it initialises NCCL at import)."""
+    from commu.model.model import MemTransformerLM
+    torch.manual_seed(seed)
+    model = MemTransformerLM(ref_cfg(**cfgd), Vocab(n_token))
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith("layer_norm.weight"):
+                p.normal_(1.0, std)
+            elif name.endswith(".bias") and p.dim() == 1:
+                p.zero_()
+            else:
+                p.normal_(0.0, std)
+    return model
+
+
+def state_np(model):
+    return {"param/" + k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()
+            if k != "crit.out_layers.0.weight"}
+
+
+def gen_forward_case(name, cfgd, n_token, B, n_seg, seed, std, reset_plan):
+    model = build_ref_model(cfgd, n_token, seed, std)
+    model.eval()
+    rng = np.random.RandomState(seed)
+    T = cfgd["tgt_len"]
+    out = dict(state_np(model))
+    out["cfg"] = np.array([cfgd["n_layer"], cfgd["n_head"], cfgd["d_model"], cfgd["d_inner"],
+                           cfgd["tgt_len"], cfgd["mem_len"], int(cfgd["same_length"]),
+                           cfgd["clamp_len"], n_token], dtype=np.int64)
+    mems = None
+    model.zero_grad()
+    for s in range(n_seg):
+        data = torch.from_numpy(rng.randint(1, n_token, size=(T, B))).long()
+        target = torch.from_numpy(rng.randint(0, n_token, size=(T, B))).long()
+        reset = torch.tensor(reset_plan[s], dtype=torch.bool) if reset_plan else None
+        loss, mems = model(data, target, reset, mems)
+        (loss.mean()).backward()
+        out["seg%d/data" % s] = data.numpy()
+        out["seg%d/target" % s] = target.numpy()
+        out["seg%d/reset" % s] = (reset.numpy() if reset is not None else np.zeros(B, bool))
+        out["seg%d/loss" % s] = loss.detach().numpy()
+        out["seg%d/mems" % s] = mems.detach().numpy()
+    for k, p in model.named_parameters():
+        if k == "crit.out_layers.0.weight":
+            continue
+        out["grad/" + k] = p.grad.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "M_final", mems.shape[1])
+
+
+def gen_decode_case(name, cfgd, n_token, B, n_ctx, n_new, seed, std):
+    model = build_ref_model(cfgd, n_token, seed, std)
+    model.eval()
+    model.reset_length(1, cfgd["mem_len"])
+    rng = np.random.RandomState(seed + 1)
+    out = dict(state_np(model))
+    out["cfg"] = np.array([cfgd["n_layer"], cfgd["n_head"], cfgd["d_model"], cfgd["d_inner"],
+                           1, cfgd["mem_len"], int(cfgd["same_length"]), cfgd["clamp_len"],
+                           n_token], dtype=np.int64)
+    ctx = torch.from_numpy(rng.randint(1, n_token, size=(n_ctx, B))).long()
+    toks, logits_all = [], []
+    with torch.no_grad():
+        _, mems = model.forward_generate(ctx[:-1], None)          # context prefill (multi-token)
+        cur = ctx[-1:]
+        for _ in range(n_new):
+            lg, mems = model.forward_generate(cur, mems)
+            nxt = 1 + lg[-1, :, 1:].argmax(dim=-1)               # greedy, token 0 never sampled
+            toks.append(nxt.numpy())
+            logits_all.append(lg[-1].numpy())
+            cur = nxt[None, :]
+    out["ctx"] = ctx.numpy()
+    out["tokens"] = np.stack(toks)              # [n_new, B]
+    out["logits"] = np.stack(logits_all)        # [n_new, B, V]
+    out["final_mems"] = mems.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    srt = np.sort(out["logits"][:, :, 1:], axis=-1)
+    print("wrote", name, "min greedy margin", float((srt[..., -1] - srt[..., -2]).min()))
+
+
+def gen_sampler_case(name, seed):
+    _stub_modules()
+    from commu.midi_generator.midi_inferrer import InferenceTask
+    rng = np.random.RandomState(seed)
+    out = {}
+    for ci, (temp, top_k, wrong) in enumerate([(0.95, 32, []), (0.95, 32, [5, 300]), (1.3, 8, [17]),
+                                               (0.0, 32, [])]):
+        task = InferenceTask(torch.device("cpu"))
+        task.input_data = SimpleNamespace(temperature=temp, top_k=top_k)
+        full = torch.from_numpy((rng.randn(729) * 3.0).astype(np.float32))
+        logits = full[1:].clone()                 # what calc_logits_and_mems returns (:206)
+        probs = task.calc_probs(logits)
+        probs = task.apply_sampling(probs, wrong)
+        out["case%d/logits_full" % ci] = full.numpy()
+        out["case%d/params" % ci] = np.array([temp, top_k], dtype=np.float64)
+        out["case%d/wrong" % ci] = np.array(wrong, dtype=np.int64)
+        out["case%d/probs" % ci] = probs.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
+def gen_train_case(name, cfgd, n_token, B, chunks, n_steps, seed, std, lr, warmup, lr_min=1e-4):
+    """Restates train.py:133-169 + 441-461 around the reference model with torch.optim.Adam."""
+    model = build_ref_model(cfgd, n_token, seed, std)
+    model.train()
+    rng = np.random.RandomState(seed + 7)
+    T = cfgd["tgt_len"]
+    out = dict(state_np(model))
+    out["cfg"] = np.array([cfgd["n_layer"], cfgd["n_head"], cfgd["d_model"], cfgd["d_inner"],
+                           cfgd["tgt_len"], cfgd["mem_len"], int(cfgd["same_length"]),
+                           cfgd["clamp_len"], n_token], dtype=np.int64)
+    out["hyper"] = np.array([lr, warmup, lr_min, 1.0, chunks], dtype=np.float64)
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=0.0)
+
+    def lam(step):
+        if step == 0 and warmup == 0:
+            return 1.0
+        return max((warmup ** 0.5) / (step ** 0.5), lr_min / lr) if step > warmup else step / warmup
+
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lam)
+    mems = [None] * chunks
+    losses, gnorms, lrs = [], [], []
+    for step in range(n_steps):
+        data = torch.from_numpy(rng.randint(1, n_token, size=(T, B))).long()
+        target = torch.from_numpy(rng.randint(0, n_token, size=(T, B))).long()
+        reset = torch.from_numpy(rng.rand(B) < 0.2)
+        out["step%d/data" % step] = data.numpy()
+        out["step%d/target" % step] = target.numpy()
+        out["step%d/reset" % step] = reset.numpy()
+        model.zero_grad()
+        tot = 0.0
+        dc, tc, rc = torch.chunk(data, chunks, 1), torch.chunk(target, chunks, 1), torch.chunk(reset, chunks, 0)
+        for i in range(chunks):
+            loss, mems[i] = model(dc[i].contiguous(), tc[i].contiguous(), rc[i].contiguous(), mems[i])
+            loss = loss[tc[i] != 0].float().mean() / chunks
+            tot += loss.item()
+            loss.backward()
+        gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        opt.zero_grad()
+        sched.step()
+        losses.append(tot)
+        gnorms.append(float(gn))
+    out["losses"] = np.array(losses)
+    out["gnorms"] = np.array(gnorms)
+    out["lrs"] = np.array(lrs)
+    for k, v in model.state_dict().items():
+        if k != "crit.out_layers.0.weight":
+            out["final/" + k] = v.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name, "losses", losses)
+
+
+def main():
+    sys.path.insert(0, REF)
+    torch.set_num_threads(4)
+    cfgA = dict(n_layer=2, n_head=4, d_model=64, d_inner=128, tgt_len=12, mem_len=16,
+                same_length=False, clamp_len=-1)
+    gen_forward_case("fwd_basic", cfgA, n_token=729, B=3, n_seg=3, seed=11, std=0.05,
+                     reset_plan=[[0, 0, 0], [0, 1, 0], [1, 0, 0]])
+    cfgB = dict(n_layer=2, n_head=6, d_model=60, d_inner=100, tgt_len=8, mem_len=24,
+                same_length=True, clamp_len=20)
+    gen_forward_case("fwd_samelen_dh10", cfgB, n_token=53, B=2, n_seg=5, seed=12, std=0.08,
+                     reset_plan=[[0, 0], [0, 0], [1, 0], [0, 0], [0, 1]])
+    cfgC = dict(n_layer=3, n_head=4, d_model=64, d_inner=128, tgt_len=1, mem_len=20,
+                same_length=True, clamp_len=-1)
+    gen_decode_case("decode_greedy", cfgC, n_token=97, B=2, n_ctx=6, n_new=40, seed=13, std=0.2)
+    gen_sampler_case("sampler_probs", seed=14)
+    cfgE = dict(n_layer=2, n_head=2, d_model=32, d_inner=64, tgt_len=10, mem_len=10,
+                same_length=False, clamp_len=-1)
+    gen_train_case("train_steps", cfgE, n_token=61, B=4, chunks=2, n_steps=6, seed=15, std=0.05,
+                   lr=0.004, warmup=3)
+
+
+if __name__ == "__main__":
+    main()
