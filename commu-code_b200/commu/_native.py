@@ -103,3 +103,59 @@ def gemm(a, b, *, m, n, k, lda=None, ldb=None, a_mn=False, b_mn=False, split_k=1
     args.f32_atomic = int(f32_atomic)
     args.impl = impl
     check(lib().commu_gemm_bf16(ctypes.byref(args), stream_ptr()))
+
+
+# ------------------------------------------------------------------------------------------------
+# Typed signatures of the remaining entry points (kept in one table so a CPU test can verify that
+# every symbol declared in include/commu_b200.h is exported and bound).
+# ------------------------------------------------------------------------------------------------
+P, I, L, F, U = c_void_p, c_int, c_int64, c_float, ctypes.c_uint
+SIGNATURES = {
+    "commu_abi_version": [],
+    "commu_device_info": [P, P, P],
+    "commu_prof_arm": [U],
+    "commu_prof_read": [I, P, P],
+    "commu_gemm_bf16": [P, P],
+    "commu_embed_fwd": [P, P, I, I, F, L, P, L, P, L, P],
+    "commu_embed_bwd": [P, P, L, I, F, L, P, P],
+    "commu_pos_table": [P, I, I, I, I, P, P, P],
+    "commu_layernorm_fwd": [P, L, P, P, I, I, F, L, P, L, P, L, P, P, P],
+    "commu_layernorm_bwd": [P, L, P, L, P, P, P, I, I, L, P, L, P, L, P, P, P],
+    "commu_nll_fwd": [P, L, I, P, L, P, P, P],
+    "commu_nll_bwd": [P, L, I, I, P, P, P, L, P, L, P],
+    "commu_colsum_bf16": [P, L, I, L, P, P],
+    "commu_cast_pad": [P, L, I, I, I, I, I, I, P, L, I, P],
+    "commu_unpad_accum": [P, L, I, I, I, I, I, I, P, L, F, P],
+    "commu_sumsq": [P, L, P, P],
+    "commu_clip_adam": [P, P, P, P, L, F, F, F, F, I, P, F, F, P, P],
+    "commu_relattn_fwd": [P, L, P, P, L, P, L, I, P, P, P, I, I, I, I, I, I, F, P, L, P, P, P, P],
+    "commu_relattn_bwd": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, L, P, P, L, P, P, L,
+                          P, P, L, P, P, P, P],
+}
+_bound = set()
+
+
+def _as_arg(x):
+    if x is None:
+        return None
+    if hasattr(x, "data_ptr"):
+        return c_void_p(x.data_ptr())
+    return x
+
+
+def call(name, *args):
+    """Calls an entry point with torch tensors converted to device pointers; the last argument
+    (the stream) is appended automatically for every function that takes one."""
+    L_ = lib()
+    fn = getattr(L_, name)
+    sig = SIGNATURES[name]
+    if name not in _bound:
+        fn.argtypes = sig
+        fn.restype = c_int
+        _bound.add(name)
+    conv = [_as_arg(a) for a in args]
+    if len(conv) == len(sig) - 1:
+        conv.append(stream_ptr())
+    if len(conv) != len(sig):
+        raise TypeError("%s expects %d arguments, got %d" % (name, len(sig), len(conv)))
+    check(fn(*conv))

@@ -25,7 +25,9 @@ constexpr int WBAND = 80; // band rows a warp multiplies (>= 16 + BN - 1, multip
 constexpr int SW = 88;    // scratch row stride in floats (bank-spread, even)
 
 struct Params {
-  const bf16* q;    // [T*B, ldq]   (+ h*64)
+  const bf16* q;    // [T*B, ldq]   (+ h*64)   raw projected queries (forward only)
+  bf16* qu_s;       // [T*B, ldq]   bf16(q + r_w_bias): written by forward, read by backward
+  bf16* qv_s;       // [T*B, ldq]   bf16(q + r_r_bias)
   const bf16* k;    // [K*B, ldkv]
   const bf16* v;    // [K*B, ldkv]
   const bf16* r;    // [Kr, ldr]     by distance

@@ -48,6 +48,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) relattn_fwd_kernel(const Params p
       }
       *reinterpret_cast<uint4*>(sm.k[0] + swz(row, ch)) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
       *reinterpret_cast<uint4*>(sm.v[0] + swz(row, ch)) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+      if (p.qu_s && i < p.T) {  // saved for the backward passes
+        const long long off = (long long)b * p.ldq + h * DH + ((long long)i * p.B) * p.ldq + ch * 8;
+        *reinterpret_cast<uint4*>(p.qu_s + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        *reinterpret_cast<uint4*>(p.qv_s + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+      }
     }
   }
   __syncthreads();
@@ -277,8 +282,10 @@ extern "C" int commu_relattn_fwd(const void* q, int64_t ldq, const void* k, cons
                                  const void* r, int64_t ldr, int kr, const float* r_w_bias,
                                  const float* r_r_bias, const unsigned char* reset, int T, int M, int B,
                                  int H, int same_length, int shift, float scale, void* out, int64_t ldo,
-                                 float* lse, void* stream) {
+                                 float* lse, void* qu_save, void* qv_save, void* stream) {
   attn::Params p = {};
+  p.qu_s = (bf16*)qu_save; p.qv_s = (bf16*)qv_save;
+  CB_REQUIRE((qu_save == nullptr) == (qv_save == nullptr), "relattn_fwd: qu_save/qv_save must both be set or null");
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.r = (const bf16*)r;
   p.u = r_w_bias; p.vb = r_r_bias; p.reset = reset;
   p.ldq = ldq; p.ldkv = ldkv; p.ldr = ldr;
