@@ -115,6 +115,10 @@ SIGNATURES = {
     "commu_device_info": [P, P, P],
     "commu_prof_arm": [U],
     "commu_prof_read": [I, P, P],
+    "commu_comm_unique_id": [P, P],
+    "commu_comm_init": [P, P, I, I],
+    "commu_allreduce_sum_f32": [P, L, P],
+    "commu_comm_destroy": [],
     "commu_gemm_bf16": [P, P],
     "commu_embed_fwd": [P, P, I, I, F, L, P, L, P, L, P],
     "commu_embed_bwd": [P, P, L, I, F, L, P, P],

@@ -102,6 +102,7 @@ class NativeLM:
         S["lbias"] = torch.zeros(self.vp, device=dev)
         return S
 
+    @torch.no_grad()
     def refresh_shadow(self):
         """fp32 masters -> bf16 operand shadows (padded).  Call after every optimizer step."""
         if self._shadow is None:
@@ -151,6 +152,7 @@ class NativeLM:
         return t
 
     # ------------------------------------------------------------------ forward --------------------
+    @torch.no_grad()
     def hidden_forward(self, data, reset, mems, mem_len, same_length, clamp_len, save):
         """Runs embedding + L layers.  Returns (xL_f32 [T*B, dp], xL_bf16, new_mems, ctx)."""
         T, B = data.shape
@@ -238,6 +240,7 @@ class NativeLM:
                        reset_u8=reset_u8, pos=pos, tok=tok, cats=cats, layers=layers_ctx)
         return x, cats[self.L][M * B:], new_mems, ctx
 
+    @torch.no_grad()
     def forward_loss(self, data, target, reset, mems, mem_len, same_length, clamp_len, save=True):
         T, B = data.shape
         rows = T * B
@@ -254,6 +257,7 @@ class NativeLM:
             self.saved = ctx
         return nll.view(T, B), new_mems
 
+    @torch.no_grad()
     def forward_logits(self, data, mems, mem_len, same_length, clamp_len):
         T, B = data.shape
         rows = T * B
@@ -285,6 +289,7 @@ class NativeLM:
         nv.call("commu_unpad_accum", tmp, n, m_real, n_real, rseg or m_real, rseg_pad or m_real,
                 cseg or n_real, cseg_pad or n_real, grad, grad.stride(0), 1.0)
 
+    @torch.no_grad()
     def backward(self, dloss, grads):
         """dloss: fp32 [T,B] gradient of the per-token NLL.  Accumulates (+=) into `grads`
         (dict: reference parameter name -> fp32 tensor of the parameter's shape)."""

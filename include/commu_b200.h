@@ -74,6 +74,102 @@ typedef struct {
 
 int commu_gemm_bf16(const commu_gemm_args* args, void* stream);
 
+/* Per-kernel-class device timers (bench.py roofline line) and the launch counter.
+ * classes: 0 = GEMM, 1 = attention fwd, 2 = attention bwd, 3 = decode attention. */
+int commu_prof_arm(unsigned class_mask);
+int commu_prof_read(int cls, float* total_ms, int* launches);
+long long commu_launch_count(int reset);
+
+/* ------------------------------------------------------------------------------------------
+ * Embedding  x = E[tok] * scale   (AdaptiveEmbedding.forward, commu/model/model.py:409-420) and its
+ * backward (scatter-add into the 729-row table, tied with the logits weight, model.py:480-481).
+ * Outputs are [n, ld] with columns d..dp-1 zeroed.
+ * ------------------------------------------------------------------------------------------ */
+int commu_embed_fwd(const int64_t* tokens, const float* table, int d, int dp, float scale, int64_t n,
+                    float* out_f32, int64_t ld_f32, void* out_bf16, int64_t ld_bf16, void* stream);
+int commu_embed_bwd(const int64_t* tokens, const float* dx, int64_t ld, int d, float scale, int64_t n,
+                    float* dtable, void* stream);
+
+/* Sinusoid table by DISTANCE: row delta = [sin(min(delta,clamp) f) | cos(...)]
+ * (PositionalEmbedding.forward model.py:145-152 with pos_seq of :578-583; row delta of this table is
+ * row klen-1-delta of the reference's pos_emb). */
+int commu_pos_table(const float* inv_freq, int klen, int clamp_len, int d, int dp, void* out_bf16,
+                    float* out_f32, void* stream);
+
+/* LayerNorm over the d real columns (eps as given; reference uses nn.LayerNorm default 1e-5,
+ * model.py:214, :171, applied at :352 and :179).  z already contains residual + sub-block output. */
+int commu_layernorm_fwd(const float* z, int64_t ldz, const float* gamma, const float* beta, int d, int dp,
+                        float eps, int64_t rows, float* y_f32, int64_t ldy, void* y_bf16, int64_t ldyb,
+                        float* mean, float* rstd, void* stream);
+int commu_layernorm_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* mean,
+                        const float* rstd, const float* gamma, int d, int dp, int64_t rows, float* dz_f32,
+                        int64_t lddz, void* dz_bf16, int64_t lddzb, float* dgamma, float* dbeta,
+                        void* stream);
+
+/* Per-token NLL = -log_softmax(logits)[target] (ProjectedAdaptiveLogSoftmax.forward, n_clusters == 0
+ * branch, model.py:64-73) and its backward dlogits = (softmax - onehot) * dloss (bf16, Vp columns). */
+int commu_nll_fwd(const float* logits, int64_t ld, int V, const int64_t* target, int64_t rows, float* nll,
+                  float* lse, void* stream);
+int commu_nll_bwd(const float* logits, int64_t ld, int V, int Vp, const float* lse, const int64_t* target,
+                  const float* dloss, int64_t rows, void* dlogits_bf16, int64_t ldd, void* stream);
+
+/* out[c] += sum_r x[r,c]  (bias gradients of CoreNet.0 / CoreNet.3 / logits bias). */
+int commu_colsum_bf16(const void* x, int64_t ld, int ncols, int64_t rows, float* out, void* stream);
+
+/* fp32 master weight [R,C] -> bf16 operand shadow with segment padding
+ * (dst row = (r / rseg) * rseg_pad + r % rseg, same for columns), optional transpose; and the inverse
+ * accumulation of a padded fp32 gradient into the reference-layout gradient. */
+int commu_cast_pad(const float* src, int64_t ld_src, int R, int C, int rseg, int rseg_pad, int cseg,
+                   int cseg_pad, void* dst_bf16, int64_t ld_dst, int transpose, void* stream);
+int commu_unpad_accum(const float* src, int64_t ld_src, int R, int C, int rseg, int rseg_pad, int cseg,
+                      int cseg_pad, float* dst, int64_t ld_dst, float scale, void* stream);
+
+/* Optimizer tail (train.py:159-169): out_accum += sum(g^2); then
+ * g' = g * grad_scale * min(1, clip / (||g * grad_scale|| + 1e-6)) (clip_grad_norm_) followed by Adam
+ * (torch.optim.Adam: no amsgrad, weight_decay 0) on flat fp32 arenas.  step >= 1. */
+int commu_sumsq(const float* g, int64_t n, float* out_accum, void* stream);
+int commu_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                    float beta2, float eps, int step, const float* gnorm_sq, float clip, float grad_scale,
+                    float* gnorm_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused relative-position attention (RelPartialLearnableMultiHeadAttn.forward, model.py:312-345,
+ * with _rel_shift :251-265 and the mask of :549-574 folded in analytically).
+ *   q   : bf16 [T*B, ldq]   row = i*B + b, head h at columns h*64 .. h*64+63 (head dim padded to 64)
+ *   k, v: bf16 [K*B, ldkv]  K = T + M
+ *   r   : bf16 [kr, ldr]    projected sinusoid table indexed by distance, kr >= K
+ *   r_w_bias, r_r_bias: fp32 [H, 64]
+ *   reset: uint8 [B] or NULL (1 = this column restarted: memory keys j < M are masked)
+ *   valid(i,j) = j <= i + M  &&  (!same_length || j > i - shift)  &&  (!reset[b] || j >= M)
+ *   out : bf16 [T*B, ldo];  lse: fp32 [B,H,T] = log sum_j exp(scale * score)
+ *   qu_save / qv_save (both or neither): bf16 [T*B, ldq] receive bf16(q + r_w_bias), bf16(q + r_r_bias)
+ *   for the backward.
+ * ------------------------------------------------------------------------------------------ */
+int commu_relattn_fwd(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                      const void* r, int64_t ldr, int kr, const float* r_w_bias, const float* r_r_bias,
+                      const unsigned char* reset, int T, int M, int B, int H, int same_length, int shift,
+                      float scale, void* out, int64_t ldo, float* lse, void* qu_save, void* qv_save,
+                      void* stream);
+/* Backward of the above (the reference uses torch autograd).  dq: bf16 [T*B, lddq]; dk, dv: bf16
+ * [K*B, lddkv] (every key row written); dr: fp32 [kr, H*64] and du, dvb: fp32 [H,64] are accumulated
+ * (+=, caller zeroes); delta_ws: fp32 [B,H,T] workspace. */
+int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
+                      int64_t ldkv, const void* r, int64_t ldr, int kr, const unsigned char* reset, int T,
+                      int M, int B, int H, int same_length, int shift, float scale, const void* out,
+                      int64_t ldo, const float* lse, const void* dout, int64_t lddo, float* delta_ws,
+                      void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, float* dr, float* du,
+                      float* dvb, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange: one NCCL sum all-reduce of the flat fp32 gradient arena per
+ * optimizer step (replaces the per-micro-batch DDP bucket all-reduce, train.py:155, 467-473).
+ * NCCL is dlopen'ed (nccl_path may be NULL/"" to use the default soname).
+ * ------------------------------------------------------------------------------------------ */
+int commu_comm_unique_id(const char* nccl_path, void* id_out_128_bytes);
+int commu_comm_init(const char* nccl_path, const void* id_128_bytes, int rank, int world);
+int commu_allreduce_sum_f32(float* buf, int64_t n, void* stream);
+int commu_comm_destroy(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -215,6 +215,46 @@ def gen_train_case(name, cfgd, n_token, B, chunks, n_steps, seed, std, lr, warmu
     print("wrote", name, "losses", losses)
 
 
+def gen_dataset_case(name, seed):
+    """Batches produced by the reference ComMUDataset on a synthetic corpus (file format of
+    SURVEY.md 8d, written by the new repo's writer; the corpus itself is stored in the fixture)."""
+    import tempfile
+    _stub_modules()
+    from commu.model.dataset import ComMUDataset
+    rng = np.random.RandomState(seed)
+    d = tempfile.mkdtemp()
+    out = {}
+    for tag, n in (("train", 23), ("val", 7)):
+        inp = np.empty(n, dtype=object)
+        tgt = np.empty(n, dtype=object)
+        for i in range(n):
+            ln = int(rng.randint(20, 90))
+            inp[i] = rng.randint(560, 729, size=11).astype(np.int64)
+            ev = rng.randint(2, 560, size=ln).astype(np.int16)
+            ev[-1] = 1
+            tgt[i] = ev
+            out["corpus/%s/%d/input" % (tag, i)] = inp[i]
+            out["corpus/%s/%d/target" % (tag, i)] = tgt[i]
+        np.save(os.path.join(d, "input_%s.npy" % tag), inp, allow_pickle=True)
+        np.save(os.path.join(d, "target_%s.npy" % tag), tgt, allow_pickle=True)
+    ds = ComMUDataset(d, None)
+    it = ds.get_iterator(5, 16, "cpu", "train", True, seed=1111)()
+    for b in range(40):                      # > one epoch (23 samples x ~55 tokens / (5 x 16))
+        data, target, reset, ntok = next(it)
+        out["train/%d/data" % b] = data.numpy().copy()
+        out["train/%d/target" % b] = target.numpy().copy()
+        out["train/%d/reset" % b] = reset.numpy().copy()
+        out["train/%d/ntok" % b] = np.array(ntok)
+    for rank in range(2):
+        for b, (data, target, first, ntok) in enumerate(ds.eval_iterator(3, 16, "cpu", "valid", rank, 2)()):
+            out["eval%d/%d/data" % (rank, b)] = data.numpy().copy()
+            out["eval%d/%d/target" % (rank, b)] = target.numpy().copy()
+            out["eval%d/%d/first" % (rank, b)] = np.array(first)
+            out["eval%d/%d/ntok" % (rank, b)] = np.array(ntok)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def main():
     sys.path.insert(0, REF)
     torch.set_num_threads(4)
@@ -230,6 +270,7 @@ def main():
                 same_length=True, clamp_len=-1)
     gen_decode_case("decode_greedy", cfgC, n_token=97, B=2, n_ctx=6, n_new=40, seed=13, std=0.2)
     gen_sampler_case("sampler_probs", seed=14)
+    gen_dataset_case("dataset_batches", seed=16)
     cfgE = dict(n_layer=2, n_head=2, d_model=32, d_inner=64, tgt_len=10, mem_len=10,
                 same_length=False, clamp_len=-1)
     gen_train_case("train_steps", cfgE, n_token=61, B=4, chunks=2, n_steps=6, seed=15, std=0.05,

@@ -1,0 +1,133 @@
+"""End-to-end GPU parity of the drop-in MemTransformerLM / Trainer against (a) the golden fixtures
+generated from the reference and (b) the pinned oracle, through the public Python surface (which
+calls the C-ABI).  Tolerances: the product computes with bf16 operands / fp32 accumulation, the
+reference in fp32; north_star asks for training loss within 1e-3 relative."""
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_golden, orc, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+class _Vocab:
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+
+def build_model(cfg, params):
+    from commu.model.model import MemTransformerLM
+    c = NS(MODEL=NS(num_layers=cfg.n_layer, num_heads=cfg.n_head, units=cfg.d_model, inner_size=cfg.d_inner,
+                    dropout=0.0, attention_dropout=0.0, same_length=cfg.same_length, clamp_len=cfg.clamp_len),
+           TRAIN=NS(tgt_length=cfg.tgt_len, mem_length=cfg.mem_len))
+    m = MemTransformerLM(c, _Vocab(cfg.n_token))
+    sd = {k: v.clone() for k, v in params.items()}
+    sd["crit.out_layers.0.weight"] = sd["word_emb.emb_layers.0.weight"]
+    sd["pos_emb.inv_freq"] = m.pos_emb.inv_freq.clone()
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+def _segments_vs_golden(name, loss_tol, grad_tol):
+    z, cfg, P = load_golden(name)
+    model = build_model(cfg, P)
+    model.train()
+    mems = None
+    nseg = len([k for k in z.files if k.endswith("/loss")])
+    for s in range(nseg):
+        data = torch.from_numpy(z["seg%d/data" % s]).cuda()
+        target = torch.from_numpy(z["seg%d/target" % s]).cuda()
+        reset = torch.from_numpy(z["seg%d/reset" % s]).cuda()
+        loss, mems = model(data, target, reset, mems)
+        loss.mean().backward()
+        ref = torch.from_numpy(z["seg%d/loss" % s])
+        assert (loss.detach().cpu() - ref).abs().max() < 0.05, (name, s)
+        assert abs(float(loss.mean()) - float(ref.mean())) / float(ref.mean()) < loss_tol, (name, s)
+        rm = torch.from_numpy(z["seg%d/mems" % s])
+        assert tuple(mems.shape) == tuple(rm.shape)
+        assert (mems.float().cpu() - rm).abs().max() < 0.05 * rm.abs().max() + 0.02, (name, s)
+    worst = 0.0
+    for k, p in model.named_parameters():
+        if k == "crit.out_layers.0.weight":
+            continue
+        e = rel_err(p.grad.cpu(), z["grad/" + k])
+        worst = max(worst, e)
+        assert e < grad_tol, (name, k, e)
+    return worst
+
+
+def test_fwd_bwd_golden_basic():
+    _segments_vs_golden("fwd_basic", 1e-3, 0.05)
+
+
+def test_fwd_bwd_golden_samelen_clamp_dh10():
+    _segments_vs_golden("fwd_samelen_dh10", 1e-3, 0.05)
+
+
+def test_aligned_shapes_vs_oracle():
+    """Dh = 64, d % 64 == 0: the direct (no un-padding) gradient path; 3 segments with memory."""
+    cfg = orc.make_cfg(n_layer=2, n_head=2, d_model=128, d_inner=256, tgt_len=96, mem_len=128,
+                       same_length=False, clamp_len=-1, n_token=729)
+    P = orc.init_params(cfg, seed=5, std=0.05)
+    model = build_model(cfg, P)
+    Pl = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    g = torch.Generator().manual_seed(9)
+    mems_o, mems_n = None, None
+    for s in range(3):
+        data = torch.randint(1, 729, (96, 3), generator=g)
+        target = torch.randint(0, 729, (96, 3), generator=g)
+        reset = torch.tensor([False, s == 1, False])
+        lo, mems_o = orc.forward_loss(cfg, Pl, data, target, reset, mems_o)
+        lo.mean().backward()
+        ln, mems_n = model(data.cuda(), target.cuda(), reset.cuda(), mems_n)
+        ln.mean().backward()
+        assert abs(float(ln.mean()) - float(lo.mean())) / float(lo.mean()) < 1e-3
+        assert (ln.detach().cpu() - lo.detach()).abs().max() < 0.05
+    for k, p in model.named_parameters():
+        if k == "crit.out_layers.0.weight":
+            continue
+        assert rel_err(p.grad.cpu(), Pl[k].grad) < 0.05, k
+
+
+def test_train_steps_golden():
+    from commu.engine.trainer import Trainer
+    z, cfg, P = load_golden("train_steps")
+    lr, warmup, lr_min, clip, chunks = z["hyper"]
+    model = build_model(cfg, P)
+    tr = Trainer(model, lr=float(lr), warmup_step=int(warmup), lr_min=float(lr_min), clip=float(clip),
+                 batch_chunk=int(chunks))
+    for s in range(len(z["losses"])):
+        data = torch.from_numpy(z["step%d/data" % s]).cuda()
+        target = torch.from_numpy(z["step%d/target" % s]).cuda()
+        reset = torch.from_numpy(z["step%d/reset" % s]).cuda()
+        assert abs(tr.current_lr() - z["lrs"][s]) < 1e-12
+        loss, gn = tr.train_step(data, target, reset)
+        assert abs(float(loss) - z["losses"][s]) / z["losses"][s] < 1e-3, (s, float(loss), z["losses"][s])
+        assert abs(float(gn) - z["gnorms"][s]) / z["gnorms"][s] < 0.03, (s, float(gn), z["gnorms"][s])
+    sd = model.state_dict()
+    for k in P:
+        assert rel_err(sd[k].cpu(), z["final/" + k]) < 0.05, k
+
+
+def test_forward_generate_vs_golden_logits():
+    z, cfg, P = load_golden("decode_greedy")
+    model = build_model(cfg, P)
+    model.eval()
+    model.reset_length(1, cfg.mem_len)
+    ctx = torch.from_numpy(z["ctx"]).cuda()
+    _, mems = model.forward_generate(ctx[:-1], None)
+    cur = ctx[-1:]
+    n_ok = 0
+    for t in range(z["tokens"].shape[0]):
+        lg, mems = model.forward_generate(cur, mems)
+        ref = torch.from_numpy(z["logits"][t])
+        assert (lg[-1].cpu() - ref).abs().max() < 0.05 * ref.abs().max() + 0.02
+        cur = torch.from_numpy(z["tokens"][t])[None].cuda()     # teacher-force the reference tokens
+        n_ok += 1
+    assert n_ok == z["tokens"].shape[0]
