@@ -1,0 +1,325 @@
+"""Benchmark of the ComMU Transformer-XL training hot path (BASELINE.json configs[1]:
+12-layer d512 n_head=8 d_inner=2048, seq_len = mem_len = 2048, vocab 729, synthetic tokens).
+
+    python bench.py --gpus N --steps K --warmup W [--impl native|reference]
+
+One JSON line on stdout (rank 0).  A "step" is one optimizer step (micro-batch forward, backward,
+gradient all-reduce for N>1, clip, Adam) over B_PER_GPU synthetic sequences of 2048 tokens per GPU
+with the recurrent memory full (2048).  `value` = trained tokens/s of the whole job with inputs
+resident in HBM; `e2e` = the same through Trainer.train_step with host (pinned) inputs copied in and
+the loss read back every step.  `--impl reference` times the CPU port of the reference algorithm
+(oracle/, "kind": "port") on the host cores.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "commu-code_b200"))
+
+import torch  # noqa: E402
+
+CFG = dict(n_layer=12, n_head=8, d_model=512, d_inner=2048, tgt_len=2048, mem_len=2048, n_token=729)
+B_PER_GPU = int(os.environ.get("COMMU_BENCH_BATCH", "16"))
+METRIC = "train tokens/sec @12L d512 seq2048 mem2048"
+
+
+def algorithmic_flops_per_token(L, d, Di, T, M, B, V):
+    """minimal-algorithm FLOPs per trained token (causal-visible keys)."""
+    K = T + M
+    macs_fwd_layer = d * d + 2 * d * d * K / T + d * d * K / (T * B) + 3 * d * (M + (T + 1) / 2) + d * d + 2 * d * Di
+    f_fwd = 2 * (L * macs_fwd_layer + d * V)
+    f_train = 3 * f_fwd - 2 * L * 2 * d * d * M / T
+    attn_fwd_flops_per_bh = 2 * 3 * (d // 8) * (T * M + T * (T + 1) / 2)   # per (b, h): AC + BD + AV
+    return f_fwd, f_train, attn_fwd_flops_per_bh
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(bf16=j.get("bf16_tflops_sustained", j.get("bf16_tflops")), bf16_burst=j.get("bf16_tflops"),
+                    hbm=j.get("hbm_gbs"), source="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx or None, samples=len(sm),
+                    reasons=sorted(reasons))
+
+    def stop(self):
+        if self.proc:
+            self.proc.kill()
+
+
+def synthetic_tokens(T, B, n, gen):
+    """Full columns: event tokens uniform in [2,559]; no pad, reset rarely true."""
+    data = torch.randint(2, 560, (n, T + 1, B), generator=gen, dtype=torch.int64)
+    return data[:, :-1].contiguous(), data[:, 1:].contiguous()
+
+
+def run_native(args):
+    import torch.distributed as dist
+    from types import SimpleNamespace as NS
+    from commu import _native as nv
+    from commu.engine.trainer import GradComm, Trainer
+    from commu.model.model import MemTransformerLM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torch.distributed.run" % args.gpus)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    comm = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        comm = GradComm(rank, world, dev)
+
+    class Vocab:
+        def __len__(self):
+            return CFG["n_token"]
+
+    cfg = NS(MODEL=NS(num_layers=CFG["n_layer"], num_heads=CFG["n_head"], units=CFG["d_model"],
+                      inner_size=CFG["d_inner"], dropout=0.0, attention_dropout=0.0, same_length=False,
+                      clamp_len=-1),
+             TRAIN=NS(tgt_length=CFG["tgt_len"], mem_length=CFG["mem_len"]))
+    torch.manual_seed(1111)
+    model = MemTransformerLM(cfg, Vocab())
+    with torch.no_grad():      # init recipe of train.py:291-342
+        for n, p in model.named_parameters():
+            if n.endswith("layer_norm.weight"):
+                p.normal_(1.0, 0.01)
+            elif n.endswith(".bias") and p.dim() == 1:
+                p.zero_()
+            else:
+                p.normal_(0.0, 0.01)
+    model = model.to(dev)
+    model.train()
+    tr = Trainer(model, lr=0.004 / world, warmup_step=100, lr_min=1e-4, clip=1.0, batch_chunk=1, world=world,
+                 comm=comm)
+    T, B = CFG["tgt_len"], B_PER_GPU
+    K, W = args.steps, args.warmup
+    gen = torch.Generator().manual_seed(1111 + 1000 * rank)
+    n_batches = 4
+    hd, ht = synthetic_tokens(T, B, n_batches, gen)
+    hd, ht = hd.pin_memory(), ht.pin_memory()
+    dd, dt = hd.to(dev), ht.to(dev)
+    reset_h = torch.zeros(B, dtype=torch.bool).pin_memory()
+    reset_d = reset_h.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- warm-up (fills the recurrent memory, compiles nothing: all kernels are prebuilt) ----
+    for s in range(W):
+        tr.train_step(dd[s % n_batches], dt[s % n_batches], reset_d)
+    barrier()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    lib = nv.lib()
+    # ---- device-resident arm ----
+    lib.commu_prof_arm(0b0111)
+    lib.commu_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    e0.record()
+    for s in range(K):
+        loss, _ = tr.train_step(dd[s % n_batches], dt[s % n_batches], reset_d)
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    launches = int(lib.commu_launch_count(1))
+    import ctypes
+    prof = {}
+    for cls, name in ((0, "gemm"), (1, "attn_fwd"), (2, "attn_bwd")):
+        ms, n = ctypes.c_float(0), ctypes.c_int(0)
+        nv.check(lib.commu_prof_read(cls, ctypes.byref(ms), ctypes.byref(n)))
+        prof[name] = dict(ms=ms.value, launches=n.value)
+    lib.commu_prof_arm(0)
+    final_loss = float(loss)
+
+    # ---- end-to-end arm: host inputs in, loss out, every step ----
+    barrier()
+    e0.record()
+    for s in range(K):
+        d_ = hd[s % n_batches].to(dev, non_blocking=True)
+        t_ = ht[s % n_batches].to(dev, non_blocking=True)
+        r_ = reset_h.to(dev, non_blocking=True)
+        loss, _ = tr.train_step(d_, t_, r_)
+        loss_host = loss.item()
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.window(t_wall0, t_wall1) if sampler else None
+    if sampler:
+        sampler.stop()
+
+    if rank == 0:
+        pk = peaks()
+        tokens_step = T * B * world
+        value = tokens_step * K / (ms_dev / 1e3)
+        e2e = tokens_step * K / (ms_e2e / 1e3)
+        f_fwd, f_train, attn_bh = algorithmic_flops_per_token(CFG["n_layer"], CFG["d_model"], CFG["d_inner"],
+                                                              T, CFG["mem_len"], B, CFG["n_token"])
+        dom = max(("attn_fwd", "attn_bwd", "gemm"), key=lambda k: prof[k]["ms"])
+        if dom == "attn_bwd":
+            fl = 2 * attn_bh * B * CFG["n_head"]
+        elif dom == "attn_fwd":
+            fl = attn_bh * B * CFG["n_head"]
+        else:
+            fl = None
+        roof = None
+        if fl is not None and prof[dom]["launches"]:
+            dur = prof[dom]["ms"] / prof[dom]["launches"] / 1e3
+            ach = fl / dur / 1e12
+            roof = dict(kernel=dom, bound="tensor", achieved=round(ach, 2), peak=pk["bf16"], unit="TFLOP/s",
+                        frac=round(ach / pk["bf16"], 4), traffic=None, peak_source=pk["source"],
+                        flops_per_launch=fl, avg_launch_ms=round(dur * 1e3, 4))
+        out = {
+            "metric": METRIC, "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": round(ms_dev / K, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1]: 12L d512 H8 Di2048 T=2048 M=2048 V=729 train step "
+                                   "(fwd+bwd+clip+Adam), dropout 0, batch_chunk 1",
+                       "global_batch": B * world, "per_gpu_batch": B, "seq_len": T, "mem_len": CFG["mem_len"],
+                       "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (activations ~%d MB/GPU) >> 126 MB L2" % int(0.64 * 12 * B / 16 * 1000)},
+            "e2e": {"value": round(e2e, 1), "unit": "tokens/s", "ms_per_step": round(ms_e2e / K, 3),
+                    "h2d_bytes_per_step": int(2 * T * B * 8 + B), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "roofline": roof,
+            "step_mfu": {"algorithmic_gflop_per_token": round(f_train / 1e9, 4),
+                         "achieved_tflops_per_gpu": round(value / world * f_train / 1e12, 1),
+                         "frac_of_bf16_peak": round(value / world * f_train / 1e12 / pk["bf16"], 4)},
+            "kernel_time_ms_per_step": {k: round(v["ms"] / K, 3) for k, v in prof.items()},
+            "clocks": clocks,
+            "final_loss": round(final_loss, 5),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(1, 1)
+        print(json.dumps(out), flush=True)
+    if comm is not None:
+        comm.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(steps, warmup):
+    """Reference algorithm on the host cores: oracle port (torch CPU fp32, all threads), bounded
+    sample = B=1 sequence of 2048 tokens per step with the memory carried over."""
+    from oracle import transfoxl_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = orc.make_cfg(CFG["n_layer"], CFG["n_head"], CFG["d_model"], CFG["d_inner"], CFG["tgt_len"],
+                       CFG["mem_len"], False, -1, CFG["n_token"])
+    P = orc.init_params(cfg, seed=1111, std=0.01)
+    opt = orc.AdamState(P)
+    gen = torch.Generator().manual_seed(7)
+    mems = [None]
+    T = CFG["tgt_len"]
+    times = []
+    for s in range(warmup + steps):
+        tok = torch.randint(2, 560, (T + 1, 1), generator=gen)
+        t0 = time.time()
+        _, _, mems, _ = orc.train_step(cfg, P, opt, [(tok[:-1], tok[1:], torch.zeros(1, dtype=torch.bool))],
+                                       mems, lr=1e-4)
+        if s >= warmup:
+            times.append(time.time() - t0)
+    tot = sum(times)
+    return {"value": round(T * len(times) / tot, 2), "unit": "tokens/s", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": "%d step(s) of B=1 x T=2048 (M=2048) fwd+bwd+clip+Adam, %.1f s" %
+                                      (len(times), tot)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    t0 = time.time()
+    cb = cpu_baseline(K, W)
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tokens/s",
+           "n_gpus": args.gpus, "steps": K, "warmup": W,
+           "ms_per_step": round(CFG["tgt_len"] / cb["value"] * 1e3, 1), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[1] on CPU (oracle port of the reference algorithm): 12L d512 "
+                                  "H8 Di2048 T=2048 M=2048, bounded sample B=1 per step", "global_batch": 1,
+                      "seq_len": CFG["tgt_len"], "parallelism": "cpu"},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0, "wall_s": round(time.time() - t0, 1)}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

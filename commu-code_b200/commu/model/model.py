@@ -73,7 +73,7 @@ class _NativeLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, data, target, reset, mems, *params):
         eng = model._engine()
-        need = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need = model._need_save   # grad mode is always off inside Function.forward; decided by the caller
         loss, new_mems = eng.forward_loss(data, target, reset, mems, model.mem_len, model.same_length,
                                           model.clamp_len, save=need)
         model._last_mems = new_mems
@@ -133,6 +133,7 @@ class MemTransformerLM(nn.Module):
         self._check_inputs(data, mems)
         self._note_dropout()
         plist = self._params()
+        self._need_save = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
         loss = _NativeLoss.apply(self, data, target, reset_mems, mems, *plist)
         new_mems, self._last_mems = self._last_mems, None
         return loss, new_mems

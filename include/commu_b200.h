@@ -170,6 +170,31 @@ int commu_comm_init(const char* nccl_path, const void* id_128_bytes, int rank, i
 int commu_allreduce_sum_f32(float* buf, int64_t n, void* stream);
 int commu_comm_destroy(void);
 
+/* ------------------------------------------------------------------------------------------
+ * Incremental decode (generate.py hot loop: InferenceTask.calc_logits_and_mems / calc_probs /
+ * apply_sampling / infer_token, commu/midi_generator/midi_inferrer.py:199-237, over
+ * MemTransformerLM.forward_generate, commu/model/model.py:606-628).
+ * ------------------------------------------------------------------------------------------ */
+/* out[b,n] = act(sum_k x[b,k] W[n,k] + bias[n]) + res[b,n], B <= 64 rows; W fp32 or bf16 [N,K]. */
+int commu_decode_linear(const float* x, int64_t ldx, const void* w, int64_t ldw, int w_bf16, const float* bias,
+                        int relu, const float* res, int64_t ldr, float* out, int64_t ldo, int B, int N, int K,
+                        void* stream);
+/* dst[row*row_stride + h*head_stride + offset + e] = src[row, col_off + h*Dh + e], e < 64 (zero padded):
+ * stages q, appends K / V to the ring cache slot, builds the R-by-distance table. */
+int commu_pad_heads(const float* src, int64_t ld_src, int col_off, int rows, int H, int Dh, void* dst,
+                    int dst_bf16, int64_t row_stride, int64_t head_stride, int64_t offset, void* stream);
+/* Single-query relative attention over the projected K/V ring cache [B,H,C,64]: ages 0..n_vis-1
+ * (age 0 at ring slot cur_slot) with score_a = scale*((q+r_w_bias).k_a + (q+r_r_bias).R[a]). */
+int commu_decode_attn(const float* q, const void* kcache, const void* vcache, const void* rtab, int cache_bf16,
+                      const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
+                      float scale, float* out, int64_t ldo, void* stream);
+/* Sampler over B rows of raw logits (token 0 is never sampled, midi_inferrer.py:206/:220): temperature
+ * (0 = greedy one-hot, :211-213), top-k (:224-226), top-p (new), wrong-token mask (:227-229),
+ * renormalise (:230-231), counter-based multinomial draw (:234-237).  tokens and/or probs_out. */
+int commu_sample(const float* logits, int64_t ld, int B, int V, float temperature, int top_k, float top_p,
+                 const unsigned char* wrong, uint64_t seed, uint64_t offset, int64_t* tokens, float* probs_out,
+                 int64_t ldp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
