@@ -1,0 +1,471 @@
+// Fused relative-position attention forward on tcgen05 tensor cores (v2).
+//
+// One CTA = 128 query rows of one (batch, head); key tiles of 128.  Per key tile t three MMAs run on
+// the 5th-gen tensor cores with accumulators in TMEM:
+//     S(t)    = (q+u) K_t^T                 [128 x 128]   A,B from 128B-swizzled smem (TMA-staged)
+//     BD(b)   = (q+v) R_b^T                 [128 x 128]   one new 128-distance block of R per tile
+//     Opart   = P(t) V_t                    [128 x 64]    A = P in TMEM (bf16), B = V tile (MN-major)
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
+// allocator, warps 4-7 = softmax (thread = query row, tcgen05.ld 32x32b).
+//
+// Relative shift: the distances a (query tile, key tile) pair needs are the 255-row band
+// delta = dlo + c, c = li + 127 - lj.  It is covered by two 128-row blocks: "lo" (new for this key
+// tile) and "hi" (the previous tile's "lo").  A softmax thread copies ITS OWN row of each BD block
+// from TMEM to a private fp16 row in shared memory and re-reads it at c = li + 127 - lj; rows are
+// thread-private, so no barrier is involved.  T x K never exists in HBM.
+//
+// Replaces commu/model/model.py:312-345 (AC, BD, _rel_shift, mask, softmax, AV).
+#include <cuda_fp16.h>
+#include "api_common.h"
+#include "attn_common.cuh"
+
+namespace cb_host {
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer);
+int check_attn_common(const attn::Params& p, const char* who);
+}
+
+namespace {
+using attn::Params;
+using attn::key_lo;
+
+constexpr int TM = 128;   // query rows per CTA
+constexpr int TN = 128;   // keys per tile
+constexpr int DH = 64;
+constexpr int NTHREADS = 256;
+constexpr int STAGE_ROW = 272;            // bytes per staged fp16 BD row (256 + 16 pad: conflict-free 16B stores)
+constexpr int TILE_BYTES = TN * DH * 2;   // 16 KB
+// TMEM columns
+constexpr int COL_S = 0;      // 2 x 128
+constexpr int COL_BD = 256;   // 128
+constexpr int COL_O = 384;    // 64
+constexpr int COL_P = 448;    // 64 (bf16 pairs)
+
+struct Smem {
+  uint8_t qu[TILE_BYTES];
+  uint8_t qv[TILE_BYTES];
+  uint8_t k[2][TILE_BYTES];
+  uint8_t v[2][TILE_BYTES];
+  uint8_t r[2][TILE_BYTES];
+  uint8_t bd[2][TM * STAGE_ROW];
+  uint64_t q_ready;
+  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2], r_full[2], r_empty[2];
+  uint64_t s_full[2], s_empty[2], bd_full, bd_empty, p_full, o_full, o_empty;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct Ring {  // stage / parity bookkeeping of a 2-deep mbarrier ring
+  int idx = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance() {
+    idx ^= 1;
+    if (idx == 0) phase ^= 1;
+  }
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                      const __grid_constant__ CUtensorMap tm_r, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int i0 = (gridDim.x - 1 - blockIdx.x) * TM;
+  const bool reset = p.reset && p.reset[b];
+  const int i_last = min(p.T - 1, i0 + TM - 1);
+  const int jt_first = key_lo(i0, p.M, p.same_length, p.shift, reset) / TN;
+  const int jt_last = (i_last + p.M) / TN;
+  const int nt = jt_last - jt_first + 1;
+  // distance of band column c for tile t: delta = i0 + M - (j0 + 127) + c ; block beta covers
+  // R rows [dbase - 128*beta, +128) with dbase = "hi" block of the first tile
+  const int dbase = i0 + p.M - (jt_first * TN + TN - 1) + TN;
+
+  if (threadIdx.x == 0) {
+    cb::mbar_init(&sm.q_ready, 128);
+    for (int s = 0; s < 2; ++s) {
+      cb::mbar_init(&sm.k_full[s], 1); cb::mbar_init(&sm.k_empty[s], 1);
+      cb::mbar_init(&sm.v_full[s], 1); cb::mbar_init(&sm.v_empty[s], 1);
+      cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1);
+      cb::mbar_init(&sm.s_full[s], 1); cb::mbar_init(&sm.s_empty[s], 128);
+    }
+    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, 128);
+    cb::mbar_init(&sm.p_full, 128);
+    cb::mbar_init(&sm.o_full, 1); cb::mbar_init(&sm.o_empty, 128);
+    cb::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    cb::tma_prefetch_desc(&tm_k);
+    cb::tma_prefetch_desc(&tm_v);
+    cb::tma_prefetch_desc(&tm_r);
+  }
+  if (warp == 2) {
+    cb::tmem_alloc(&sm.tmem_base, 512);
+    cb::tmem_relinquish();
+  }
+  cb::tc_fence_before();
+  __syncthreads();
+  cb::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (cb::elect_one()) {
+      Ring rk, rv, rr;
+      auto load_r = [&](int beta) {
+        cb::mbar_wait(&sm.r_empty[rr.idx], rr.phase ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.r_full[rr.idx], TILE_BYTES);
+        cb::tma_load_2d(sm.r[rr.idx], &tm_r, &sm.r_full[rr.idx], h * DH, dbase - TN * beta);
+        rr.advance();
+      };
+      load_r(0);
+      for (int t = 0; t < nt; ++t) {
+        const int j0 = (jt_first + t) * TN;
+        cb::mbar_wait(&sm.k_empty[rk.idx], rk.phase ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.k_full[rk.idx], TILE_BYTES);
+        cb::tma_load_3d(sm.k[rk.idx], &tm_k, &sm.k_full[rk.idx], h * DH, b, j0);
+        rk.advance();
+        load_r(t + 1);
+        cb::mbar_wait(&sm.v_empty[rv.idx], rv.phase ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.v_full[rv.idx], TILE_BYTES);
+        cb::tma_load_3d(sm.v[rv.idx], &tm_v, &sm.v_full[rv.idx], h * DH, b, j0);
+        rv.advance();
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (cb::elect_one()) {
+      const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);   // S, BD: both operands K-major
+      const uint32_t idesc_o = cb::umma_idesc_bf16(TM, DH, 0, 1);   // PV: A in TMEM, B = V (MN-major)
+      Ring rk, rv, rr, rs;
+      uint32_t bd_phase = 0, p_phase = 0, o_phase = 0;
+      const uint32_t a_qu = cb::smem_u32(sm.qu), a_qv = cb::smem_u32(sm.qv);
+      cb::mbar_wait(&sm.q_ready, 0);
+      cb::tc_fence_after();
+      auto issue_bd = [&]() {
+        cb::mbar_wait(&sm.r_full[rr.idx], rr.phase);
+        cb::mbar_wait(&sm.bd_empty, bd_phase ^ 1);
+        cb::tc_fence_after();
+        const uint64_t ad = cb::umma_smem_desc(a_qv, 16, 1024);
+        const uint64_t bd = cb::umma_smem_desc(cb::smem_u32(sm.r[rr.idx]), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          cb::umma_bf16_ss(tmem + COL_BD, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
+        cb::umma_commit(&sm.r_empty[rr.idx]);
+        cb::umma_commit(&sm.bd_full);
+        rr.advance();
+        bd_phase ^= 1;
+      };
+      auto issue_s = [&]() {
+        cb::mbar_wait(&sm.k_full[rk.idx], rk.phase);
+        cb::mbar_wait(&sm.s_empty[rs.idx], rs.phase ^ 1);
+        cb::tc_fence_after();
+        const uint64_t ad = cb::umma_smem_desc(a_qu, 16, 1024);
+        const uint64_t bd = cb::umma_smem_desc(cb::smem_u32(sm.k[rk.idx]), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k)
+          cb::umma_bf16_ss(tmem + COL_S + rs.idx * TN, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
+        cb::umma_commit(&sm.k_empty[rk.idx]);
+        cb::umma_commit(&sm.s_full[rs.idx]);
+        rk.advance();
+        rs.advance();
+      };
+      issue_bd();   // beta = 0 ("hi" of the first tile)
+      issue_s();    // S(0)
+      issue_bd();   // beta = 1
+      for (int t = 0; t < nt; ++t) {
+        if (t + 1 < nt) {
+          issue_s();   // S(t+1)
+          issue_bd();  // beta = t+2
+        }
+        cb::mbar_wait(&sm.p_full, p_phase);
+        cb::mbar_wait(&sm.v_full[rv.idx], rv.phase);
+        cb::mbar_wait(&sm.o_empty, o_phase ^ 1);
+        cb::tc_fence_after();
+        const uint64_t vd = cb::umma_smem_desc(cb::smem_u32(sm.v[rv.idx]), 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < TN / 16; ++k)
+          umma_bf16_ts(tmem + COL_O, tmem + COL_P + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, k > 0);
+        cb::umma_commit(&sm.v_empty[rv.idx]);
+        cb::umma_commit(&sm.o_full);
+        rv.advance();
+        p_phase ^= 1;
+        o_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== softmax warps ==============================
+    const int li = (warp - 4) * 32 + lane;      // row inside the tile == TMEM lane
+    const int i = i0 + li;
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp - 4) * 32) << 16);
+    // ---- stage (q + r_w_bias), (q + r_r_bias) rows in the UMMA K-major 128B-swizzled layout ----
+    {
+      const bf16* qrow = p.q + ((long long)i * p.B + b) * p.ldq + h * DH;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint4 raw = make_uint4(0, 0, 0, 0);
+        if (i < p.T) raw = *reinterpret_cast<const uint4*>(qrow + ch * 8);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        uint32_t ou[4], ov[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float lo = cb::bf16_lo(w[e]), hi = cb::bf16_hi(w[e]);
+          const int c = h * DH + ch * 8 + e * 2;
+          ou[e] = cb::pack_bf16(lo + __ldg(p.u + c), hi + __ldg(p.u + c + 1));
+          ov[e] = cb::pack_bf16(lo + __ldg(p.vb + c), hi + __ldg(p.vb + c + 1));
+        }
+        *reinterpret_cast<uint4*>(sm.qu + attn::swz(li, ch)) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        *reinterpret_cast<uint4*>(sm.qv + attn::swz(li, ch)) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        if (p.qu_s && i < p.T) {
+          const long long off = ((long long)i * p.B + b) * p.ldq + h * DH + ch * 8;
+          *reinterpret_cast<uint4*>(p.qu_s + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+          *reinterpret_cast<uint4*>(p.qv_s + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+        }
+      }
+      cb::fence_proxy_async();
+      cb::mbar_arrive(&sm.q_ready);
+    }
+    uint32_t bd_phase = 0, o_phase = 0;
+    Ring rs;
+    // copy this thread's row of the BD block in TMEM to its private fp16 row of staging buffer `buf`
+    auto stage_bd = [&](int buf) {
+      cb::mbar_wait(&sm.bd_full, bd_phase);
+      cb::tc_fence_after();
+      uint8_t* row = sm.bd[buf] + li * STAGE_ROW;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + c * 32, r);
+        cb::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 q;
+          __half2 h0 = __floats2half2_rn(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
+          __half2 h1 = __floats2half2_rn(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
+          __half2 h2 = __floats2half2_rn(__uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
+          __half2 h3 = __floats2half2_rn(__uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
+          q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
+          q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(row + c * 64 + e * 2) = q;
+        }
+      }
+      cb::tc_fence_before();
+      cb::mbar_arrive(&sm.bd_empty);
+      bd_phase ^= 1;
+    };
+    float o[DH];
+#pragma unroll
+    for (int e = 0; e < DH; ++e) o[e] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const int hi_i = i < p.T ? i + p.M : -1;
+    const int lo_i = key_lo(i, p.M, p.same_length, p.shift, reset);
+
+    stage_bd(0);  // beta = 0
+    for (int t = 0; t < nt; ++t) {
+      stage_bd((t + 1) & 1);  // beta = t+1 ("lo" of this tile); "hi" = beta t sits in buffer t&1
+      const __half* lo_row = reinterpret_cast<const __half*>(sm.bd[(t + 1) & 1] + li * STAGE_ROW);
+      const __half* hi_row = reinterpret_cast<const __half*>(sm.bd[t & 1] + li * STAGE_ROW);
+      cb::mbar_wait(&sm.s_full[rs.idx], rs.phase);
+      cb::tc_fence_after();
+      const int j0 = (jt_first + t) * TN;
+      float s[TN];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + rs.idx * TN + c * 32, r);
+        cb::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const int lj = c * 32 + e;
+          // relative shift: band column li + 127 - lj; < 128 -> "lo" block, else "hi" block
+          const int idx = li + (TN - 1) - lj;
+          const float bdv = __half2float(idx < TN ? lo_row[idx] : hi_row[idx - TN]);
+          const int j = j0 + lj;
+          const float sv = (__uint_as_float(r[e]) + bdv) * sl2;
+          s[lj] = (j <= hi_i && j >= lo_i) ? sv : -INFINITY;
+        }
+      }
+      cb::tc_fence_before();
+      cb::mbar_arrive(&sm.s_empty[rs.idx]);
+      rs.advance();
+      float mx = m_run;
+#pragma unroll
+      for (int e = 0; e < TN; ++e) mx = fmaxf(mx, s[e]);
+      const float msafe = mx == -INFINITY ? 0.f : mx;
+      const float corr = exp2f(m_run - msafe);
+      m_run = mx;
+      float rsum = 0.f;
+      uint32_t pk[TN / 2];
+#pragma unroll
+      for (int e = 0; e < TN; e += 2) {
+        const float p0 = exp2f(s[e] - msafe), p1 = exp2f(s[e + 1] - msafe);
+        rsum += p0 + p1;
+        pk[e / 2] = cb::pack_bf16(p0, p1);
+      }
+      l_run = l_run * corr + rsum;
+      // ---- fold the previous tile's partial O (needs the correction of THIS tile too) ----
+      // order: O_prev was produced with the max in force when P(t-1) was written, so it is first
+      // accumulated into o[] (below, at the end of the previous iteration's scope), then o[] is
+      // rescaled by this tile's correction.
+      if (t > 0) {
+        cb::mbar_wait(&sm.o_full, o_phase);
+        cb::tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32];
+          cb::tmem_ld_32x32b_x32(lane_addr + COL_O + c * 32, r);
+          cb::tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(r[e]);
+        }
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.o_empty);
+        o_phase ^= 1;
+      }
+#pragma unroll
+      for (int e = 0; e < DH; ++e) o[e] *= corr;
+      // ---- P(t) -> TMEM (bf16 pairs, 64 columns) ----
+      {
+        uint32_t r0[32], r1[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          r0[e] = pk[e];
+          r1[e] = pk[32 + e];
+        }
+        tmem_st_32x32b_x32(lane_addr + COL_P, r0);
+        tmem_st_32x32b_x32(lane_addr + COL_P + 32, r1);
+        tmem_st_wait();
+      }
+      cb::tc_fence_before();
+      cb::mbar_arrive(&sm.p_full);
+    }
+    // last partial O
+    cb::mbar_wait(&sm.o_full, o_phase);
+    cb::tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t r[32];
+      cb::tmem_ld_32x32b_x32(lane_addr + COL_O + c * 32, r);
+      cb::tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(r[e]);
+    }
+    cb::tc_fence_before();
+    cb::mbar_arrive(&sm.o_empty);
+    // ---- finalize ----
+    if (i < p.T) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      bf16* orow = p.out + ((long long)i * p.B + b) * p.ldo + h * DH;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint4 q;
+        q.x = cb::pack_bf16(o[ch * 8 + 0] * inv, o[ch * 8 + 1] * inv);
+        q.y = cb::pack_bf16(o[ch * 8 + 2] * inv, o[ch * 8 + 3] * inv);
+        q.z = cb::pack_bf16(o[ch * 8 + 4] * inv, o[ch * 8 + 5] * inv);
+        q.w = cb::pack_bf16(o[ch * 8 + 6] * inv, o[ch * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(orow + ch * 8) = q;
+      }
+      if (p.lse) p.lse[((long long)b * p.H + h) * p.T + i] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+    }
+  }
+  cb::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    cb::tc_fence_after();
+    cb::tmem_dealloc(tmem, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3D map over a [rows, B, cols] bf16 tensor (row = i*B + b): dims {cols, B, rows}, box {64, 1, 128}
+int make_tmap_rows3d(CUtensorMap* map, const void* ptr, uint64_t cols, uint64_t B, uint64_t rows, uint64_t ld) {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr_fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr_fn, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return cb_host::fail(COMMU_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    fn = reinterpret_cast<EncodeTiledFn>(ptr_fn);
+  }
+  cuuint64_t dims[3] = {cols, B, rows};
+  cuuint64_t strides[2] = {ld * 2, ld * 2 * B};
+  cuuint32_t box[3] = {64, 1, 128};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cb_host::fail(COMMU_ERR_CUDA, "cuTensorMapEncodeTiled(3d) failed (%d)", (int)r);
+  return 0;
+}
+
+}  // namespace
+
+// Same contract as commu_relattn_fwd (the v1 warp-MMA kernel); this is the tcgen05 implementation.
+extern "C" int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                                    const void* r, int64_t ldr, int kr, const float* r_w_bias,
+                                    const float* r_r_bias, const unsigned char* reset, int T, int M, int B,
+                                    int H, int same_length, int shift, float scale, void* out, int64_t ldo,
+                                    float* lse, void* qu_save, void* qv_save, void* stream) {
+  attn::Params p = {};
+  p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.r = (const bf16*)r;
+  p.qu_s = (bf16*)qu_save; p.qv_s = (bf16*)qv_save;
+  p.u = r_w_bias; p.vb = r_r_bias; p.reset = reset;
+  p.ldq = ldq; p.ldkv = ldkv; p.ldr = ldr;
+  p.T = T; p.M = M; p.B = B; p.H = H; p.Kr = kr;
+  p.same_length = same_length; p.shift = shift; p.scale = scale;
+  p.out = (bf16*)out; p.ldo = ldo; p.lse = lse;
+  int rc = cb_host::check_attn_common(p, "relattn_fwd_tc");
+  if (rc) return rc;
+  CB_REQUIRE(out && (ldo % 8 == 0), "relattn_fwd_tc: bad output");
+  CB_REQUIRE((qu_save == nullptr) == (qv_save == nullptr), "relattn_fwd_tc: qu_save/qv_save must both be set or null");
+  const int Ktot = T + M;
+  CUtensorMap tk, tv, tr;
+  // K and V live in the same [K*B, ldkv] matrix; each map starts at its own base pointer.  The column
+  // extent is one head-row group of H*64 columns reachable from that base.
+  rc = make_tmap_rows3d(&tk, k, (uint64_t)H * 64, B, Ktot, ldkv);
+  if (rc) return rc;
+  rc = make_tmap_rows3d(&tv, v, (uint64_t)H * 64, B, Ktot, ldkv);
+  if (rc) return rc;
+  rc = cb_host::make_tmap_bf16_2d(&tr, r, (uint64_t)H * 64, kr, ldr, 64, 128);
+  if (rc) return rc;
+  static bool attr = false;
+  const int smem_bytes = (int)sizeof(Smem) + 1024;
+  if (!attr) {
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr = true;
+  }
+  dim3 grid(cb_host::ceil_div(T, TM), H, B);
+  cb_host::ProfScope prof(cb_host::PROF_ATTN_FWD, (cudaStream_t)stream);
+  relattn_fwd_tc_kernel<<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(tk, tv, tr, p);
+  cb_host::count_launch();
+  CB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -150,6 +150,13 @@ int commu_relattn_fwd(const void* q, int64_t ldq, const void* k, const void* v, 
                       const unsigned char* reset, int T, int M, int B, int H, int same_length, int shift,
                       float scale, void* out, int64_t ldo, float* lse, void* qu_save, void* qv_save,
                       void* stream);
+/* Same contract, tcgen05 implementation (TMA-staged K/V/R tiles, S / BD / PV accumulators in TMEM,
+ * P fed to the PV MMA from TMEM).  Requires ldo % 8 == 0. */
+int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
+                         const void* r, int64_t ldr, int kr, const float* r_w_bias, const float* r_r_bias,
+                         const unsigned char* reset, int T, int M, int B, int H, int same_length, int shift,
+                         float scale, void* out, int64_t ldo, float* lse, void* qu_save, void* qv_save,
+                         void* stream);
 /* Backward of the above (the reference uses torch autograd).  dq: bf16 [T*B, lddq]; dk, dv: bf16
  * [K*B, lddkv] (every key row written); dr: fp32 [kr, H*64] and du, dvb: fp32 [H,64] are accumulated
  * (+=, caller zeroes); delta_ws: fp32 [B,H,T] workspace. */

@@ -44,8 +44,10 @@ ATT_CASES = [
 ]
 
 
-@pytest.mark.parametrize("T,M,B,H,same_length,mem_len,with_reset", ATT_CASES)
-def test_relattn_fwd(T, M, B, H, same_length, mem_len, with_reset):
+@pytest.mark.parametrize("T,M,B,H,same_length,mem_len,with_reset", ATT_CASES + [(300, 500, 2, 2, 0, 512, 1),
+                                                                         (384, 384, 1, 2, 1, 384, 0)])
+@pytest.mark.parametrize("impl", ["commu_relattn_fwd", "commu_relattn_fwd_tc"])
+def test_relattn_fwd(T, M, B, H, same_length, mem_len, with_reset, impl):
     from commu import _native as nv
     torch.manual_seed(T * 13 + M)
     dev = "cuda"
@@ -67,7 +69,7 @@ def test_relattn_fwd(T, M, B, H, same_length, mem_len, with_reset):
     k_t = kv[:, :, 0]
     v_t = kv[:, :, 1]
     reset_u8 = reset.to(torch.uint8) if reset is not None else None
-    nv.call("commu_relattn_fwd", q, H * Dh, k_t, v_t, 2 * H * Dh, r, H * Dh, K, u, vb, reset_u8,
+    nv.call(impl, q, H * Dh, k_t, v_t, 2 * H * Dh, r, H * Dh, K, u, vb, reset_u8,
             T, M, B, H, same_length, shift, scale, out, H * Dh, lse, None, None)
     torch.cuda.synchronize()
     ref, ref_lse, _, _ = _relattn_ref(q.float(), k_t.float(), v_t.float(), r.float(), u, vb, reset, T, M,
