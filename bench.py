@@ -250,6 +250,11 @@ def run_native(args):
             "clocks": clocks,
             "final_loss": round(final_loss, 5),
         }
+        if world == 1 and not args.no_decode:
+            try:
+                out["decode"] = decode_bench(model, dev, pk)
+            except Exception as e:      # the decode arm must never hide the training metric
+                out["decode"] = {"error": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(1, 1)
         print(json.dumps(out), flush=True)
@@ -257,6 +262,51 @@ def run_native(args):
         comm.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def decode_bench(model, dev, pk, n_new=256, batch=64, mem_len=2048, precision="bf16"):
+    """BASELINE configs[3]: batch 64, 12L d512, mem_len 2048 (pre-filled), top-p 0.9 / T 0.95.
+    Returns tokens/s/sequence, the HBM roofline fraction of the decode-attention kernel, and the whole
+    step's fraction of the algorithmic 52 MB/token/sequence."""
+    import ctypes
+    from commu import _native as nv
+    from commu.engine.decode import DecodeEngine, DecodeState
+    lib = nv.lib()
+    model.eval()
+    eng = DecodeEngine(model, batch=batch, mem_len=mem_len, same_length=True, precision=precision)
+    gen = torch.Generator().manual_seed(5)
+    state = DecodeState()
+    fill = torch.randint(2, 560, (mem_len + 8, batch), generator=gen).to(dev)
+    for t in range(fill.shape[0]):                      # pre-fill the ring cache
+        logits, state = eng.step(fill[t].contiguous(), state)
+    cur, _ = eng.sample(logits, 0.95, 0, 0.9, None, 1, 0)
+    torch.cuda.synchronize()
+    lib.commu_prof_arm(0b1000)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(n_new):
+        logits, state = eng.step(cur, state)
+        cur, _ = eng.sample(logits, 0.95, 0, 0.9, None, 1, t + 1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    pms, pn = ctypes.c_float(0), ctypes.c_int(0)
+    nv.check(lib.commu_prof_read(3, ctypes.byref(pms), ctypes.byref(pn)))
+    lib.commu_prof_arm(0)
+    esz = 2 if precision == "bf16" else 4
+    L, H, d = CFG["n_layer"], CFG["n_head"], CFG["d_model"]
+    attn_bytes = batch * H * mem_len * 64 * esz * 2 + H * mem_len * 64 * esz     # K + V per sequence, R once
+    step_bytes = L * attn_bytes + 41.3e6 * esz
+    res = {"tokens_per_s_per_seq": round(n_new / (ms / 1e3), 1), "batch": batch, "new_tokens": n_new,
+           "ms_per_token_step": round(ms / n_new, 4), "precision": precision, "sampler": "top_p=0.9 T=0.95",
+           "aggregate_tokens_per_s": round(n_new * batch / (ms / 1e3), 1),
+           "step_hbm_frac": round(step_bytes / (ms / n_new / 1e3) / 1e9 / pk["hbm"], 4)}
+    if pn.value:
+        dur = pms.value / pn.value / 1e3
+        res["roofline"] = {"kernel": "decode_attn", "bound": "hbm", "achieved": round(attn_bytes / dur / 1e9, 1),
+                           "peak": pk["hbm"], "unit": "GB/s", "frac": round(attn_bytes / dur / 1e9 / pk["hbm"], 4),
+                           "traffic": None, "avg_launch_ms": round(dur * 1e3, 4)}
+    return res
 
 
 def cpu_baseline(steps, warmup):
@@ -312,6 +362,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

@@ -14,6 +14,7 @@ Layout conventions
     consumes -- wrapped in a `Mems` handle that mimics the reference tensor's surface.
 """
 import math
+import os
 
 import torch
 
@@ -80,7 +81,9 @@ class NativeLM:
         self._shadow = None
         self._shadow_version = None
         self._pos_cache = {}
-        self.grad_sink = None       # dict name -> fp32 grad tensor (reference layout), set by caller
+        # attention forward implementation: "tc" = tcgen05 / TMEM kernel, "v1" = warp-MMA kernel
+        self.attn_fwd_impl = {"tc": "commu_relattn_fwd_tc", "v1": "commu_relattn_fwd"}[
+            os.environ.get("COMMU_ATTN_FWD", "v1")]
         self.saved = None
 
     # ------------------------------------------------------------------ weight shadows ------------
@@ -198,7 +201,7 @@ class NativeLM:
             lse = torch.empty(B, self.H, T, device=dev)
             qu = torch.empty(rows, self.hd, device=dev, dtype=bf) if save else None
             qv = torch.empty(rows, self.hd, device=dev, dtype=bf) if save else None
-            nv.call("commu_relattn_fwd", q, self.hd, kv, kv[:, self.hd:], 2 * self.hd, r, self.hd, K,
+            nv.call(self.attn_fwd_impl, q, self.hd, kv, kv[:, self.hd:], 2 * self.hd, r, self.hd, K,
                     S["u"], S["vb"], reset_u8, T, M, B, self.H, int(bool(same_length)), shift, scale,
                     av, self.hd, lse, qu, qv)
             z1 = torch.empty(rows, self.dp, device=dev)

@@ -167,7 +167,8 @@ class MemTransformerLM(nn.Module):
 
     def _engine(self):
         dev = self.r_w_bias.device
-        if self._eng is None or self._eng.dev != dev or self._eng_ids != [id(p) for p in self._params()]:
+        self._params()
+        if self._eng is None or self._eng.dev != dev or self._eng_ids != [id(p) for p in self._param_list]:
             P = dict(zip(self._param_names, self._param_list))
             self._eng = NativeLM(P, self.n_layer, self.n_head, self.d_model, self.d_inner, self.n_token,
                                  self.pos_emb.inv_freq)

@@ -106,6 +106,7 @@ def _cpu_init(cls):
         self._shadow_version = None
         self._pos_cache = {}
         self.saved = None
+        self.attn_fwd_impl = "commu_relattn_fwd"
     return init
 
 
