@@ -6,13 +6,15 @@
 //     BD(b)   = (q+v) R_b^T                 [128 x 128]   one new 128-distance block of R per tile
 //     Opart   = P(t) V_t                    [128 x 64]    A = P in TMEM (bf16), B = V tile (MN-major)
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
-// allocator, warps 4-7 = softmax (thread = query row, tcgen05.ld 32x32b).
+// allocator, warps 4-11 = two softmax warpgroups (thread = one query row x 64 key columns,
+// tcgen05.ld 32x32b; the two threads of a row exchange their partial max through shared memory).
 //
 // Relative shift: the distances a (query tile, key tile) pair needs are the 255-row band
 // delta = dlo + c, c = li + 127 - lj.  It is covered by two 128-row blocks: "lo" (new for this key
 // tile) and "hi" (the previous tile's "lo").  A softmax thread copies ITS OWN row of each BD block
-// from TMEM to a private fp16 row in shared memory and re-reads it at c = li + 127 - lj; rows are
-// thread-private, so no barrier is involved.  T x K never exists in HBM.
+// from TMEM to an fp16 row in shared memory and re-reads it at c = li + 127 - lj (a row is shared only
+// by the two threads that own it).  Which block a 32-key chunk needs is warp-uniform except on the
+// diagonal chunk, so the re-read is `base - 2*lj` with immediate offsets.  T x K never exists in HBM.
 //
 // Replaces commu/model/model.py:312-345 (AC, BD, _rel_shift, mask, softmax, AV).
 #include <cuda_fp16.h>
@@ -32,8 +34,8 @@ using attn::key_lo;
 constexpr int TM = 128;   // query rows per CTA
 constexpr int TN = 128;   // keys per tile
 constexpr int DH = 64;
-constexpr int NTHREADS = 256;
-constexpr int STAGE_ROW = 272;            // bytes per staged fp16 BD row (256 + 16 pad: conflict-free 16B stores)
+constexpr int NTHREADS = 384;             // 4 control warps + 2 softmax warpgroups
+constexpr int STAGE_ROW = 528;            // bytes per staged fp16 BD row: [block half 0 | half 1] + 16 pad
 constexpr int TILE_BYTES = TN * DH * 2;   // 16 KB
 // TMEM columns
 constexpr int COL_S = 0;      // 2 x 128
@@ -47,7 +49,9 @@ struct Smem {
   uint8_t k[2][TILE_BYTES];
   uint8_t v[2][TILE_BYTES];
   uint8_t r[2][TILE_BYTES];
-  uint8_t bd[2][TM * STAGE_ROW];
+  uint8_t bd[TM * STAGE_ROW];
+  float xch[2][TM];   // per-row partial max exchanged between the two softmax warpgroups
+  float xsum[2][TM];  // per-row partial sums (end of kernel)
   uint64_t q_ready;
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2], r_full[2], r_empty[2];
   uint64_t s_full[2], s_empty[2], bd_full, bd_empty, p_full, o_full, o_empty;
@@ -77,6 +81,14 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 struct Ring {  // stage / parity bookkeeping of a 2-deep mbarrier ring
   int idx = 0;
@@ -105,16 +117,16 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
   const int dbase = i0 + p.M - (jt_first * TN + TN - 1) + TN;
 
   if (threadIdx.x == 0) {
-    cb::mbar_init(&sm.q_ready, 128);
+    cb::mbar_init(&sm.q_ready, 256);
     for (int s = 0; s < 2; ++s) {
       cb::mbar_init(&sm.k_full[s], 1); cb::mbar_init(&sm.k_empty[s], 1);
       cb::mbar_init(&sm.v_full[s], 1); cb::mbar_init(&sm.v_empty[s], 1);
       cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1);
-      cb::mbar_init(&sm.s_full[s], 1); cb::mbar_init(&sm.s_empty[s], 128);
+      cb::mbar_init(&sm.s_full[s], 1); cb::mbar_init(&sm.s_empty[s], 256);
     }
-    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, 128);
-    cb::mbar_init(&sm.p_full, 128);
-    cb::mbar_init(&sm.o_full, 1); cb::mbar_init(&sm.o_empty, 128);
+    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, 256);
+    cb::mbar_init(&sm.p_full, 256);
+    cb::mbar_init(&sm.o_full, 1); cb::mbar_init(&sm.o_empty, 256);
     cb::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -217,68 +229,75 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       }
     }
   } else if (warp >= 4) {
-    // ============================== softmax warps ==============================
-    const int li = (warp - 4) * 32 + lane;      // row inside the tile == TMEM lane
+    // ============================== softmax warpgroups ==============================
+    // thread = (query row li, column half g): g = 0 owns key columns 0..63 / out dims 0..31, g = 1 the rest
+    const int g = (warp - 4) >> 2;
+    const int wq = (warp - 4) & 3;              // TMEM lane quadrant
+    const int li = wq * 32 + lane;
     const int i = i0 + li;
-    const uint32_t lane_addr = tmem + (static_cast<uint32_t>((warp - 4) * 32) << 16);
-    // ---- stage (q + r_w_bias), (q + r_r_bias) rows in the UMMA K-major 128B-swizzled layout ----
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+    // ---- stage (q + r_w_bias) [g = 0] / (q + r_r_bias) [g = 1] rows, UMMA K-major 128B-swizzled ----
     {
       const bf16* qrow = p.q + ((long long)i * p.B + b) * p.ldq + h * DH;
+      const float* bias = g == 0 ? p.u : p.vb;
+      uint8_t* tile = g == 0 ? sm.qu : sm.qv;
+      bf16* save = g == 0 ? p.qu_s : p.qv_s;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         uint4 raw = make_uint4(0, 0, 0, 0);
         if (i < p.T) raw = *reinterpret_cast<const uint4*>(qrow + ch * 8);
         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-        uint32_t ou[4], ov[4];
+        uint32_t ob[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float lo = cb::bf16_lo(w[e]), hi = cb::bf16_hi(w[e]);
           const int c = h * DH + ch * 8 + e * 2;
-          ou[e] = cb::pack_bf16(lo + __ldg(p.u + c), hi + __ldg(p.u + c + 1));
-          ov[e] = cb::pack_bf16(lo + __ldg(p.vb + c), hi + __ldg(p.vb + c + 1));
+          ob[e] = cb::pack_bf16(cb::bf16_lo(w[e]) + __ldg(bias + c), cb::bf16_hi(w[e]) + __ldg(bias + c + 1));
         }
-        *reinterpret_cast<uint4*>(sm.qu + attn::swz(li, ch)) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
-        *reinterpret_cast<uint4*>(sm.qv + attn::swz(li, ch)) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-        if (p.qu_s && i < p.T) {
-          const long long off = ((long long)i * p.B + b) * p.ldq + h * DH + ch * 8;
-          *reinterpret_cast<uint4*>(p.qu_s + off) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
-          *reinterpret_cast<uint4*>(p.qv_s + off) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-        }
+        *reinterpret_cast<uint4*>(tile + attn::swz(li, ch)) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+        if (save && i < p.T)
+          *reinterpret_cast<uint4*>(save + ((long long)i * p.B + b) * p.ldq + h * DH + ch * 8) =
+              make_uint4(ob[0], ob[1], ob[2], ob[3]);
       }
       cb::fence_proxy_async();
       cb::mbar_arrive(&sm.q_ready);
     }
     uint32_t bd_phase = 0, o_phase = 0;
     Ring rs;
-    // copy this thread's row of the BD block in TMEM to its private fp16 row of staging buffer `buf`
-    auto stage_bd = [&](int buf) {
+    uint8_t* my_row = sm.bd + li * STAGE_ROW;
+    // copy this thread's 64 columns of the BD block in TMEM into half `half` of its row's fp16 staging
+    auto stage_bd = [&](int half) {
       cb::mbar_wait(&sm.bd_full, bd_phase);
       cb::tc_fence_after();
-      uint8_t* row = sm.bd[buf] + li * STAGE_ROW;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + c * 32, r);
-        cb::tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; e += 8) {
-          uint4 q;
-          __half2 h0 = __floats2half2_rn(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-          __half2 h1 = __floats2half2_rn(__uint_as_float(r[e + 2]), __uint_as_float(r[e + 3]));
-          __half2 h2 = __floats2half2_rn(__uint_as_float(r[e + 4]), __uint_as_float(r[e + 5]));
-          __half2 h3 = __floats2half2_rn(__uint_as_float(r[e + 6]), __uint_as_float(r[e + 7]));
-          q.x = *reinterpret_cast<uint32_t*>(&h0); q.y = *reinterpret_cast<uint32_t*>(&h1);
-          q.z = *reinterpret_cast<uint32_t*>(&h2); q.w = *reinterpret_cast<uint32_t*>(&h3);
-          *reinterpret_cast<uint4*>(row + c * 64 + e * 2) = q;
-        }
-      }
+      uint32_t r0[32], r1[32];
+      cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 64, r0);
+      cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 64 + 32, r1);
+      cb::tmem_ld_wait();
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.bd_empty);
       bd_phase ^= 1;
-    };
-    float o[DH];
+      uint8_t* dst = my_row + half * 256 + g * 128;
 #pragma unroll
-    for (int e = 0; e < DH; ++e) o[e] = 0.f;
+      for (int e = 0; e < 32; e += 8) {
+        uint4 q0, q1;
+        __half2 a0 = __floats2half2_rn(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1]));
+        __half2 a1 = __floats2half2_rn(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3]));
+        __half2 a2 = __floats2half2_rn(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5]));
+        __half2 a3 = __floats2half2_rn(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7]));
+        q0.x = *reinterpret_cast<uint32_t*>(&a0); q0.y = *reinterpret_cast<uint32_t*>(&a1);
+        q0.z = *reinterpret_cast<uint32_t*>(&a2); q0.w = *reinterpret_cast<uint32_t*>(&a3);
+        __half2 b0 = __floats2half2_rn(__uint_as_float(r1[e]), __uint_as_float(r1[e + 1]));
+        __half2 b1 = __floats2half2_rn(__uint_as_float(r1[e + 2]), __uint_as_float(r1[e + 3]));
+        __half2 b2 = __floats2half2_rn(__uint_as_float(r1[e + 4]), __uint_as_float(r1[e + 5]));
+        __half2 b3 = __floats2half2_rn(__uint_as_float(r1[e + 6]), __uint_as_float(r1[e + 7]));
+        q1.x = *reinterpret_cast<uint32_t*>(&b0); q1.y = *reinterpret_cast<uint32_t*>(&b1);
+        q1.z = *reinterpret_cast<uint32_t*>(&b2); q1.w = *reinterpret_cast<uint32_t*>(&b3);
+        *reinterpret_cast<uint4*>(dst + e * 2) = q0;
+        *reinterpret_cast<uint4*>(dst + 64 + e * 2) = q1;
+      }
+    };
+    float o[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) o[e] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     const float sl2 = p.scale * 1.4426950408889634f;
     const int hi_i = i < p.T ? i + p.M : -1;
@@ -286,102 +305,116 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
 
     stage_bd(0);  // beta = 0
     for (int t = 0; t < nt; ++t) {
-      stage_bd((t + 1) & 1);  // beta = t+1 ("lo" of this tile); "hi" = beta t sits in buffer t&1
-      const __half* lo_row = reinterpret_cast<const __half*>(sm.bd[(t + 1) & 1] + li * STAGE_ROW);
-      const __half* hi_row = reinterpret_cast<const __half*>(sm.bd[t & 1] + li * STAGE_ROW);
+      stage_bd((t + 1) & 1);  // beta = t+1 = "lo" of this tile; "hi" = beta t sits in half t&1
+      named_bar(1, 256);      // both column halves of the staged rows are visible
+      // band column of key lj is idx = li + 127 - lj: idx < 128 -> "lo" block [idx], else "hi" block [idx-128]
+      const uint8_t* lo_base = my_row + ((t + 1) & 1) * 256 + 2 * (li + TN - 1);
+      const uint8_t* hi_base = my_row + (t & 1) * 256 + 2 * (li - 1);
       cb::mbar_wait(&sm.s_full[rs.idx], rs.phase);
       cb::tc_fence_after();
-      const int j0 = (jt_first + t) * TN;
-      float s[TN];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + rs.idx * TN + c * 32, r);
+      const int jc0 = (jt_first + t) * TN + g * 64;
+      float s[64];
+      {
+        uint32_t r0[32], r1[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + rs.idx * TN + g * 64, r0);
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + rs.idx * TN + g * 64 + 32, r1);
         cb::tmem_ld_wait();
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.s_empty[rs.idx]);
+        rs.advance();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int lj = c * 32 + e;
-          // relative shift: band column li + 127 - lj; < 128 -> "lo" block, else "hi" block
-          const int idx = li + (TN - 1) - lj;
-          const float bdv = __half2float(idx < TN ? lo_row[idx] : hi_row[idx - TN]);
-          const int j = j0 + lj;
-          const float sv = (__uint_as_float(r[e]) + bdv) * sl2;
-          s[lj] = (j <= hi_i && j >= lo_i) ? sv : -INFINITY;
+        for (int c = 0; c < 2; ++c) {
+          const int chunk = 2 * g + c;   // 32-key chunk index inside the tile; rows of this warp are 32*wq..
+          if (chunk < wq) {              // every lj < li  -> "hi" block (warp-uniform)
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int lj = chunk * 32 + e;
+              const float bdv = __half2float(*reinterpret_cast<const __half*>(hi_base - 2 * lj));
+              s[c * 32 + e] = __uint_as_float(c == 0 ? r0[e] : r1[e]) + bdv;
+            }
+          } else if (chunk > wq) {       // every lj > li  -> "lo" block
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int lj = chunk * 32 + e;
+              const float bdv = __half2float(*reinterpret_cast<const __half*>(lo_base - 2 * lj));
+              s[c * 32 + e] = __uint_as_float(c == 0 ? r0[e] : r1[e]) + bdv;
+            }
+          } else {                       // diagonal chunk: per element
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int lj = chunk * 32 + e;
+              const uint8_t* src = (lj < li ? hi_base : lo_base) - 2 * lj;
+              const float bdv = __half2float(*reinterpret_cast<const __half*>(src));
+              s[c * 32 + e] = __uint_as_float(c == 0 ? r0[e] : r1[e]) + bdv;
+            }
+          }
         }
       }
-      cb::tc_fence_before();
-      cb::mbar_arrive(&sm.s_empty[rs.idx]);
-      rs.advance();
-      float mx = m_run;
+      if (!(jc0 + 63 <= hi_i && jc0 >= lo_i)) {   // boundary tile: analytic mask
 #pragma unroll
-      for (int e = 0; e < TN; ++e) mx = fmaxf(mx, s[e]);
+        for (int e = 0; e < 64; ++e) {
+          const int j = jc0 + e;
+          if (j > hi_i || j < lo_i) s[e] = -INFINITY;
+        }
+      }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 64; ++e) mx = fmaxf(mx, s[e]);
+      sm.xch[g][li] = mx;
+      named_bar(2, 256);
+      mx = fmaxf(fmaxf(mx, sm.xch[g ^ 1][li]) * sl2, m_run);
       const float msafe = mx == -INFINITY ? 0.f : mx;
-      const float corr = exp2f(m_run - msafe);
+      const float corr = ex2(m_run - msafe);
       m_run = mx;
       float rsum = 0.f;
-      uint32_t pk[TN / 2];
+      uint32_t pk[32];
 #pragma unroll
-      for (int e = 0; e < TN; e += 2) {
-        const float p0 = exp2f(s[e] - msafe), p1 = exp2f(s[e + 1] - msafe);
+      for (int e = 0; e < 64; e += 2) {
+        const float p0 = ex2(fmaf(s[e], sl2, -msafe)), p1 = ex2(fmaf(s[e + 1], sl2, -msafe));
         rsum += p0 + p1;
         pk[e / 2] = cb::pack_bf16(p0, p1);
       }
       l_run = l_run * corr + rsum;
-      // ---- fold the previous tile's partial O (needs the correction of THIS tile too) ----
-      // order: O_prev was produced with the max in force when P(t-1) was written, so it is first
-      // accumulated into o[] (below, at the end of the previous iteration's scope), then o[] is
-      // rescaled by this tile's correction.
+      // ---- fold the previous tile's partial O (scale of the previous max), then rescale ----
       if (t > 0) {
         cb::mbar_wait(&sm.o_full, o_phase);
         cb::tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t r[32];
-          cb::tmem_ld_32x32b_x32(lane_addr + COL_O + c * 32, r);
-          cb::tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(r[e]);
-        }
+        uint32_t r[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_O + g * 32, r);
+        cb::tmem_ld_wait();
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.o_empty);
         o_phase ^= 1;
-      }
 #pragma unroll
-      for (int e = 0; e < DH; ++e) o[e] *= corr;
-      // ---- P(t) -> TMEM (bf16 pairs, 64 columns) ----
-      {
-        uint32_t r0[32], r1[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          r0[e] = pk[e];
-          r1[e] = pk[32 + e];
-        }
-        tmem_st_32x32b_x32(lane_addr + COL_P, r0);
-        tmem_st_32x32b_x32(lane_addr + COL_P + 32, r1);
-        tmem_st_wait();
+        for (int e = 0; e < 32; ++e) o[e] = (o[e] + __uint_as_float(r[e])) * corr;
       }
+      // ---- P(t) -> TMEM (bf16 pairs; this thread's 64 keys = 32 columns) ----
+      tmem_st_32x32b_x32(lane_addr + COL_P + g * 32, pk);
+      tmem_st_wait();
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.p_full);
     }
     // last partial O
     cb::mbar_wait(&sm.o_full, o_phase);
     cb::tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t r[32];
-      cb::tmem_ld_32x32b_x32(lane_addr + COL_O + c * 32, r);
+      cb::tmem_ld_32x32b_x32(lane_addr + COL_O + g * 32, r);
       cb::tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) o[c * 32 + e] += __uint_as_float(r[e]);
+      for (int e = 0; e < 32; ++e) o[e] += __uint_as_float(r[e]);
     }
     cb::tc_fence_before();
     cb::mbar_arrive(&sm.o_empty);
-    // ---- finalize ----
+    // ---- finalize: the two column halves add their partial sums ----
+    sm.xsum[g][li] = l_run;
+    named_bar(2, 256);
+    const float l_tot = l_run + sm.xsum[g ^ 1][li];
     if (i < p.T) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      bf16* orow = p.out + ((long long)i * p.B + b) * p.ldo + h * DH;
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      bf16* orow = p.out + ((long long)i * p.B + b) * p.ldo + h * DH + g * 32;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch = 0; ch < 4; ++ch) {
         uint4 q;
         q.x = cb::pack_bf16(o[ch * 8 + 0] * inv, o[ch * 8 + 1] * inv);
         q.y = cb::pack_bf16(o[ch * 8 + 2] * inv, o[ch * 8 + 3] * inv);
@@ -389,7 +422,8 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
         q.w = cb::pack_bf16(o[ch * 8 + 6] * inv, o[ch * 8 + 7] * inv);
         *reinterpret_cast<uint4*>(orow + ch * 8) = q;
       }
-      if (p.lse) p.lse[((long long)b * p.H + h) * p.T + i] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+      if (p.lse && g == 0)
+        p.lse[((long long)b * p.H + h) * p.T + i] = (m_run + log2f(l_tot)) * 0.6931471805599453f;
     }
   }
   cb::tc_fence_before();
