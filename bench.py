@@ -281,15 +281,39 @@ def decode_bench(model, dev, pk, n_new=256, batch=64, mem_len=2048, precision="b
         logits, state = eng.step(fill[t].contiguous(), state)
     cur, _ = eng.sample(logits, 0.95, 0, 0.9, None, 1, 0)
     torch.cuda.synchronize()
-    lib.commu_prof_arm(0b1000)
+    # the timed loop replays ONE captured CUDA graph per token (embed, 12 layers, logits, sampler);
+    # ring slot / visible count / sampler counter are device-resident (commu_decode_advance)
+    dstate = torch.tensor([state.slot, 0, state.count, 0], dtype=torch.int32, device=dev)
+
+    def one_step():
+        nv.call("commu_decode_advance", dstate, eng.C, eng.mem_len, 0)
+        eng._step_kernels(cur, 0, 1, dstate)
+        nv.call("commu_sample", eng.ws["logits"], eng.V, batch, eng.V, 0.95, 0, 0.9, None, 1, 0, cur, None, eng.V, dstate)
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        one_step()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        one_step()
+    for _ in range(3):
+        graph.replay()
+    torch.cuda.synchronize()
+    lib.commu_prof_arm(0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(n_new):
-        logits, state = eng.step(cur, state)
-        cur, _ = eng.sample(logits, 0.95, 0, 0.9, None, 1, t + 1)
+        graph.replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    # per-kernel timing of the decode attention (events cannot live inside a graph): eager steps
+    lib.commu_prof_arm(0b1000)
+    for t in range(8):
+        one_step()
+    torch.cuda.synchronize()
     pms, pn = ctypes.c_float(0), ctypes.c_int(0)
     nv.check(lib.commu_prof_read(3, ctypes.byref(pms), ctypes.byref(pn)))
     lib.commu_prof_arm(0)

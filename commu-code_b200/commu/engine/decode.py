@@ -80,7 +80,7 @@ class DecodeEngine:
                 n = min(64, C - r0)
                 self._linear(pos[r0:r0 + n], wr, None, False, None, rflat[r0:r0 + n], n, H * Dh, d)
             rt = torch.zeros(C, H, 64, device=dev, dtype=cdt)
-            nv.call("commu_pad_heads", rflat, H * Dh, 0, C, H, Dh, rt, int(self.bf16), H * 64, 64, 0)
+            nv.call("commu_pad_heads", rflat, H * Dh, 0, C, H, Dh, rt, int(self.bf16), H * 64, 64, 0, None)
             self.rt.append(rt)
         self.emb32 = sd["word_emb.emb_layers.0.weight"].detach()
         self.emb = wcast(self.emb32)
@@ -102,22 +102,30 @@ class DecodeEngine:
     @torch.no_grad()
     def step(self, tokens, state):
         """tokens: int64 [B] on device.  Returns (logits fp32 [B, V] (a reused workspace), new state)."""
-        B, H, Dh, d, C = self.B, self.H, self.Dh, self.d, self.C
-        ws = self.ws
-        slot = (state.slot + 1) % C
+        slot = (state.slot + 1) % self.C
         cached = min(state.count, self.mem_len)
         n_vis = min(cached + 1, self.mem_len + (0 if self.same_length else 1))
+        self._step_kernels(tokens, slot, n_vis, None)
+        return self.ws["logits"], DecodeState(min(state.count + 1, self.mem_len), slot)
+
+    def _step_kernels(self, tokens, slot, n_vis, dstate):
+        """One token for every sequence.  With `dstate` (device int32[4]) the ring slot / visible count are
+        read on the device, so the identical launch sequence can be replayed from a CUDA graph."""
+        B, H, Dh, d, C = self.B, self.H, self.Dh, self.d, self.C
+        ws = self.ws
+        cb = int(self.bf16)
         nv.call("commu_embed_fwd", tokens, self.emb32, d, d, math.sqrt(d), B, ws["x"], d, None, 0)
         x = ws["x"]
         for l in range(self.L):
             w = self.W[l]
             self._linear(x, w["qkv"], None, False, None, ws["qkv"], B, 3 * H * Dh, d)
-            cb = int(self.bf16)
-            nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 0, B, H, Dh, ws["q"], 0, H * 64, 64, 0)
-            nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, H * Dh, B, H, Dh, self.kc[l], cb, H * C * 64, C * 64, slot * 64)
-            nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 2 * H * Dh, B, H, Dh, self.vc[l], cb, H * C * 64, C * 64, slot * 64)
+            nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 0, B, H, Dh, ws["q"], 0, H * 64, 64, 0, None)
+            nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, H * Dh, B, H, Dh, self.kc[l], cb, H * C * 64, C * 64,
+                    slot * 64, dstate)
+            nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 2 * H * Dh, B, H, Dh, self.vc[l], cb, H * C * 64, C * 64,
+                    slot * 64, dstate)
             nv.call("commu_decode_attn", ws["q"], self.kc[l], self.vc[l], self.rt[l], cb, self.u, self.vb, B, H, C,
-                    n_vis, slot, self.scale, ws["att"], H * 64)
+                    n_vis, slot, self.scale, ws["att"], H * 64, dstate)
             self._linear(ws["att"], w["o"], None, False, x, ws["z"], B, d, H * 64)
             self._ln(ws["z"], w["g1"], w["be1"], ws["y"])
             self._linear(ws["y"], w["w1"], w["b1"], True, None, ws["h"], B, self.Di, d)
@@ -125,7 +133,6 @@ class DecodeEngine:
             self._ln(ws["z"], w["g2"], w["be2"], ws["x"])
             x = ws["x"]
         self._linear(x, self.emb, self.lbias, False, None, ws["logits"], B, self.V, d)
-        return ws["logits"], DecodeState(min(state.count + 1, self.mem_len), slot)
 
     @torch.no_grad()
     def prefill(self, ctx, state=None):
@@ -144,17 +151,45 @@ class DecodeEngine:
         toks = torch.empty(B, dtype=torch.int64, device=self.dev)
         probs = torch.empty(B, self.V, device=self.dev) if want_probs else None
         nv.call("commu_sample", logits, logits.stride(0), B, self.V, float(temperature), int(top_k), float(top_p),
-                wrong, int(seed), int(offset), toks, probs, self.V)
+                wrong, int(seed), int(offset), toks, probs, self.V, None)
         return toks, probs
 
     @torch.no_grad()
-    def generate(self, ctx, n_new, temperature=0.95, top_k=0, top_p=0.9, seed=0):
-        """Batched generation (BASELINE config 4): ctx int64 [T0, B] -> tokens int64 [n_new, B]."""
-        logits, state = self.prefill(ctx[:-1]) if ctx.shape[0] > 1 else (None, DecodeState())
-        cur = ctx[-1].contiguous()
+    def generate(self, ctx, n_new, temperature=0.95, top_k=0, top_p=0.9, seed=0, use_graph=True):
+        """Batched generation (BASELINE config 4): ctx int64 [T0, B] -> tokens int64 [n_new, B].
+        With use_graph the per-token launch sequence (embed, L layers, logits, sampler) is captured ONCE in
+        a CUDA graph; ring slot, visible-key count and sampler counter live in a device int32[4]."""
+        state = DecodeState()
+        if ctx.shape[0] > 1:
+            _, state = self.prefill(ctx[:-1], state)
+        cur = ctx[-1].contiguous().clone()
         out = torch.empty(n_new, self.B, dtype=torch.int64, device=self.dev)
-        for t in range(n_new):
-            logits, state = self.step(cur, state)
-            cur, _ = self.sample(logits, temperature, top_k, top_p, None, seed, t)
+        if not use_graph:
+            for t in range(n_new):
+                logits, state = self.step(cur, state)
+                cur, _ = self.sample(logits, temperature, top_k, top_p, None, seed, t)
+                out[t] = cur
+            return out
+        dstate = torch.tensor([state.slot, 0, state.count, 0], dtype=torch.int32, device=self.dev)
+        extra = 0 if self.same_length else 1
+
+        def one_step():
+            nv.call("commu_decode_advance", dstate, self.C, self.mem_len, extra)
+            self._step_kernels(cur, 0, 1, dstate)
+            nv.call("commu_sample", self.ws["logits"], self.V, self.B, self.V, float(temperature), int(top_k),
+                    float(top_p), None, int(seed), 0, cur, None, self.V, dstate)
+
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):        # warm-up outside capture (one real step)
+            one_step()
+            out[0] = cur
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            one_step()
+        for t in range(1, n_new):
+            graph.replay()
             out[t] = cur
+        self.last_state = dstate
         return out

@@ -57,7 +57,7 @@ class InferenceTask:
         else:
             full[0, 1:] = logits
         probs = torch.empty(1, V, device=logits.device)
-        nv.call("commu_sample", full, V, 1, V, temp, 0, 0.0, None, 0, 0, None, probs, V)
+        nv.call("commu_sample", full, V, 1, V, temp, 0, 0.0, None, 0, 0, None, probs, V, None)
         return probs[0]
 
     def apply_sampling(self, probs, wrong_tokens):
@@ -70,7 +70,7 @@ class InferenceTask:
         lg = torch.log(probs).unsqueeze(0).contiguous()
         out = torch.empty(1, V, device=probs.device)
         top_p = float(getattr(self.input_data, "top_p", 0.0) or 0.0)
-        nv.call("commu_sample", lg, V, 1, V, 1.0, int(self.input_data.top_k), top_p, wrong, 0, 0, None, out, V)
+        nv.call("commu_sample", lg, V, 1, V, 1.0, int(self.input_data.top_k), top_p, wrong, 0, 0, None, out, V, None)
         probs.copy_(out[0])
         return probs
 
@@ -81,5 +81,5 @@ class InferenceTask:
         V = probs.shape[0]
         tok = torch.empty(1, dtype=torch.int64, device=probs.device)
         self._draws += 1
-        nv.call("commu_sample", lg, V, 1, V, 1.0, 0, 0.0, None, self.seed, self._draws, tok, None, V)
+        nv.call("commu_sample", lg, V, 1, V, 1.0, 0, 0.0, None, self.seed, self._draws, tok, None, V, None)
         return int(tok.item())

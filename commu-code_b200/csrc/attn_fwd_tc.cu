@@ -86,6 +86,23 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// explicit shared-space accesses with 32-bit addresses: ptxas folds `base + constant` into the
+// instruction immediate, so the unrolled shear reads cost one LDS each (no 64-bit pointer math)
+__device__ __forceinline__ float lds_f16(uint32_t addr) {
+  unsigned short h;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+  float f;
+  asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+  return f;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -263,7 +280,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     }
     uint32_t bd_phase = 0, o_phase = 0;
     Ring rs;
-    uint8_t* my_row = sm.bd + li * STAGE_ROW;
+    const uint32_t my_row = cb::smem_u32(sm.bd) + li * STAGE_ROW;
     // copy this thread's 64 columns of the BD block in TMEM into half `half` of its row's fp16 staging
     auto stage_bd = [&](int half) {
       cb::mbar_wait(&sm.bd_full, bd_phase);
@@ -275,24 +292,17 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.bd_empty);
       bd_phase ^= 1;
-      uint8_t* dst = my_row + half * 256 + g * 128;
+      const uint32_t dst = my_row + half * 256 + g * 128;
 #pragma unroll
       for (int e = 0; e < 32; e += 8) {
-        uint4 q0, q1;
-        __half2 a0 = __floats2half2_rn(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1]));
-        __half2 a1 = __floats2half2_rn(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3]));
-        __half2 a2 = __floats2half2_rn(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5]));
-        __half2 a3 = __floats2half2_rn(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7]));
-        q0.x = *reinterpret_cast<uint32_t*>(&a0); q0.y = *reinterpret_cast<uint32_t*>(&a1);
-        q0.z = *reinterpret_cast<uint32_t*>(&a2); q0.w = *reinterpret_cast<uint32_t*>(&a3);
-        __half2 b0 = __floats2half2_rn(__uint_as_float(r1[e]), __uint_as_float(r1[e + 1]));
-        __half2 b1 = __floats2half2_rn(__uint_as_float(r1[e + 2]), __uint_as_float(r1[e + 3]));
-        __half2 b2 = __floats2half2_rn(__uint_as_float(r1[e + 4]), __uint_as_float(r1[e + 5]));
-        __half2 b3 = __floats2half2_rn(__uint_as_float(r1[e + 6]), __uint_as_float(r1[e + 7]));
-        q1.x = *reinterpret_cast<uint32_t*>(&b0); q1.y = *reinterpret_cast<uint32_t*>(&b1);
-        q1.z = *reinterpret_cast<uint32_t*>(&b2); q1.w = *reinterpret_cast<uint32_t*>(&b3);
-        *reinterpret_cast<uint4*>(dst + e * 2) = q0;
-        *reinterpret_cast<uint4*>(dst + 64 + e * 2) = q1;
+        sts_v4(dst + e * 2, pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1])),
+               pack_f16(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3])),
+               pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
+               pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
+        sts_v4(dst + 64 + e * 2, pack_f16(__uint_as_float(r1[e]), __uint_as_float(r1[e + 1])),
+               pack_f16(__uint_as_float(r1[e + 2]), __uint_as_float(r1[e + 3])),
+               pack_f16(__uint_as_float(r1[e + 4]), __uint_as_float(r1[e + 5])),
+               pack_f16(__uint_as_float(r1[e + 6]), __uint_as_float(r1[e + 7])));
       }
     };
     float o[32];
@@ -308,8 +318,8 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       stage_bd((t + 1) & 1);  // beta = t+1 = "lo" of this tile; "hi" = beta t sits in half t&1
       named_bar(1, 256);      // both column halves of the staged rows are visible
       // band column of key lj is idx = li + 127 - lj: idx < 128 -> "lo" block [idx], else "hi" block [idx-128]
-      const uint8_t* lo_base = my_row + ((t + 1) & 1) * 256 + 2 * (li + TN - 1);
-      const uint8_t* hi_base = my_row + (t & 1) * 256 + 2 * (li - 1);
+      const uint32_t lo_base = my_row + ((t + 1) & 1) * 256 + 2 * (li + TN - 1);
+      const uint32_t hi_base = my_row + (t & 1) * 256 + 2 * (li - 1);
       cb::mbar_wait(&sm.s_full[rs.idx], rs.phase);
       cb::tc_fence_after();
       const int jc0 = (jt_first + t) * TN + g * 64;
@@ -324,29 +334,15 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
         rs.advance();
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const int chunk = 2 * g + c;   // 32-key chunk index inside the tile; rows of this warp are 32*wq..
-          if (chunk < wq) {              // every lj < li  -> "hi" block (warp-uniform)
+          const int chunk = 2 * g + c;   // 32-key chunk of the tile; this warp's rows are 32*wq .. 32*wq+31
+          // chunk < wq: every lj < li -> "hi" block; chunk > wq: "lo" block; chunk == wq: per element
+          const uint32_t base = chunk < wq ? hi_base : lo_base;
+          const bool diag = chunk == wq;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int lj = chunk * 32 + e;
-              const float bdv = __half2float(*reinterpret_cast<const __half*>(hi_base - 2 * lj));
-              s[c * 32 + e] = __uint_as_float(c == 0 ? r0[e] : r1[e]) + bdv;
-            }
-          } else if (chunk > wq) {       // every lj > li  -> "lo" block
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int lj = chunk * 32 + e;
-              const float bdv = __half2float(*reinterpret_cast<const __half*>(lo_base - 2 * lj));
-              s[c * 32 + e] = __uint_as_float(c == 0 ? r0[e] : r1[e]) + bdv;
-            }
-          } else {                       // diagonal chunk: per element
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int lj = chunk * 32 + e;
-              const uint8_t* src = (lj < li ? hi_base : lo_base) - 2 * lj;
-              const float bdv = __half2float(*reinterpret_cast<const __half*>(src));
-              s[c * 32 + e] = __uint_as_float(c == 0 ? r0[e] : r1[e]) + bdv;
-            }
+          for (int e = 0; e < 32; ++e) {
+            const int lj = chunk * 32 + e;
+            const uint32_t src = (diag && lj < li) ? hi_base : base;
+            s[c * 32 + e] = __uint_as_float(c == 0 ? r0[e] : r1[e]) + lds_f16(src - 2 * lj);
           }
         }
       }

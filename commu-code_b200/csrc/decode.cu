@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) decode_linear_kernel(
 // e < 64, zero-padded beyond Dh.  Serves q staging, K/V ring append and the R table.
 template <typename CT>
 __global__ void pad_heads_kernel(const float* __restrict__ src, long long ld_src, int col_off, int rows,
-                                 int H, int Dh, CT* __restrict__ dst, long long rs, long long hs, long long off) {
+                                 int H, int Dh, CT* __restrict__ dst, long long rs, long long hs, long long off,
+                                 const int* __restrict__ dstate) {
+  if (dstate) off = (long long)dstate[0] * 64;   // ring slot kept on the device (CUDA-graph replay)
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)rows * H * 64) return;
   const int e = idx & 63;
@@ -136,8 +138,12 @@ template <typename CT>
 __global__ void __launch_bounds__(DA_WARPS * 32) decode_attn_kernel(
     const float* __restrict__ q, const CT* __restrict__ kc, const CT* __restrict__ vc,
     const CT* __restrict__ rt, const float* __restrict__ u, const float* __restrict__ vb, int H, int C,
-    int n_vis, int cur_slot, float scale, float* __restrict__ out, long long ldo) {
+    int n_vis, int cur_slot, float scale, float* __restrict__ out, long long ldo, const int* __restrict__ dstate) {
   __shared__ float sh_m[DA_WARPS], sh_l[DA_WARPS], sh_o[DA_WARPS][64];
+  if (dstate) {
+    cur_slot = dstate[0];
+    n_vis = dstate[1];
+  }
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane >> 3, part = lane & 7;
@@ -244,8 +250,9 @@ constexpr int SAMP_N = 1024;
 __global__ void __launch_bounds__(SAMP_N) sampler_kernel(
     const float* __restrict__ logits, long long ld, int V, float temperature, int top_k, float top_p,
     const unsigned char* __restrict__ wrong, unsigned long long seed, unsigned long long offset,
-    long long* __restrict__ tokens, float* __restrict__ probs_out, long long ldp) {
+    long long* __restrict__ tokens, float* __restrict__ probs_out, long long ldp, const int* __restrict__ dstate) {
   __shared__ float key[SAMP_N];
+  if (dstate) offset += (unsigned long long)dstate[3];
   __shared__ int idx[SAMP_N];
   __shared__ float red[32];
   __shared__ float prob[SAMP_N];
@@ -374,9 +381,29 @@ __global__ void __launch_bounds__(SAMP_N) sampler_kernel(
   }
 }
 
+// state = {slot, n_vis, cached, step}: advanced once at the start of every decode step
+__global__ void decode_advance_kernel(int* state, int C, int mem_len, int extra_visible) {
+  const int slot = (state[0] + 1) % C;
+  const int cached = min(state[2], mem_len);
+  state[0] = slot;
+  state[1] = min(cached + 1, mem_len + extra_visible);
+  state[2] = min(cached + 1, mem_len);
+  state[3] = state[3] + 1;
+}
+
 }  // namespace
 
 extern "C" {
+
+// Device-resident decode bookkeeping for CUDA-graph replay: state = int32[4] {slot, n_vis, cached, step}
+// (initialise to {-1, 0, 0, 0}).  extra_visible = 0 for same_length models, 1 otherwise.
+int commu_decode_advance(int* state, int C, int mem_len, int extra_visible, void* stream) {
+  CB_REQUIRE(state && C > 0 && mem_len > 0, "decode_advance: bad args");
+  decode_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, C, mem_len, extra_visible);
+  cb_host::count_launch();
+  CB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // out[b,n] = act(x W^T + bias) + res.  W is fp32 (w_bf16 = 0) or bf16 (w_bf16 = 1), [N, K] row-major.
 // Replaces the nn.Linear calls of the reference on the T = 1 decode step.
@@ -399,15 +426,16 @@ int commu_decode_linear(const float* x, int64_t ldx, const void* w, int64_t ldw,
 // dst[row*row_stride + h*head_stride + offset + e] = src[row, col_off + h*Dh + e] (zero for e >= Dh),
 // dst element type fp32 (dst_bf16 = 0) or bf16.
 int commu_pad_heads(const float* src, int64_t ld_src, int col_off, int rows, int H, int Dh, void* dst,
-                    int dst_bf16, int64_t row_stride, int64_t head_stride, int64_t offset, void* stream) {
+                    int dst_bf16, int64_t row_stride, int64_t head_stride, int64_t offset, const int* dev_state,
+                    void* stream) {
   CB_REQUIRE(src && dst && rows > 0 && H > 0 && Dh > 0 && Dh <= 64, "pad_heads: bad args");
   const long long n = (long long)rows * H * 64;
   const unsigned grid = (unsigned)((n + 255) / 256);
   cudaStream_t s = (cudaStream_t)stream;
   if (dst_bf16)
-    pad_heads_kernel<bf16><<<grid, 256, 0, s>>>(src, ld_src, col_off, rows, H, Dh, (bf16*)dst, row_stride, head_stride, offset);
+    pad_heads_kernel<bf16><<<grid, 256, 0, s>>>(src, ld_src, col_off, rows, H, Dh, (bf16*)dst, row_stride, head_stride, offset, dev_state);
   else
-    pad_heads_kernel<float><<<grid, 256, 0, s>>>(src, ld_src, col_off, rows, H, Dh, (float*)dst, row_stride, head_stride, offset);
+    pad_heads_kernel<float><<<grid, 256, 0, s>>>(src, ld_src, col_off, rows, H, Dh, (float*)dst, row_stride, head_stride, offset, dev_state);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -417,18 +445,19 @@ int commu_pad_heads(const float* src, int64_t ld_src, int col_off, int rows, int
 // The n_vis most recent ring entries (ages 0..n_vis-1, age 0 at slot cur_slot) are attended.
 int commu_decode_attn(const float* q, const void* kcache, const void* vcache, const void* rtab, int cache_bf16,
                       const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
-                      float scale, float* out, int64_t ldo, void* stream) {
-  CB_REQUIRE(q && kcache && vcache && rtab && out && n_vis >= 1 && n_vis <= C && cur_slot >= 0 && cur_slot < C,
+                      float scale, float* out, int64_t ldo, const int* dev_state, void* stream) {
+  CB_REQUIRE(q && kcache && vcache && rtab && out, "decode_attn: null arg");
+  CB_REQUIRE(dev_state || (n_vis >= 1 && n_vis <= C && cur_slot >= 0 && cur_slot < C),
              "decode_attn: bad args (n_vis=%d C=%d slot=%d)", n_vis, C, cur_slot);
   cudaStream_t s = (cudaStream_t)stream;
   cb_host::ProfScope prof(cb_host::PROF_DECODE_ATTN, s);
   dim3 grid(H, B);
   if (cache_bf16)
     decode_attn_kernel<bf16><<<grid, DA_WARPS * 32, 0, s>>>(q, (const bf16*)kcache, (const bf16*)vcache, (const bf16*)rtab,
-                                                            r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo);
+                                                            r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo, dev_state);
   else
     decode_attn_kernel<float><<<grid, DA_WARPS * 32, 0, s>>>(q, (const float*)kcache, (const float*)vcache, (const float*)rtab,
-                                                             r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo);
+                                                             r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo, dev_state);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -440,11 +469,11 @@ int commu_decode_attn(const float* q, const void* kcache, const void* vcache, co
 //   tokens: int64 [B] sampled ids (or NULL);  probs_out: fp32 [B, ldp] final distribution (or NULL).
 int commu_sample(const float* logits, int64_t ld, int B, int V, float temperature, int top_k, float top_p,
                  const unsigned char* wrong, uint64_t seed, uint64_t offset, int64_t* tokens, float* probs_out,
-                 int64_t ldp, void* stream) {
+                 int64_t ldp, const int* dev_state, void* stream) {
   CB_REQUIRE(logits && B > 0 && V > 1 && V <= SAMP_N, "sample: vocabulary must be <= %d", SAMP_N);
   CB_REQUIRE(tokens || probs_out, "sample: no output requested");
   sampler_kernel<<<B, SAMP_N, 0, (cudaStream_t)stream>>>(logits, ld, V, temperature, top_k, top_p, wrong, seed,
-                                                         offset, (long long*)tokens, probs_out, ldp);
+                                                         offset, (long long*)tokens, probs_out, ldp, dev_state);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

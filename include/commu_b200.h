@@ -189,18 +189,24 @@ int commu_decode_linear(const float* x, int64_t ldx, const void* w, int64_t ldw,
 /* dst[row*row_stride + h*head_stride + offset + e] = src[row, col_off + h*Dh + e], e < 64 (zero padded):
  * stages q, appends K / V to the ring cache slot, builds the R-by-distance table. */
 int commu_pad_heads(const float* src, int64_t ld_src, int col_off, int rows, int H, int Dh, void* dst,
-                    int dst_bf16, int64_t row_stride, int64_t head_stride, int64_t offset, void* stream);
+                    int dst_bf16, int64_t row_stride, int64_t head_stride, int64_t offset, const int* dev_state,
+                    void* stream);
+/* Device-resident step bookkeeping (int32[4] {slot, n_vis, cached, step}, init {-1,0,0,0}) so that a whole
+ * decode step can be captured once in a CUDA graph and replayed: when `dev_state` is non-NULL the ring
+ * slot / visible-key count / sampler offset of commu_pad_heads, commu_decode_attn and commu_sample come
+ * from it instead of the host arguments. */
+int commu_decode_advance(int* state, int C, int mem_len, int extra_visible, void* stream);
 /* Single-query relative attention over the projected K/V ring cache [B,H,C,64]: ages 0..n_vis-1
  * (age 0 at ring slot cur_slot) with score_a = scale*((q+r_w_bias).k_a + (q+r_r_bias).R[a]). */
 int commu_decode_attn(const float* q, const void* kcache, const void* vcache, const void* rtab, int cache_bf16,
                       const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
-                      float scale, float* out, int64_t ldo, void* stream);
+                      float scale, float* out, int64_t ldo, const int* dev_state, void* stream);
 /* Sampler over B rows of raw logits (token 0 is never sampled, midi_inferrer.py:206/:220): temperature
  * (0 = greedy one-hot, :211-213), top-k (:224-226), top-p (new), wrong-token mask (:227-229),
  * renormalise (:230-231), counter-based multinomial draw (:234-237).  tokens and/or probs_out. */
 int commu_sample(const float* logits, int64_t ld, int B, int V, float temperature, int top_k, float top_p,
                  const unsigned char* wrong, uint64_t seed, uint64_t offset, int64_t* tokens, float* probs_out,
-                 int64_t ldp, void* stream);
+                 int64_t ldp, const int* dev_state, void* stream);
 
 #ifdef __cplusplus
 }

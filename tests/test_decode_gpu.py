@@ -77,7 +77,7 @@ def test_sampler_matches_reference_probs():
             wr = torch.zeros(1, V, dtype=torch.uint8, device="cuda")
             wr[0, torch.from_numpy(wrong).cuda()] = 1
         probs = torch.empty(1, V, device="cuda")
-        nv.call("commu_sample", full, V, 1, V, float(temp), int(top_k), 0.0, wr, 0, 0, None, probs, V)
+        nv.call("commu_sample", full, V, 1, V, float(temp), int(top_k), 0.0, wr, 0, 0, None, probs, V, None)
         ref = z["case%d/probs" % ci]
         got = probs[0].cpu().numpy()
         assert np.array_equal(got > 0, ref > 0), ci
@@ -91,7 +91,7 @@ def test_sampler_top_p_and_draws():
     lg = (torch.randn(B, V) * 2).cuda()
     probs = torch.empty(B, V, device="cuda")
     toks = torch.empty(B, dtype=torch.int64, device="cuda")
-    nv.call("commu_sample", lg, V, B, V, 0.95, 0, 0.9, None, 123, 7, toks, probs, V)
+    nv.call("commu_sample", lg, V, B, V, 0.95, 0, 0.9, None, 123, 7, toks, probs, V, None)
     for b in range(0, B, 9):
         ref = orc.sampler_probs(lg[b].cpu(), 0.95, 0, 0.9, [])
         got = probs[b].cpu()
@@ -105,11 +105,25 @@ def test_sampler_top_p_and_draws():
     t1 = torch.empty(1, dtype=torch.int64, device="cuda")
     n = 4000
     for i in range(n):
-        nv.call("commu_sample", row, V, 1, V, 1.0, 8, 0.0, None, 99, i, t1, p1, V)
+        nv.call("commu_sample", row, V, 1, V, 1.0, 8, 0.0, None, 99, i, t1, p1, V, None)
         counts[int(t1)] += 1
     pr = p1[0].cpu()
     assert set(torch.nonzero(counts).flatten().tolist()) <= set(torch.nonzero(pr).flatten().tolist())
     assert (counts / n - pr).abs().max() < 0.03
+
+
+def test_generate_graph_equals_eager_greedy():
+    """CUDA-graph replay of the decode step (device-resident ring state) == eager per-step launches."""
+    from commu.engine.decode import DecodeEngine
+    z, cfg, P = load_golden("decode_greedy")
+    model = build_model(cfg, P)
+    ctx = torch.from_numpy(z["ctx"]).cuda()
+    eng = DecodeEngine(model, batch=2, mem_len=cfg.mem_len, same_length=True, precision="fp32")
+    a = eng.generate(ctx, 40, temperature=0.0, top_k=0, top_p=0.0, use_graph=False).cpu().numpy()
+    eng2 = DecodeEngine(model, batch=2, mem_len=cfg.mem_len, same_length=True, precision="fp32")
+    b = eng2.generate(ctx, 40, temperature=0.0, top_k=0, top_p=0.0, use_graph=True).cpu().numpy()
+    assert np.array_equal(a, z["tokens"])
+    assert np.array_equal(b, z["tokens"])
 
 
 def test_inference_task_surface():

@@ -151,6 +151,6 @@ def test_decode_plumbing(stub, monkeypatch):
     for prec in ("fp32", "bf16"):
         eng = dec.DecodeEngine(m, 3, 24, True, prec)
         ctx = torch.randint(1, 53, (5, 3))
-        out = eng.generate(ctx, 4, temperature=0.95, top_k=0, top_p=0.9, seed=1)
+        out = eng.generate(ctx, 4, temperature=0.95, top_k=0, top_p=0.9, seed=1, use_graph=False)
         assert out.shape == (4, 3)
     assert "commu_decode_attn" in stub.calls and "commu_sample" in stub.calls
