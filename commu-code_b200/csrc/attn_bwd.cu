@@ -10,6 +10,7 @@
 //              windows are read through the anti-diagonal (relative-shift) re-indexing.
 //
 // Autograd counterpart of commu/model/model.py:312-345 (the reference relies on torch autograd).
+#include <stdlib.h>
 #include "api_common.h"
 #include "attn_common.cuh"
 
@@ -516,6 +517,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) relattn_bwd_dr_kernel(const Param
 namespace cb_host {
 int check_attn_common(const attn::Params& p, const char* who);
 }
+extern "C" int commu_relattn_bwd_dkv_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
+                                        int64_t ldkv, const void* r, int64_t ldr, int kr,
+                                        const unsigned char* reset, int T, int M, int B, int H, int same_length,
+                                        int shift, float scale, const float* lse, const void* dout, int64_t lddo,
+                                        const float* delta, void* dk, void* dv, int64_t lddkv, void* stream_);
 
 // Backward of commu_relattn_fwd.  Inputs are the forward's operands plus the saved (q+r_w_bias),
 // (q+r_r_bias) bf16 tensors (layout of q), the forward output `out`, its LSE and dout.
@@ -564,8 +570,16 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
   }
   const int Ktot = T + M;
   relattn_bwd_dq_kernel<<<dim3(cb_host::ceil_div(T, attn::BM), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(p);
-  relattn_bwd_dkv_kernel<<<dim3(cb_host::ceil_div(Ktot, attn::BN), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(
-      p, (bf16*)dk, (bf16*)dv, lddkv);
+  // dk / dv pass: tcgen05 kernel by default-off switch COMMU_ATTN_BWD_DKV=tc, else the warp-MMA pass
+  static const bool dkv_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DKV"); return e && e[0] == 't'; }();
+  if (dkv_tc) {
+    int rc2 = commu_relattn_bwd_dkv_tc(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift,
+                                       scale, lse, dout, lddo, delta_ws, dk, dv, lddkv, stream_);
+    if (rc2) return rc2;
+  } else {
+    relattn_bwd_dkv_kernel<<<dim3(cb_host::ceil_div(Ktot, attn::BN), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(
+        p, (bf16*)dk, (bf16*)dv, lddkv);
+  }
   relattn_bwd_dr_kernel<<<dim3(cb_host::ceil_div(Ktot, attn::BN), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(p);
   cb_host::count_launch(4);
   CB_CHECK_CUDA(cudaGetLastError());

@@ -1,0 +1,394 @@
+// Relative-position attention backward on tcgen05 tensor cores: the dk / dv pass.
+//
+// One CTA = 128 keys of one (batch, head); it walks the query tiles that can see those keys.  Per
+// query tile five products run on the tensor cores with accumulators in TMEM:
+//     S    = (q+u) K^T          [128 q x 128 keys]      A, B: TMA-staged, K-major
+//     BD   = (q+v) R_blk^T      twice (the "lo" and "hi" 128-distance blocks of the band)
+//     dP   = dO V^T             [128 q x 128 keys]
+//     dV  += P^T dO             [128 keys x 64]          A = P  tile written by the softmax threads (MN-major)
+//     dK  += dS^T (q+u)         [128 keys x 64]          A = dS tile (MN-major), B = (q+u) tile (MN-major)
+// The softmax threads (thread = query row x 64 key columns) recompute P = exp2(score*log2e - LSE),
+// form dS = P * (dP - Delta), and store both as bf16 rows of two shared-memory tiles whose layout is at
+// once the K-major [q][key] tile and the MN-major operand the dV / dK products need - no transpose.
+// The relative shift is the same private-row fp16 staging as in the forward kernel, one block at a time.
+//
+// Autograd counterpart of commu/model/model.py:312-345 for d(keys), d(values).
+#include "api_common.h"
+#include "attn_common.cuh"
+#include "attn_tc_common.cuh"
+
+namespace cb_host {
+int check_attn_common(const attn::Params& p, const char* who);
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer);
+}
+
+namespace {
+using attn::Params;
+using attn::key_lo;
+using namespace attn_tc;
+
+constexpr int TM = 128, TN = 128, DH = 64;
+constexpr int NTHREADS = 384;
+constexpr int TILE_BYTES = 128 * DH * 2;      // 16 KB
+constexpr int STAGE_ROW = 272;                // one staged fp16 BD block row (256 B + 16 pad)
+constexpr int COL_S = 0, COL_DP = 128, COL_BD = 256, COL_DV = 384, COL_DK = 448;
+
+struct Smem {
+  uint8_t k[TILE_BYTES];
+  uint8_t v[TILE_BYTES];
+  uint8_t qu[TILE_BYTES];
+  uint8_t qv[TILE_BYTES];
+  uint8_t dout[TILE_BYTES];
+  uint8_t r[2][TILE_BYTES];
+  uint8_t p[2 * TILE_BYTES];    // [2 key atoms][128 q rows][128 B]
+  uint8_t ds[2 * TILE_BYTES];
+  uint8_t bd[TM * STAGE_ROW];
+  uint64_t kv_full, q_full, q_empty, r_full[2], r_empty[2];
+  uint64_t s_full, s_empty, bd_full, bd_empty, pds_full, pds_empty, acc_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                          const __grid_constant__ CUtensorMap tm_qu, const __grid_constant__ CUtensorMap tm_qv,
+                          const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_r,
+                          const Params p, bf16* __restrict__ dk_out, bf16* __restrict__ dv_out, long long lddkv) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int j0 = blockIdx.x * TN;
+  const bool reset = p.reset && p.reset[b];
+  const int Ktot = p.T + p.M;
+  // query tiles that can see a key of this tile (same bounds as the v1 dkv pass)
+  int i_min = max(0, j0 - p.M);
+  int i_max = p.T - 1;
+  if (p.same_length) i_max = min(i_max, j0 + TN - 2 + p.shift);
+  if (reset && j0 + TN - 1 < p.M) i_max = -1;
+  const int it_first = i_min / TM;
+  const int nq = i_max >= it_first * TM ? (i_max / TM - it_first + 1) : 0;
+  // R block gamma covers rows [dlo0 + 128*gamma, +128), dlo0 = band start of the first query tile
+  const int dlo0 = it_first * TM + p.M - j0 - (TN - 1);
+
+  if (threadIdx.x == 0) {
+    cb::mbar_init(&sm.kv_full, 1);
+    cb::mbar_init(&sm.q_full, 1); cb::mbar_init(&sm.q_empty, 1);
+    for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1); }
+    cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_empty, 256);
+    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, 256);
+    cb::mbar_init(&sm.pds_full, 256); cb::mbar_init(&sm.pds_empty, 1);
+    cb::mbar_init(&sm.acc_full, 1);
+    cb::fence_barrier_init();
+  }
+  if (warp == 2) {
+    cb::tmem_alloc(&sm.tmem_base, 512);
+    cb::tmem_relinquish();
+  }
+  cb::tc_fence_before();
+  __syncthreads();
+  cb::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (cb::elect_one() && nq > 0) {
+      cb::mbar_arrive_expect_tx(&sm.kv_full, 2 * TILE_BYTES);
+      cb::tma_load_3d(sm.k, &tm_k, &sm.kv_full, h * DH, b, j0);
+      cb::tma_load_3d(sm.v, &tm_v, &sm.kv_full, h * DH, b, j0);
+      Ring rr;
+      uint32_t q_phase = 0;
+      auto load_r = [&](int gamma) {
+        cb::mbar_wait(&sm.r_empty[rr.idx], rr.phase ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.r_full[rr.idx], TILE_BYTES);
+        cb::tma_load_2d(sm.r[rr.idx], &tm_r, &sm.r_full[rr.idx], h * DH, dlo0 + TN * gamma);
+        rr.advance();
+      };
+      load_r(0);
+      for (int n = 0; n < nq; ++n) {
+        const int i0 = (it_first + n) * TM;
+        cb::mbar_wait(&sm.q_empty, q_phase ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.q_full, 3 * TILE_BYTES);
+        cb::tma_load_3d(sm.qu, &tm_qu, &sm.q_full, h * DH, b, i0);
+        cb::tma_load_3d(sm.qv, &tm_qv, &sm.q_full, h * DH, b, i0);
+        cb::tma_load_3d(sm.dout, &tm_do, &sm.q_full, h * DH, b, i0);
+        q_phase ^= 1;
+        load_r(n + 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (cb::elect_one() && nq > 0) {
+      const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);   // S, BD, dP: K-major x K-major
+      const uint32_t idesc_g = cb::umma_idesc_bf16(TN, DH, 1, 1);   // dV, dK: MN-major A (tile^T), MN-major B
+      Ring rr;
+      uint32_t q_phase = 0, s_phase = 0, bd_phase = 0, pds_phase = 0;
+      cb::mbar_wait(&sm.kv_full, 0);
+      const uint32_t a_qu = cb::smem_u32(sm.qu), a_qv = cb::smem_u32(sm.qv), a_do = cb::smem_u32(sm.dout);
+      const uint32_t a_k = cb::smem_u32(sm.k), a_v = cb::smem_u32(sm.v);
+      auto issue_bd = [&](int ridx) {
+        cb::mbar_wait(&sm.bd_empty, bd_phase ^ 1);
+        cb::tc_fence_after();
+        const uint64_t ad = cb::umma_smem_desc(a_qv, 16, 1024);
+        const uint64_t bd = cb::umma_smem_desc(cb::smem_u32(sm.r[ridx]), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_BD, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
+        cb::umma_commit(&sm.bd_full);
+        bd_phase ^= 1;
+      };
+      for (int n = 0; n < nq; ++n) {
+        cb::mbar_wait(&sm.q_full, q_phase);
+        // R blocks of this query tile: "lo" = gamma n (buffer n&1), "hi" = gamma n+1 (buffer (n+1)&1)
+        cb::mbar_wait(&sm.r_full[rr.idx], rr.phase);            // gamma = n   (loaded one iteration ago, or now)
+        cb::mbar_wait(&sm.s_empty, s_phase ^ 1);
+        cb::tc_fence_after();
+        {  // S and dP
+          const uint64_t aq = cb::umma_smem_desc(a_qu, 16, 1024), bk = cb::umma_smem_desc(a_k, 16, 1024);
+          const uint64_t ad = cb::umma_smem_desc(a_do, 16, 1024), bv = cb::umma_smem_desc(a_v, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_S, aq + 2 * k, bk + 2 * k, idesc_s, k > 0);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_DP, ad + 2 * k, bv + 2 * k, idesc_s, k > 0);
+          cb::umma_commit(&sm.s_full);
+        }
+        issue_bd(rr.idx);                                        // BD "lo"
+        const int lo_idx = rr.idx;
+        rr.advance();
+        cb::mbar_wait(&sm.r_full[rr.idx], rr.phase);            // gamma = n+1
+        issue_bd(rr.idx);                                        // BD "hi"
+        cb::umma_commit(&sm.r_empty[lo_idx]);                    // gamma n is dead after this tile
+        // (gamma n+1 stays: it is the next tile's "lo"; rr now points at it)
+        // dV += P^T dO ; dK += dS^T (q+u)
+        cb::mbar_wait(&sm.pds_full, pds_phase);
+        cb::tc_fence_after();
+        {
+          const uint64_t ap = cb::umma_smem_desc(cb::smem_u32(sm.p), TILE_BYTES, 1024);
+          const uint64_t as = cb::umma_smem_desc(cb::smem_u32(sm.ds), TILE_BYTES, 1024);
+          const uint64_t bo = cb::umma_smem_desc(a_do, 8192, 1024), bq = cb::umma_smem_desc(a_qu, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < TM / 16; ++k)
+            cb::umma_bf16_ss(tmem + COL_DV, ap + (uint64_t)(k * 128), bo + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < TM / 16; ++k)
+            cb::umma_bf16_ss(tmem + COL_DK, as + (uint64_t)(k * 128), bq + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
+          cb::umma_commit(&sm.pds_empty);
+          cb::umma_commit(&sm.q_empty);
+        }
+        q_phase ^= 1;
+        s_phase ^= 1;
+        pds_phase ^= 1;
+      }
+      cb::umma_commit(&sm.acc_full);
+    }
+  } else if (warp >= 4) {
+    // ============================== softmax warpgroups ==============================
+    const int g = (warp - 4) >> 2;
+    const int wq = (warp - 4) & 3;
+    const int li = wq * 32 + lane;               // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+    const uint32_t my_row = cb::smem_u32(sm.bd) + li * STAGE_ROW;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
+    const float* lse_p = p.lse + ((long long)b * p.H + h) * p.T;
+    const float* del_p = p.delta + ((long long)b * p.H + h) * p.T;
+
+    for (int n = 0; n < nq; ++n) {
+      const int i = (it_first + n) * TM + li;
+      const float lse2 = i < p.T ? lse_p[i] * 1.4426950408889634f : 0.f;
+      const float delta = i < p.T ? del_p[i] : 0.f;
+      const int hi_i = i < p.T ? i + p.M : -1;
+      const int lo_i = key_lo(i, p.M, p.same_length, p.shift, reset);
+      // ---- scores of this thread's 64 key columns ----
+      cb::mbar_wait(&sm.s_full, s_phase);
+      cb::tc_fence_after();
+      float s[64];
+      {
+        uint32_t r0[32], r1[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + g * 64, r0);
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + g * 64 + 32, r1);
+        cb::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          s[e] = __uint_as_float(r0[e]);
+          s[32 + e] = __uint_as_float(r1[e]);
+        }
+      }
+      // ---- relative shift, one 128-distance block at a time: pass 0 = "lo" (keys lj >= li), pass 1 = "hi" ----
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        cb::mbar_wait(&sm.bd_full, bd_phase);
+        cb::tc_fence_after();
+        {
+          uint32_t r0[32], r1[32];
+          cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 64, r0);
+          cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 64 + 32, r1);
+          cb::tmem_ld_wait();
+          cb::tc_fence_before();
+          cb::mbar_arrive(&sm.bd_empty);
+          bd_phase ^= 1;
+          named_bar(1, 256);   // everyone finished reading the previously staged block
+          const uint32_t dst = my_row + g * 128;
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            sts_v4(dst + e * 2, pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1])),
+                   pack_f16(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3])),
+                   pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
+                   pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
+            sts_v4(dst + 64 + e * 2, pack_f16(__uint_as_float(r1[e]), __uint_as_float(r1[e + 1])),
+                   pack_f16(__uint_as_float(r1[e + 2]), __uint_as_float(r1[e + 3])),
+                   pack_f16(__uint_as_float(r1[e + 4]), __uint_as_float(r1[e + 5])),
+                   pack_f16(__uint_as_float(r1[e + 6]), __uint_as_float(r1[e + 7])));
+          }
+        }
+        named_bar(2, 256);   // both column halves of the staged block are visible
+        // band column of key lj: idx = li + 127 - lj; "lo" holds idx < 128 (lj >= li), "hi" holds idx - 128
+        const uint32_t base = pass == 0 ? my_row + 2 * (li + TN - 1) : my_row + 2 * (li - 1);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int chunk = 2 * g + c;
+          const bool all = pass == 0 ? chunk > wq : chunk < wq;    // warp-uniform
+          if (all) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) s[c * 32 + e] += lds_f16(base - 2 * (chunk * 32 + e));
+          } else if (chunk == wq) {                                // diagonal chunk: per element
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const int lj = chunk * 32 + e;
+              const bool use = pass == 0 ? lj >= li : lj < li;
+              const float bdv = lds_f16(use ? base - 2 * lj : my_row);
+              if (use) s[c * 32 + e] += bdv;
+            }
+          }
+        }
+      }
+      // ---- P = exp2(score*log2e - LSE), dS = P * (dP - Delta)  (the 1/sqrt(Dh) factor is applied to dK at the end)
+      const int jc0 = j0 + g * 64;
+      const bool full = (jc0 + 63 <= hi_i) && (jc0 >= lo_i);
+      uint32_t pk[32], dsk[32];
+      {
+        uint32_t r0[32], r1[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_DP + g * 64, r0);
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_DP + g * 64 + 32, r1);
+        cb::tmem_ld_wait();
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.s_empty);
+        s_phase ^= 1;
+#pragma unroll
+        for (int e = 0; e < 64; e += 2) {
+          float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
+          if (!full) {
+            const int j = jc0 + e;
+            if (j > hi_i || j < lo_i) p0 = 0.f;
+            if (j + 1 > hi_i || j + 1 < lo_i) p1 = 0.f;
+          }
+          const float dp0 = __uint_as_float(e < 32 ? r0[e] : r1[e - 32]);
+          const float dp1 = __uint_as_float(e < 32 ? r0[e + 1] : r1[e - 31]);
+          pk[e / 2] = cb::pack_bf16(p0, p1);
+          dsk[e / 2] = cb::pack_bf16(p0 * (dp0 - delta), p1 * (dp1 - delta));
+        }
+      }
+      // ---- rows of the P / dS tiles: key atom g, query row li, 8 swizzled 16-byte chunks ----
+      cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
+      {
+        const uint32_t prow = cb::smem_u32(sm.p) + g * TILE_BYTES;
+        const uint32_t drow = cb::smem_u32(sm.ds) + g * TILE_BYTES;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint32_t off = attn::swz(li, ch);
+          sts_v4(prow + off, pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
+          sts_v4(drow + off, dsk[ch * 4], dsk[ch * 4 + 1], dsk[ch * 4 + 2], dsk[ch * 4 + 3]);
+        }
+      }
+      cb::fence_proxy_async();
+      cb::mbar_arrive(&sm.pds_full);
+      pds_phase ^= 1;
+    }
+    // ---- epilogue: dV, dK rows (thread = key row li, 32 of the 64 head dims) ----
+    const int j = j0 + li;
+    if (nq > 0) {
+      cb::mbar_wait(&sm.acc_full, 0);
+      cb::tc_fence_after();
+      uint32_t rv[32], rk[32];
+      cb::tmem_ld_32x32b_x32(lane_addr + COL_DV + g * 32, rv);
+      cb::tmem_ld_32x32b_x32(lane_addr + COL_DK + g * 32, rk);
+      cb::tmem_ld_wait();
+      if (j < Ktot) {
+        bf16* dvr = dv_out + ((long long)j * p.B + b) * lddkv + h * DH + g * 32;
+        bf16* dkr = dk_out + ((long long)j * p.B + b) * lddkv + h * DH + g * 32;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 a, c2;
+          a.x = cb::pack_bf16(__uint_as_float(rv[ch * 8 + 0]), __uint_as_float(rv[ch * 8 + 1]));
+          a.y = cb::pack_bf16(__uint_as_float(rv[ch * 8 + 2]), __uint_as_float(rv[ch * 8 + 3]));
+          a.z = cb::pack_bf16(__uint_as_float(rv[ch * 8 + 4]), __uint_as_float(rv[ch * 8 + 5]));
+          a.w = cb::pack_bf16(__uint_as_float(rv[ch * 8 + 6]), __uint_as_float(rv[ch * 8 + 7]));
+          c2.x = cb::pack_bf16(__uint_as_float(rk[ch * 8 + 0]) * p.scale, __uint_as_float(rk[ch * 8 + 1]) * p.scale);
+          c2.y = cb::pack_bf16(__uint_as_float(rk[ch * 8 + 2]) * p.scale, __uint_as_float(rk[ch * 8 + 3]) * p.scale);
+          c2.z = cb::pack_bf16(__uint_as_float(rk[ch * 8 + 4]) * p.scale, __uint_as_float(rk[ch * 8 + 5]) * p.scale);
+          c2.w = cb::pack_bf16(__uint_as_float(rk[ch * 8 + 6]) * p.scale, __uint_as_float(rk[ch * 8 + 7]) * p.scale);
+          *reinterpret_cast<uint4*>(dvr + ch * 8) = a;
+          *reinterpret_cast<uint4*>(dkr + ch * 8) = c2;
+        }
+      }
+    } else if (j < Ktot) {   // nothing attends to these keys: zero gradients
+      bf16* dvr = dv_out + ((long long)j * p.B + b) * lddkv + h * DH + g * 32;
+      bf16* dkr = dk_out + ((long long)j * p.B + b) * lddkv + h * DH + g * 32;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        *reinterpret_cast<uint4*>(dvr + ch * 8) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(dkr + ch * 8) = make_uint4(0, 0, 0, 0);
+      }
+    }
+  }
+  cb::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    cb::tc_fence_after();
+    cb::tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+
+// dk / dv of commu_relattn_bwd on tcgen05 (same operand contract; dq, dr, du, dvb come from the other passes).
+// delta must already hold rowsum(dO * O) [B,H,T].
+extern "C" int commu_relattn_bwd_dkv_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
+                                        int64_t ldkv, const void* r, int64_t ldr, int kr,
+                                        const unsigned char* reset, int T, int M, int B, int H, int same_length,
+                                        int shift, float scale, const float* lse, const void* dout, int64_t lddo,
+                                        const float* delta, void* dk, void* dv, int64_t lddkv, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  attn::Params p = {};
+  p.q = (const bf16*)qu; p.k = (const bf16*)k; p.v = (const bf16*)v; p.r = (const bf16*)r;
+  p.qu_s = (bf16*)const_cast<void*>(qu); p.qv_s = (bf16*)const_cast<void*>(qv);
+  static const float dummy = 0.f;
+  p.u = &dummy; p.vb = &dummy;
+  p.reset = reset;
+  p.ldq = ldq; p.ldkv = ldkv; p.ldr = ldr;
+  p.T = T; p.M = M; p.B = B; p.H = H; p.Kr = kr;
+  p.same_length = same_length; p.shift = shift; p.scale = scale;
+  p.lse = const_cast<float*>(lse); p.delta = delta;
+  p.dout = (const bf16*)dout; p.lddo = lddo;
+  int rc = cb_host::check_attn_common(p, "relattn_bwd_dkv_tc");
+  if (rc) return rc;
+  CB_REQUIRE(qv && lse && dout && delta && dk && dv && lddkv % 8 == 0 && lddo % 8 == 0, "relattn_bwd_dkv_tc: bad args");
+  const int Ktot = T + M;
+  CUtensorMap tk, tv, tqu, tqv, tdo, tr;
+  if ((rc = make_tmap_rows3d(&tk, k, (uint64_t)H * 64, B, Ktot, ldkv))) return rc;
+  if ((rc = make_tmap_rows3d(&tv, v, (uint64_t)H * 64, B, Ktot, ldkv))) return rc;
+  if ((rc = make_tmap_rows3d(&tqu, qu, (uint64_t)H * 64, B, T, ldq))) return rc;
+  if ((rc = make_tmap_rows3d(&tqv, qv, (uint64_t)H * 64, B, T, ldq))) return rc;
+  if ((rc = make_tmap_rows3d(&tdo, dout, (uint64_t)H * 64, B, T, lddo))) return rc;
+  if ((rc = cb_host::make_tmap_bf16_2d(&tr, r, (uint64_t)H * 64, kr, ldr, 64, 128))) return rc;
+  static bool attr = false;
+  const int smem_bytes = (int)sizeof(Smem) + 1024;
+  if (!attr) {
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr = true;
+  }
+  dim3 grid(cb_host::ceil_div(Ktot, TN), H, B);
+  relattn_bwd_dkv_tc_kernel<<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p, (bf16*)dk, (bf16*)dv, lddkv);
+  cb_host::count_launch();
+  CB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

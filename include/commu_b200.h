@@ -167,6 +167,15 @@ int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, const void* k
                       void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, float* dr, float* du,
                       float* dvb, void* stream);
 
+/* dk / dv pass of commu_relattn_bwd on tcgen05 tensor cores (TMA-staged tiles, TMEM accumulators);
+ * `delta` = rowsum(dO * O) [B,H,T] must already be computed.  commu_relattn_bwd dispatches here when
+ * the environment variable COMMU_ATTN_BWD_DKV=tc is set. */
+int commu_relattn_bwd_dkv_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
+                             int64_t ldkv, const void* r, int64_t ldr, int kr, const unsigned char* reset,
+                             int T, int M, int B, int H, int same_length, int shift, float scale,
+                             const float* lse, const void* dout, int64_t lddo, const float* delta, void* dk,
+                             void* dv, int64_t lddkv, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Data-parallel gradient exchange: one NCCL sum all-reduce of the flat fp32 gradient arena per
  * optimizer step (replaces the per-micro-batch DDP bucket all-reduce, train.py:155, 467-473).
