@@ -83,7 +83,7 @@ class NativeLM:
         self._pos_cache = {}
         # attention forward implementation: "tc" = tcgen05 / TMEM kernel, "v1" = warp-MMA kernel
         self.attn_fwd_impl = {"tc": "commu_relattn_fwd_tc", "v1": "commu_relattn_fwd"}[
-            os.environ.get("COMMU_ATTN_FWD", "v1")]
+            os.environ.get("COMMU_ATTN_FWD", "tc")]
         self.saved = None
 
     # ------------------------------------------------------------------ weight shadows ------------

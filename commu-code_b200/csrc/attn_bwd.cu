@@ -570,8 +570,8 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
   }
   const int Ktot = T + M;
   relattn_bwd_dq_kernel<<<dim3(cb_host::ceil_div(T, attn::BM), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(p);
-  // dk / dv pass: tcgen05 kernel by default-off switch COMMU_ATTN_BWD_DKV=tc, else the warp-MMA pass
-  static const bool dkv_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DKV"); return e && e[0] == 't'; }();
+  // dk / dv pass: tcgen05 kernel (default), or the warp-MMA pass with COMMU_ATTN_BWD_DKV=v1
+  static const bool dkv_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DKV"); return !(e && e[0] == 'v'); }();
   if (dkv_tc) {
     int rc2 = commu_relattn_bwd_dkv_tc(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift,
                                        scale, lse, dout, lddo, delta_ws, dk, dv, lddkv, stream_);

@@ -168,8 +168,8 @@ int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, const void* k
                       float* dvb, void* stream);
 
 /* dk / dv pass of commu_relattn_bwd on tcgen05 tensor cores (TMA-staged tiles, TMEM accumulators);
- * `delta` = rowsum(dO * O) [B,H,T] must already be computed.  commu_relattn_bwd dispatches here when
- * the environment variable COMMU_ATTN_BWD_DKV=tc is set. */
+ * `delta` = rowsum(dO * O) [B,H,T] must already be computed.  commu_relattn_bwd dispatches here by
+ * default (COMMU_ATTN_BWD_DKV=v1 selects the warp-MMA pass instead). */
 int commu_relattn_bwd_dkv_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
                              int64_t ldkv, const void* r, int64_t ldr, int kr, const unsigned char* reset,
                              int T, int M, int B, int H, int same_length, int shift, float scale,
