@@ -119,7 +119,7 @@ SIGNATURES = {
     "commu_decode_linear": [P, L, P, L, I, P, I, P, L, P, L, I, I, I, P],
     "commu_pad_heads": [P, L, I, I, I, I, P, I, L, L, L, P, P],
     "commu_decode_advance": [P, I, I, I, P],
-    "commu_decode_attn": [P, P, P, P, I, P, P, I, I, I, I, I, F, P, L, P, P],
+    "commu_decode_attn": [P, P, P, P, I, P, P, I, I, I, I, I, F, P, L, P, P, P],
     "commu_sample": [P, L, I, I, F, I, F, P, ctypes.c_uint64, ctypes.c_uint64, P, P, L, P, P],
     "commu_comm_unique_id": [P, P],
     "commu_comm_init": [P, P, I, I],

@@ -89,6 +89,12 @@ class DecodeEngine:
         f = lambda *s: torch.empty(*s, device=dev)
         self.ws = dict(x=f(B, d), qkv=f(B, 3 * H * Dh), q=f(B, H, 64), att=f(B, H * 64), z=f(B, d), y=f(B, d),
                        h=f(B, self.Di), logits=f(B, self.V))
+        # bf16 throughput mode: the linear layers run on the tcgen05 GEMM (weights streamed once per step,
+        # the 64 batch rows are one half-filled 128-row MMA tile), so activations also exist as bf16 operands
+        self.tc_linear = self.bf16 and d % 8 == 0 and self.Di % 8 == 0 and (H * Dh) % 8 == 0
+        if self.tc_linear:
+            hb = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
+            self.wsb = dict(x=hb(B, d), att=hb(B, H * 64), y=hb(B, d), h=hb(B, self.Di))
 
     def _linear(self, x, w, bias, relu, res, out, B, N, K):
         nv.call("commu_decode_linear", x, x.stride(0), w, w.stride(0), int(w.dtype == torch.bfloat16), bias,
@@ -114,25 +120,42 @@ class DecodeEngine:
         B, H, Dh, d, C = self.B, self.H, self.Dh, self.d, self.C
         ws = self.ws
         cb = int(self.bf16)
-        nv.call("commu_embed_fwd", tokens, self.emb32, d, d, math.sqrt(d), B, ws["x"], d, None, 0)
+        tc = self.tc_linear
+        wb = self.wsb if tc else None
+        nv.call("commu_embed_fwd", tokens, self.emb32, d, d, math.sqrt(d), B, ws["x"], d, wb["x"] if tc else None, d)
         x = ws["x"]
         for l in range(self.L):
             w = self.W[l]
-            self._linear(x, w["qkv"], None, False, None, ws["qkv"], B, 3 * H * Dh, d)
+            if tc:
+                nv.gemm(wb["x"], w["qkv"], m=B, n=3 * H * Dh, k=d, out_f32=ws["qkv"])
+            else:
+                self._linear(x, w["qkv"], None, False, None, ws["qkv"], B, 3 * H * Dh, d)
             nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 0, B, H, Dh, ws["q"], 0, H * 64, 64, 0, None)
             nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, H * Dh, B, H, Dh, self.kc[l], cb, H * C * 64, C * 64,
                     slot * 64, dstate)
             nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 2 * H * Dh, B, H, Dh, self.vc[l], cb, H * C * 64, C * 64,
                     slot * 64, dstate)
             nv.call("commu_decode_attn", ws["q"], self.kc[l], self.vc[l], self.rt[l], cb, self.u, self.vb, B, H, C,
-                    n_vis, slot, self.scale, ws["att"], H * 64, dstate)
-            self._linear(ws["att"], w["o"], None, False, x, ws["z"], B, d, H * 64)
-            self._ln(ws["z"], w["g1"], w["be1"], ws["y"])
-            self._linear(ws["y"], w["w1"], w["b1"], True, None, ws["h"], B, self.Di, d)
-            self._linear(ws["h"], w["w2"], w["b2"], False, ws["y"], ws["z"], B, d, self.Di)
-            self._ln(ws["z"], w["g2"], w["be2"], ws["x"])
+                    n_vis, slot, self.scale, ws["att"], H * 64, dstate, wb["att"] if tc else None)
+            if tc:
+                nv.gemm(wb["att"], w["o"], m=B, n=d, k=H * 64, add_f32=x, out_f32=ws["z"])
+                nv.call("commu_layernorm_fwd", ws["z"], d, w["g1"], w["be1"], d, d, 1e-5, B, ws["y"], d, wb["y"], d,
+                        None, None)
+                nv.gemm(wb["y"], w["w1"], m=B, n=self.Di, k=d, bias=w["b1"], relu=True, out_bf16=wb["h"])
+                nv.gemm(wb["h"], w["w2"], m=B, n=d, k=self.Di, bias=w["b2"], add_f32=ws["y"], out_f32=ws["z"])
+                nv.call("commu_layernorm_fwd", ws["z"], d, w["g2"], w["be2"], d, d, 1e-5, B, ws["x"], d, wb["x"], d,
+                        None, None)
+            else:
+                self._linear(ws["att"], w["o"], None, False, x, ws["z"], B, d, H * 64)
+                self._ln(ws["z"], w["g1"], w["be1"], ws["y"])
+                self._linear(ws["y"], w["w1"], w["b1"], True, None, ws["h"], B, self.Di, d)
+                self._linear(ws["h"], w["w2"], w["b2"], False, ws["y"], ws["z"], B, d, self.Di)
+                self._ln(ws["z"], w["g2"], w["be2"], ws["x"])
             x = ws["x"]
-        self._linear(x, self.emb, self.lbias, False, None, ws["logits"], B, self.V, d)
+        if tc:
+            nv.gemm(wb["x"], self.emb, m=B, n=self.V, k=d, bias=self.lbias, out_f32=ws["logits"])
+        else:
+            self._linear(x, self.emb, self.lbias, False, None, ws["logits"], B, self.V, d)
 
     @torch.no_grad()
     def prefill(self, ctx, state=None):

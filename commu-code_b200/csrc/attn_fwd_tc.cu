@@ -6,8 +6,8 @@
 //     BD(b)   = (q+v) R_b^T                 [128 x 128]   one new 128-distance block of R per tile
 //     Opart   = P(t) V_t                    [128 x 64]    A = P in TMEM (bf16), B = V tile (MN-major)
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
-// allocator, warps 4-11 = two softmax warpgroups (thread = one query row x 64 key columns,
-// tcgen05.ld 32x32b; the two threads of a row exchange their partial max through shared memory).
+// allocator, warps 4-19 = four softmax warpgroups (thread = one query row x 32 key columns,
+// tcgen05.ld 32x32b; the threads of a row exchange their partial max through shared memory).
 //
 // Relative shift: the distances a (query tile, key tile) pair needs are the 255-row band
 // delta = dlo + c, c = li + 127 - lj.  It is covered by two 128-row blocks: "lo" (new for this key
@@ -36,7 +36,11 @@ using namespace attn_tc;
 constexpr int TM = 128;   // query rows per CTA
 constexpr int TN = 128;   // keys per tile
 constexpr int DH = 64;
-constexpr int NTHREADS = 384;             // 4 control warps + 2 softmax warpgroups
+constexpr int NWG = 4;                    // softmax warpgroups (column quarters of a row)
+constexpr int SOFT = 128 * NWG;           // softmax threads
+constexpr int NTHREADS = 128 + SOFT;      // 4 control warps + NWG softmax warpgroups
+constexpr int CPT = TN / NWG;             // key columns per softmax thread
+constexpr int OPT = DH / NWG;             // output dims per softmax thread
 constexpr int STAGE_ROW = 528;            // bytes per staged fp16 BD row: [block half 0 | half 1] + 16 pad
 constexpr int TILE_BYTES = TN * DH * 2;   // 16 KB
 // TMEM columns
@@ -52,8 +56,8 @@ struct Smem {
   uint8_t v[2][TILE_BYTES];
   uint8_t r[2][TILE_BYTES];
   uint8_t bd[TM * STAGE_ROW];
-  float xch[2][TM];   // per-row partial max exchanged between the two softmax warpgroups
-  float xsum[2][TM];  // per-row partial sums (end of kernel)
+  float xch[4][TM];   // per-row partial max exchanged between the softmax warpgroups
+  float xsum[4][TM];  // per-row partial sums (end of kernel)
   uint64_t q_ready;
   uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2], r_full[2], r_empty[2];
   uint64_t s_full[2], s_empty[2], bd_full, bd_empty, p_full, o_full, o_empty;
@@ -78,16 +82,16 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
   const int dbase = i0 + p.M - (jt_first * TN + TN - 1) + TN;
 
   if (threadIdx.x == 0) {
-    cb::mbar_init(&sm.q_ready, 256);
+    cb::mbar_init(&sm.q_ready, SOFT);
     for (int s = 0; s < 2; ++s) {
       cb::mbar_init(&sm.k_full[s], 1); cb::mbar_init(&sm.k_empty[s], 1);
       cb::mbar_init(&sm.v_full[s], 1); cb::mbar_init(&sm.v_empty[s], 1);
       cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1);
-      cb::mbar_init(&sm.s_full[s], 1); cb::mbar_init(&sm.s_empty[s], 256);
+      cb::mbar_init(&sm.s_full[s], 1); cb::mbar_init(&sm.s_empty[s], SOFT);
     }
-    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, 256);
-    cb::mbar_init(&sm.p_full, 256);
-    cb::mbar_init(&sm.o_full, 1); cb::mbar_init(&sm.o_empty, 256);
+    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
+    cb::mbar_init(&sm.p_full, SOFT);
+    cb::mbar_init(&sm.o_full, 1); cb::mbar_init(&sm.o_empty, SOFT);
     cb::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -191,14 +195,14 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     }
   } else if (warp >= 4) {
     // ============================== softmax warpgroups ==============================
-    // thread = (query row li, column half g): g = 0 owns key columns 0..63 / out dims 0..31, g = 1 the rest
+    // thread = (query row li, column quarter g): owns key columns 32g..32g+31 and out dims 16g..16g+15
     const int g = (warp - 4) >> 2;
     const int wq = (warp - 4) & 3;              // TMEM lane quadrant
     const int li = wq * 32 + lane;
     const int i = i0 + li;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     // ---- stage (q + r_w_bias) [g = 0] / (q + r_r_bias) [g = 1] rows, UMMA K-major 128B-swizzled ----
-    {
+    if (g < 2) {
       const bf16* qrow = p.q + ((long long)i * p.B + b) * p.ldq + h * DH;
       const float* bias = g == 0 ? p.u : p.vb;
       uint8_t* tile = g == 0 ? sm.qu : sm.qv;
@@ -220,38 +224,32 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
               make_uint4(ob[0], ob[1], ob[2], ob[3]);
       }
       cb::fence_proxy_async();
-      cb::mbar_arrive(&sm.q_ready);
     }
+    cb::mbar_arrive(&sm.q_ready);
     uint32_t bd_phase = 0, o_phase = 0;
     Ring rs;
     const uint32_t my_row = cb::smem_u32(sm.bd) + li * STAGE_ROW;
-    // copy this thread's 64 columns of the BD block in TMEM into half `half` of its row's fp16 staging
+    // copy this thread's 32 columns of the BD block in TMEM into half `half` of its row's fp16 staging
     auto stage_bd = [&](int half) {
       cb::mbar_wait(&sm.bd_full, bd_phase);
       cb::tc_fence_after();
-      uint32_t r0[32], r1[32];
-      cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 64, r0);
-      cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 64 + 32, r1);
+      uint32_t r0[32];
+      cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 32, r0);
       cb::tmem_ld_wait();
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.bd_empty);
       bd_phase ^= 1;
-      const uint32_t dst = my_row + half * 256 + g * 128;
+      const uint32_t dst = my_row + half * 256 + g * 64;
 #pragma unroll
-      for (int e = 0; e < 32; e += 8) {
+      for (int e = 0; e < 32; e += 8)
         sts_v4(dst + e * 2, pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1])),
                pack_f16(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3])),
                pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
                pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
-        sts_v4(dst + 64 + e * 2, pack_f16(__uint_as_float(r1[e]), __uint_as_float(r1[e + 1])),
-               pack_f16(__uint_as_float(r1[e + 2]), __uint_as_float(r1[e + 3])),
-               pack_f16(__uint_as_float(r1[e + 4]), __uint_as_float(r1[e + 5])),
-               pack_f16(__uint_as_float(r1[e + 6]), __uint_as_float(r1[e + 7])));
-      }
     };
-    float o[32];
+    float o[OPT];
 #pragma unroll
-    for (int e = 0; e < 32; ++e) o[e] = 0.f;
+    for (int e = 0; e < OPT; ++e) o[e] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     const float sl2 = p.scale * 1.4426950408889634f;
     const int hi_i = i < p.T ? i + p.M : -1;
@@ -260,56 +258,56 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     stage_bd(0);  // beta = 0
     for (int t = 0; t < nt; ++t) {
       stage_bd((t + 1) & 1);  // beta = t+1 = "lo" of this tile; "hi" = beta t sits in half t&1
-      named_bar(1, 256);      // both column halves of the staged rows are visible
+      named_bar(1, SOFT);     // every column quarter of the staged rows is visible
       // band column of key lj is idx = li + 127 - lj: idx < 128 -> "lo" block [idx], else "hi" block [idx-128]
       const uint32_t lo_base = my_row + ((t + 1) & 1) * 256 + 2 * (li + TN - 1);
       const uint32_t hi_base = my_row + (t & 1) * 256 + 2 * (li - 1);
       cb::mbar_wait(&sm.s_full[rs.idx], rs.phase);
       cb::tc_fence_after();
-      const int jc0 = (jt_first + t) * TN + g * 64;
-      float s[64];
+      const int jc0 = (jt_first + t) * TN + g * CPT;
+      float s[CPT];
       {
-        uint32_t r0[32], r1[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + rs.idx * TN + g * 64, r0);
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + rs.idx * TN + g * 64 + 32, r1);
+        uint32_t r0[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + rs.idx * TN + g * 32, r0);
         cb::tmem_ld_wait();
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.s_empty[rs.idx]);
         rs.advance();
+        // this thread's 32-key chunk is chunk g; the warp's rows are 32*wq .. 32*wq+31, so
+        // g < wq: every lj < li -> "hi" block; g > wq: "lo" block; g == wq: per element  (warp-uniform)
+        if (g != wq) {
+          const uint32_t base = g < wq ? hi_base : lo_base;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int chunk = 2 * g + c;   // 32-key chunk of the tile; this warp's rows are 32*wq .. 32*wq+31
-          // chunk < wq: every lj < li -> "hi" block; chunk > wq: "lo" block; chunk == wq: per element
-          const uint32_t base = chunk < wq ? hi_base : lo_base;
-          const bool diag = chunk == wq;
+          for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]) + lds_f16(base - 2 * (g * 32 + e));
+        } else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
-            const int lj = chunk * 32 + e;
-            const uint32_t src = (diag && lj < li) ? hi_base : base;
-            s[c * 32 + e] = __uint_as_float(c == 0 ? r0[e] : r1[e]) + lds_f16(src - 2 * lj);
+            const int lj = g * 32 + e;
+            s[e] = __uint_as_float(r0[e]) + lds_f16((lj < li ? hi_base : lo_base) - 2 * lj);
           }
         }
       }
-      if (!(jc0 + 63 <= hi_i && jc0 >= lo_i)) {   // boundary tile: analytic mask
+      if (!(jc0 + CPT - 1 <= hi_i && jc0 >= lo_i)) {   // boundary tile: analytic mask
 #pragma unroll
-        for (int e = 0; e < 64; ++e) {
+        for (int e = 0; e < CPT; ++e) {
           const int j = jc0 + e;
           if (j > hi_i || j < lo_i) s[e] = -INFINITY;
         }
       }
       float mx = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 64; ++e) mx = fmaxf(mx, s[e]);
+      for (int e = 0; e < CPT; ++e) mx = fmaxf(mx, s[e]);
       sm.xch[g][li] = mx;
-      named_bar(2, 256);
-      mx = fmaxf(fmaxf(mx, sm.xch[g ^ 1][li]) * sl2, m_run);
+      named_bar(2, SOFT);
+      mx = fmaxf(fmaxf(sm.xch[0][li], sm.xch[1][li]), fmaxf(sm.xch[2][li], sm.xch[3][li]));
+      mx = fmaxf(mx * sl2, m_run);
       const float msafe = mx == -INFINITY ? 0.f : mx;
       const float corr = ex2(m_run - msafe);
       m_run = mx;
       float rsum = 0.f;
-      uint32_t pk[32];
+      uint32_t pk[CPT / 2];
 #pragma unroll
-      for (int e = 0; e < 64; e += 2) {
+      for (int e = 0; e < CPT; e += 2) {
         const float p0 = ex2(fmaf(s[e], sl2, -msafe)), p1 = ex2(fmaf(s[e + 1], sl2, -msafe));
         rsum += p0 + p1;
         pk[e / 2] = cb::pack_bf16(p0, p1);
@@ -319,17 +317,17 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       if (t > 0) {
         cb::mbar_wait(&sm.o_full, o_phase);
         cb::tc_fence_after();
-        uint32_t r[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_O + g * 32, r);
+        uint32_t r[OPT];
+        tmem_ld_32x32b_x16(lane_addr + COL_O + g * OPT, r);
         cb::tmem_ld_wait();
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.o_empty);
         o_phase ^= 1;
 #pragma unroll
-        for (int e = 0; e < 32; ++e) o[e] = (o[e] + __uint_as_float(r[e])) * corr;
+        for (int e = 0; e < OPT; ++e) o[e] = (o[e] + __uint_as_float(r[e])) * corr;
       }
-      // ---- P(t) -> TMEM (bf16 pairs; this thread's 64 keys = 32 columns) ----
-      tmem_st_32x32b_x32(lane_addr + COL_P + g * 32, pk);
+      // ---- P(t) -> TMEM (bf16 pairs; this thread's 32 keys = 16 columns) ----
+      tmem_st_32x32b_x16(lane_addr + COL_P + g * (CPT / 2), pk);
       tmem_st_wait();
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.p_full);
@@ -338,23 +336,23 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     cb::mbar_wait(&sm.o_full, o_phase);
     cb::tc_fence_after();
     {
-      uint32_t r[32];
-      cb::tmem_ld_32x32b_x32(lane_addr + COL_O + g * 32, r);
+      uint32_t r[OPT];
+      tmem_ld_32x32b_x16(lane_addr + COL_O + g * OPT, r);
       cb::tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) o[e] += __uint_as_float(r[e]);
+      for (int e = 0; e < OPT; ++e) o[e] += __uint_as_float(r[e]);
     }
     cb::tc_fence_before();
     cb::mbar_arrive(&sm.o_empty);
-    // ---- finalize: the two column halves add their partial sums ----
+    // ---- finalize: the column quarters add their partial sums ----
     sm.xsum[g][li] = l_run;
-    named_bar(2, 256);
-    const float l_tot = l_run + sm.xsum[g ^ 1][li];
+    named_bar(2, SOFT);
+    const float l_tot = (sm.xsum[0][li] + sm.xsum[1][li]) + (sm.xsum[2][li] + sm.xsum[3][li]);
     if (i < p.T) {
       const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
-      bf16* orow = p.out + ((long long)i * p.B + b) * p.ldo + h * DH + g * 32;
+      bf16* orow = p.out + ((long long)i * p.B + b) * p.ldo + h * DH + g * OPT;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < OPT / 8; ++ch) {
         uint4 q;
         q.x = cb::pack_bf16(o[ch * 8 + 0] * inv, o[ch * 8 + 1] * inv);
         q.y = cb::pack_bf16(o[ch * 8 + 2] * inv, o[ch * 8 + 3] * inv);

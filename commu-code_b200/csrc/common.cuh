@@ -66,17 +66,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// slow path kept out of line so that the many inlined waits stay a handful of instructions each
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
   long long t0 = clock64();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity), "r"(0x989680u)
+        : "memory");
+    if (ok) return;
     if ((++spins & 0x3FF) == 0 && clock64() - t0 > COMMU_WATCHDOG_CYCLES) {
       printf("commu_b200: mbarrier watchdog fired (block %d,%d,%d thread %d)\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(smem_u32(bar), parity);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -138,7 +138,8 @@ template <typename CT>
 __global__ void __launch_bounds__(DA_WARPS * 32) decode_attn_kernel(
     const float* __restrict__ q, const CT* __restrict__ kc, const CT* __restrict__ vc,
     const CT* __restrict__ rt, const float* __restrict__ u, const float* __restrict__ vb, int H, int C,
-    int n_vis, int cur_slot, float scale, float* __restrict__ out, long long ldo, const int* __restrict__ dstate) {
+    int n_vis, int cur_slot, float scale, float* __restrict__ out, long long ldo, const int* __restrict__ dstate,
+    bf16* __restrict__ out_bf16) {
   __shared__ float sh_m[DA_WARPS], sh_l[DA_WARPS], sh_o[DA_WARPS][64];
   if (dstate) {
     cur_slot = dstate[0];
@@ -234,6 +235,7 @@ __global__ void __launch_bounds__(DA_WARPS * 32) decode_attn_kernel(
       oo += sh_o[w][threadIdx.x] * c;
     }
     out[(long long)b * ldo + h * 64 + threadIdx.x] = oo / ll;
+    if (out_bf16) out_bf16[(long long)b * ldo + h * 64 + threadIdx.x] = __float2bfloat16_rn(oo / ll);
   }
 }
 
@@ -445,7 +447,7 @@ int commu_pad_heads(const float* src, int64_t ld_src, int col_off, int rows, int
 // The n_vis most recent ring entries (ages 0..n_vis-1, age 0 at slot cur_slot) are attended.
 int commu_decode_attn(const float* q, const void* kcache, const void* vcache, const void* rtab, int cache_bf16,
                       const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
-                      float scale, float* out, int64_t ldo, const int* dev_state, void* stream) {
+                      float scale, float* out, int64_t ldo, const int* dev_state, void* out_bf16, void* stream) {
   CB_REQUIRE(q && kcache && vcache && rtab && out, "decode_attn: null arg");
   CB_REQUIRE(dev_state || (n_vis >= 1 && n_vis <= C && cur_slot >= 0 && cur_slot < C),
              "decode_attn: bad args (n_vis=%d C=%d slot=%d)", n_vis, C, cur_slot);
@@ -454,10 +456,10 @@ int commu_decode_attn(const float* q, const void* kcache, const void* vcache, co
   dim3 grid(H, B);
   if (cache_bf16)
     decode_attn_kernel<bf16><<<grid, DA_WARPS * 32, 0, s>>>(q, (const bf16*)kcache, (const bf16*)vcache, (const bf16*)rtab,
-                                                            r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo, dev_state);
+                                                            r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo, dev_state, (bf16*)out_bf16);
   else
     decode_attn_kernel<float><<<grid, DA_WARPS * 32, 0, s>>>(q, (const float*)kcache, (const float*)vcache, (const float*)rtab,
-                                                             r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo, dev_state);
+                                                             r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo, dev_state, (bf16*)out_bf16);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

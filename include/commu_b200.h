@@ -206,10 +206,11 @@ int commu_pad_heads(const float* src, int64_t ld_src, int col_off, int rows, int
  * from it instead of the host arguments. */
 int commu_decode_advance(int* state, int C, int mem_len, int extra_visible, void* stream);
 /* Single-query relative attention over the projected K/V ring cache [B,H,C,64]: ages 0..n_vis-1
- * (age 0 at ring slot cur_slot) with score_a = scale*((q+r_w_bias).k_a + (q+r_r_bias).R[a]). */
+ * (age 0 at ring slot cur_slot) with score_a = scale*((q+r_w_bias).k_a + (q+r_r_bias).R[a]).
+ * out_bf16 (optional, same leading dim) receives a bf16 copy: the operand of the o_net GEMM. */
 int commu_decode_attn(const float* q, const void* kcache, const void* vcache, const void* rtab, int cache_bf16,
                       const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
-                      float scale, float* out, int64_t ldo, const int* dev_state, void* stream);
+                      float scale, float* out, int64_t ldo, const int* dev_state, void* out_bf16, void* stream);
 /* Sampler over B rows of raw logits (token 0 is never sampled, midi_inferrer.py:206/:220): temperature
  * (0 = greedy one-hot, :211-213), top-k (:224-226), top-p (new), wrong-token mask (:227-229),
  * renormalise (:230-231), counter-based multinomial draw (:234-237).  tokens and/or probs_out. */
