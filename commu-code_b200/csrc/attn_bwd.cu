@@ -517,6 +517,12 @@ __global__ void __launch_bounds__(NTHREADS, 2) relattn_bwd_dr_kernel(const Param
 namespace cb_host {
 int check_attn_common(const attn::Params& p, const char* who);
 }
+extern "C" int commu_relattn_bwd_dq_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
+                                       int64_t ldkv, const void* r, int64_t ldr, int kr,
+                                       const unsigned char* reset, int T, int M, int B, int H, int same_length,
+                                       int shift, float scale, const float* lse, const void* dout, int64_t lddo,
+                                       const float* delta, void* dq, int64_t lddq, float* du, float* dvb,
+                                       void* stream_);
 extern "C" int commu_relattn_bwd_dkv_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
                                         int64_t ldkv, const void* r, int64_t ldr, int kr,
                                         const unsigned char* reset, int T, int M, int B, int H, int same_length,
@@ -569,7 +575,14 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
         (const bf16*)out, ldo, (const bf16*)dout, lddo, T, B, H, delta_ws);
   }
   const int Ktot = T + M;
-  relattn_bwd_dq_kernel<<<dim3(cb_host::ceil_div(T, attn::BM), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(p);
+  static const bool dq_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DQ"); return e && e[0] == 't'; }();
+  if (dq_tc) {
+    int rc3 = commu_relattn_bwd_dq_tc(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift, scale,
+                                      lse, dout, lddo, delta_ws, dq, lddq, du, dvb, stream_);
+    if (rc3) return rc3;
+  } else {
+    relattn_bwd_dq_kernel<<<dim3(cb_host::ceil_div(T, attn::BM), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(p);
+  }
   // dk / dv pass: tcgen05 kernel (default), or the warp-MMA pass with COMMU_ATTN_BWD_DKV=v1
   static const bool dkv_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DKV"); return !(e && e[0] == 'v'); }();
   if (dkv_tc) {

@@ -29,7 +29,9 @@ using attn::key_lo;
 using namespace attn_tc;
 
 constexpr int TM = 128, TN = 128, DH = 64;
-constexpr int NTHREADS = 384;
+constexpr int NWG = 4;
+constexpr int SOFT = 128 * NWG;
+constexpr int NTHREADS = 128 + SOFT;
 constexpr int TILE_BYTES = 128 * DH * 2;      // 16 KB
 constexpr int STAGE_ROW = 272;                // one staged fp16 BD block row (256 B + 16 pad)
 constexpr int COL_S = 0, COL_DP = 128, COL_BD = 256, COL_DV = 384, COL_DK = 448;
@@ -75,9 +77,9 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
     cb::mbar_init(&sm.kv_full, 1);
     cb::mbar_init(&sm.q_full, 1); cb::mbar_init(&sm.q_empty, 1);
     for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1); }
-    cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_empty, 256);
-    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, 256);
-    cb::mbar_init(&sm.pds_full, 256); cb::mbar_init(&sm.pds_empty, 1);
+    cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_empty, SOFT);
+    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
+    cb::mbar_init(&sm.pds_full, SOFT); cb::mbar_init(&sm.pds_empty, 1);
     cb::mbar_init(&sm.acc_full, 1);
     cb::fence_barrier_init();
   }
@@ -182,6 +184,7 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
     }
   } else if (warp >= 4) {
     // ============================== softmax warpgroups ==============================
+    // thread = (query row li of the tile, 32-key chunk g)
     const int g = (warp - 4) >> 2;
     const int wq = (warp - 4) & 3;
     const int li = wq * 32 + lane;               // query row inside the tile == TMEM lane
@@ -198,125 +201,89 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
       const float delta = i < p.T ? del_p[i] : 0.f;
       const int hi_i = i < p.T ? i + p.M : -1;
       const int lo_i = key_lo(i, p.M, p.same_length, p.shift, reset);
-      // ---- scores of this thread's 64 key columns ----
+      // ---- scores of this thread's 32 key columns ----
       cb::mbar_wait(&sm.s_full, s_phase);
       cb::tc_fence_after();
-      float s[64];
+      float s[32];
       {
-        uint32_t r0[32], r1[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + g * 64, r0);
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + g * 64 + 32, r1);
+        uint32_t r0[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + g * 32, r0);
         cb::tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          s[e] = __uint_as_float(r0[e]);
-          s[32 + e] = __uint_as_float(r1[e]);
-        }
+        for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]);
       }
       // ---- relative shift, one 128-distance block at a time: pass 0 = "lo" (keys lj >= li), pass 1 = "hi" ----
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        cb::mbar_wait(&sm.bd_full, bd_phase);
-        cb::tc_fence_after();
-        {
-          uint32_t r0[32], r1[32];
-          cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 64, r0);
-          cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 64 + 32, r1);
-          cb::tmem_ld_wait();
-          cb::tc_fence_before();
-          cb::mbar_arrive(&sm.bd_empty);
-          bd_phase ^= 1;
-          named_bar(1, 256);   // everyone finished reading the previously staged block
-          const uint32_t dst = my_row + g * 128;
-#pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            sts_v4(dst + e * 2, pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1])),
-                   pack_f16(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3])),
-                   pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
-                   pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
-            sts_v4(dst + 64 + e * 2, pack_f16(__uint_as_float(r1[e]), __uint_as_float(r1[e + 1])),
-                   pack_f16(__uint_as_float(r1[e + 2]), __uint_as_float(r1[e + 3])),
-                   pack_f16(__uint_as_float(r1[e + 4]), __uint_as_float(r1[e + 5])),
-                   pack_f16(__uint_as_float(r1[e + 6]), __uint_as_float(r1[e + 7])));
-          }
-        }
-        named_bar(2, 256);   // both column halves of the staged block are visible
-        // band column of key lj: idx = li + 127 - lj; "lo" holds idx < 128 (lj >= li), "hi" holds idx - 128
-        const uint32_t base = pass == 0 ? my_row + 2 * (li + TN - 1) : my_row + 2 * (li - 1);
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const int chunk = 2 * g + c;
-          const bool all = pass == 0 ? chunk > wq : chunk < wq;    // warp-uniform
-          if (all) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) s[c * 32 + e] += lds_f16(base - 2 * (chunk * 32 + e));
-          } else if (chunk == wq) {                                // diagonal chunk: per element
-#pragma unroll
-            for (int e = 0; e < 32; ++e) {
-              const int lj = chunk * 32 + e;
-              const bool use = pass == 0 ? lj >= li : lj < li;
-              const float bdv = lds_f16(use ? base - 2 * lj : my_row);
-              if (use) s[c * 32 + e] += bdv;
-            }
-          }
-        }
-      }
+      cb::mbar_wait(&sm.bd_full, bd_phase);
+      cb::tc_fence_after();
+      named_bar(1, SOFT);                       // everyone finished reading the previously staged block
+      stage32(lane_addr + COL_BD + g * 32, my_row + g * 64);
+      cb::tc_fence_before();
+      cb::mbar_arrive(&sm.bd_empty);
+      bd_phase ^= 1;
+      named_bar(2, SOFT);                       // the whole staged block is visible
+      band_add<0, true>(s, my_row, li, g, wq);
+      cb::mbar_wait(&sm.bd_full, bd_phase);
+      cb::tc_fence_after();
+      named_bar(1, SOFT);
+      stage32(lane_addr + COL_BD + g * 32, my_row + g * 64);
+      cb::tc_fence_before();
+      cb::mbar_arrive(&sm.bd_empty);
+      bd_phase ^= 1;
+      named_bar(2, SOFT);
+      band_add<1, true>(s, my_row, li, g, wq);
       // ---- P = exp2(score*log2e - LSE), dS = P * (dP - Delta)  (the 1/sqrt(Dh) factor is applied to dK at the end)
-      const int jc0 = j0 + g * 64;
-      const bool full = (jc0 + 63 <= hi_i) && (jc0 >= lo_i);
-      uint32_t pk[32], dsk[32];
+      const int jc0 = j0 + g * 32;
+      const bool full = (jc0 + 31 <= hi_i) && (jc0 >= lo_i);
+      uint32_t pk[16], dsk[16];
       {
-        uint32_t r0[32], r1[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_DP + g * 64, r0);
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_DP + g * 64 + 32, r1);
+        uint32_t r0[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_DP + g * 32, r0);
         cb::tmem_ld_wait();
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.s_empty);
         s_phase ^= 1;
 #pragma unroll
-        for (int e = 0; e < 64; e += 2) {
+        for (int e = 0; e < 32; e += 2) {
           float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
           if (!full) {
             const int j = jc0 + e;
             if (j > hi_i || j < lo_i) p0 = 0.f;
             if (j + 1 > hi_i || j + 1 < lo_i) p1 = 0.f;
           }
-          const float dp0 = __uint_as_float(e < 32 ? r0[e] : r1[e - 32]);
-          const float dp1 = __uint_as_float(e < 32 ? r0[e + 1] : r1[e - 31]);
           pk[e / 2] = cb::pack_bf16(p0, p1);
-          dsk[e / 2] = cb::pack_bf16(p0 * (dp0 - delta), p1 * (dp1 - delta));
+          dsk[e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
         }
       }
-      // ---- rows of the P / dS tiles: key atom g, query row li, 8 swizzled 16-byte chunks ----
+      // ---- rows of the P / dS tiles: key atom g/2, query row li, chunks 4*(g&1) .. +3 (swizzled) ----
       cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
       {
-        const uint32_t prow = cb::smem_u32(sm.p) + g * TILE_BYTES;
-        const uint32_t drow = cb::smem_u32(sm.ds) + g * TILE_BYTES;
+        const uint32_t prow = cb::smem_u32(sm.p) + (g >> 1) * TILE_BYTES;
+        const uint32_t drow = cb::smem_u32(sm.ds) + (g >> 1) * TILE_BYTES;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const uint32_t off = attn::swz(li, ch);
-          sts_v4(prow + off, pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
-          sts_v4(drow + off, dsk[ch * 4], dsk[ch * 4 + 1], dsk[ch * 4 + 2], dsk[ch * 4 + 3]);
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const uint32_t off = attn::swz(li, (g & 1) * 4 + c4);
+          sts_v4(prow + off, pk[c4 * 4], pk[c4 * 4 + 1], pk[c4 * 4 + 2], pk[c4 * 4 + 3]);
+          sts_v4(drow + off, dsk[c4 * 4], dsk[c4 * 4 + 1], dsk[c4 * 4 + 2], dsk[c4 * 4 + 3]);
         }
       }
       cb::fence_proxy_async();
       cb::mbar_arrive(&sm.pds_full);
       pds_phase ^= 1;
     }
-    // ---- epilogue: dV, dK rows (thread = key row li, 32 of the 64 head dims) ----
+    // ---- epilogue: dV, dK rows (thread = key row li, 16 of the 64 head dims) ----
     const int j = j0 + li;
+    bf16* dvr = dv_out + ((long long)j * p.B + b) * lddkv + h * DH + g * 16;
+    bf16* dkr = dk_out + ((long long)j * p.B + b) * lddkv + h * DH + g * 16;
     if (nq > 0) {
       cb::mbar_wait(&sm.acc_full, 0);
       cb::tc_fence_after();
-      uint32_t rv[32], rk[32];
-      cb::tmem_ld_32x32b_x32(lane_addr + COL_DV + g * 32, rv);
-      cb::tmem_ld_32x32b_x32(lane_addr + COL_DK + g * 32, rk);
+      uint32_t rv[16], rk[16];
+      tmem_ld_32x32b_x16(lane_addr + COL_DV + g * 16, rv);
+      tmem_ld_32x32b_x16(lane_addr + COL_DK + g * 16, rk);
       cb::tmem_ld_wait();
       if (j < Ktot) {
-        bf16* dvr = dv_out + ((long long)j * p.B + b) * lddkv + h * DH + g * 32;
-        bf16* dkr = dk_out + ((long long)j * p.B + b) * lddkv + h * DH + g * 32;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
+        for (int ch = 0; ch < 2; ++ch) {
           uint4 a, c2;
           a.x = cb::pack_bf16(__uint_as_float(rv[ch * 8 + 0]), __uint_as_float(rv[ch * 8 + 1]));
           a.y = cb::pack_bf16(__uint_as_float(rv[ch * 8 + 2]), __uint_as_float(rv[ch * 8 + 3]));
@@ -331,10 +298,8 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         }
       }
     } else if (j < Ktot) {   // nothing attends to these keys: zero gradients
-      bf16* dvr = dv_out + ((long long)j * p.B + b) * lddkv + h * DH + g * 32;
-      bf16* dkr = dk_out + ((long long)j * p.B + b) * lddkv + h * DH + g * 32;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
+      for (int ch = 0; ch < 2; ++ch) {
         *reinterpret_cast<uint4*>(dvr + ch * 8) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(dkr + ch * 8) = make_uint4(0, 0, 0, 0);
       }

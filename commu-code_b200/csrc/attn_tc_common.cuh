@@ -74,6 +74,44 @@ __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- shear helpers for a thread that owns (tile row li, 32-column chunk g); wq = li / 32 ----
+// TMEM block columns [g*32, g*32+32) of this thread's lane -> fp16 at dst (64 bytes of its staging row)
+__device__ __forceinline__ void stage32(uint32_t taddr, uint32_t dst) {
+  uint32_t r0[32];
+  cb::tmem_ld_32x32b_x32(taddr, r0);
+  cb::tmem_ld_wait();
+#pragma unroll
+  for (int e = 0; e < 32; e += 8)
+    sts_v4(dst + e * 2, pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1])),
+           pack_f16(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3])),
+           pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
+           pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
+}
+// s[e] (+)= band value of tile column lc = 32g + e, read from ONE staged 128-wide block at `row`
+// (row = this thread's staging row).  Band column of lc is li + 127 - lc: PASS 0 = "lo" block
+// (holds lc >= li at index li+127-lc), PASS 1 = "hi" block (holds lc < li at index li-1-lc).
+// Which block a chunk needs is warp-uniform except on the diagonal chunk g == wq.
+template <int PASS, bool ACCUM>
+__device__ __forceinline__ void band_add(float (&s)[32], uint32_t row, int li, int g, int wq) {
+  const uint32_t base = PASS == 0 ? row + 2 * (li + 127) : row + 2 * (li - 1);
+  const bool all = PASS == 0 ? g > wq : g < wq;
+  if (all) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const float v = lds_f16(base - 2 * (g * 32 + e));
+      s[e] = ACCUM ? s[e] + v : v;
+    }
+  } else if (g == wq) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int lc = g * 32 + e;
+      const bool use = PASS == 0 ? lc >= li : lc < li;
+      const float v = lds_f16(use ? base - 2 * lc : row);
+      if (use) s[e] = ACCUM ? s[e] + v : v;
+    }
+  }
+}
+
 struct Ring {  // stage / parity bookkeeping of a 2-deep mbarrier ring
   int idx = 0;
   uint32_t phase = 0;

@@ -167,6 +167,14 @@ int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, const void* k
                       void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, float* dr, float* du,
                       float* dvb, void* stream);
 
+/* dq / d r_w_bias / d r_r_bias pass of commu_relattn_bwd on tcgen05 tensor cores (dS fed to the dq MMA
+ * from TMEM, the inverse relative shift written as a band tile in shared memory).  Selected inside
+ * commu_relattn_bwd with COMMU_ATTN_BWD_DQ=tc. */
+int commu_relattn_bwd_dq_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
+                            int64_t ldkv, const void* r, int64_t ldr, int kr, const unsigned char* reset,
+                            int T, int M, int B, int H, int same_length, int shift, float scale,
+                            const float* lse, const void* dout, int64_t lddo, const float* delta, void* dq,
+                            int64_t lddq, float* du, float* dvb, void* stream);
 /* dk / dv pass of commu_relattn_bwd on tcgen05 tensor cores (TMA-staged tiles, TMEM accumulators);
  * `delta` = rowsum(dO * O) [B,H,T] must already be computed.  commu_relattn_bwd dispatches here by
  * default (COMMU_ATTN_BWD_DKV=v1 selects the warp-MMA pass instead). */
