@@ -517,6 +517,11 @@ __global__ void __launch_bounds__(NTHREADS, 2) relattn_bwd_dr_kernel(const Param
 namespace cb_host {
 int check_attn_common(const attn::Params& p, const char* who);
 }
+extern "C" int commu_relattn_bwd_dr_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
+                                       int64_t ldkv, const void* r, int64_t ldr, int kr,
+                                       const unsigned char* reset, int T, int M, int B, int H, int same_length,
+                                       int shift, float scale, const float* lse, const void* dout, int64_t lddo,
+                                       const float* delta, float* dr, void* stream_);
 extern "C" int commu_relattn_bwd_dq_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
                                        int64_t ldkv, const void* r, int64_t ldr, int kr,
                                        const unsigned char* reset, int T, int M, int B, int H, int same_length,
@@ -575,7 +580,7 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
         (const bf16*)out, ldo, (const bf16*)dout, lddo, T, B, H, delta_ws);
   }
   const int Ktot = T + M;
-  static const bool dq_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DQ"); return e && e[0] == 't'; }();
+  static const bool dq_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DQ"); return !(e && e[0] == 'v'); }();
   if (dq_tc) {
     int rc3 = commu_relattn_bwd_dq_tc(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift, scale,
                                       lse, dout, lddo, delta_ws, dq, lddq, du, dvb, stream_);
@@ -593,7 +598,14 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
     relattn_bwd_dkv_kernel<<<dim3(cb_host::ceil_div(Ktot, attn::BN), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(
         p, (bf16*)dk, (bf16*)dv, lddkv);
   }
-  relattn_bwd_dr_kernel<<<dim3(cb_host::ceil_div(Ktot, attn::BN), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(p);
+  static const bool dr_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DR"); return !(e && e[0] == 'v'); }();
+  if (dr_tc) {
+    int rc4 = commu_relattn_bwd_dr_tc(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift, scale,
+                                      lse, dout, lddo, delta_ws, dr, stream_);
+    if (rc4) return rc4;
+  } else {
+    relattn_bwd_dr_kernel<<<dim3(cb_host::ceil_div(Ktot, attn::BN), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(p);
+  }
   cb_host::count_launch(4);
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

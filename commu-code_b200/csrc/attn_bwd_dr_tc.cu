@@ -1,0 +1,312 @@
+// Relative-position attention backward on tcgen05 tensor cores: the dR pass (diagonal walk).
+//
+// One CTA = 128 distances d0 .. d0+127 of one (batch, head); it walks the query tiles, i.e. it follows the
+// diagonal band j = i + M - delta of the score matrix, so the gradient of R (shared by every query and
+// batch element) accumulates in TMEM and is added to global memory once per CTA.
+// In (query, distance) coordinates the roles of K/V and R swap with respect to the other kernels:
+//     S'   = (q+v) R_tile^T               natural                         [128 q x 128 distances]
+//     AC   = (q+u) Kwin^T  (two 128-key blocks of the key window, read through the relative shift)
+//     dP   = dO    Vwin^T  (same two blocks of the value window, read through the relative shift)
+//     dR  += dS'^T (q+v)                  A = dS' tile written by the softmax threads (MN-major)
+// Window of query tile i0: keys jw0 .. jw0+255 with jw0 = i0 + M - d0 - 127; consecutive query tiles
+// share one 128-key block, which stays in shared memory.
+//
+// Autograd counterpart of commu/model/model.py:312-345 for d(r_head_k) (then d r_net.weight by a GEMM).
+#include "api_common.h"
+#include "attn_common.cuh"
+#include "attn_tc_common.cuh"
+
+namespace cb_host {
+int check_attn_common(const attn::Params& p, const char* who);
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer);
+}
+
+namespace {
+using attn::Params;
+using attn::key_lo;
+using namespace attn_tc;
+
+constexpr int TM = 128, TN = 128, DH = 64;
+constexpr int NWG = 4;
+constexpr int SOFT = 128 * NWG;
+constexpr int NTHREADS = 128 + SOFT;
+constexpr int TILE_BYTES = 128 * DH * 2;
+constexpr int STAGE_ROW = 272;
+constexpr int COL_S = 0, COL_BAND = 128, COL_DR = 256;
+
+struct Smem {
+  uint8_t r[TILE_BYTES];
+  uint8_t qu[TILE_BYTES];
+  uint8_t qv[TILE_BYTES];
+  uint8_t dout[TILE_BYTES];
+  uint8_t k[2][TILE_BYTES];
+  uint8_t v[2][TILE_BYTES];
+  uint8_t ds[2 * TILE_BYTES];   // [2 distance atoms][128 q rows][128 B]
+  uint8_t bd[TM * STAGE_ROW];
+  uint64_t r_full, q_full, q_empty, kv_full[2], kv_empty[2];
+  uint64_t s_full, s_empty, bd_full, bd_empty, pds_full, pds_empty, acc_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                         const __grid_constant__ CUtensorMap tm_qu, const __grid_constant__ CUtensorMap tm_qv,
+                         const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_r,
+                         const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int d0 = blockIdx.x * TN;
+  const bool reset = p.reset && p.reset[b];
+  // queries that own a visible key at some distance of this tile: j = i + M - delta >= lo(i) >= 0
+  int i_min = max(0, d0 - p.M);
+  if (reset) i_min = max(i_min, d0);
+  bool any = i_min < p.T;
+  if (p.same_length && d0 >= p.M + p.shift) any = false;
+  const int it_first = i_min / TM;
+  const int nq = any ? ((p.T - 1) / TM - it_first + 1) : 0;
+  // key block kappa covers keys [jw00 + 128*kappa, +128), jw00 = window start of the first query tile
+  const int jw00 = it_first * TM + p.M - d0 - (TN - 1);
+
+  if (threadIdx.x == 0) {
+    cb::mbar_init(&sm.r_full, 1);
+    cb::mbar_init(&sm.q_full, 1); cb::mbar_init(&sm.q_empty, 1);
+    for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.kv_full[s], 1); cb::mbar_init(&sm.kv_empty[s], 1); }
+    cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_empty, SOFT);
+    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
+    cb::mbar_init(&sm.pds_full, SOFT); cb::mbar_init(&sm.pds_empty, 1);
+    cb::mbar_init(&sm.acc_full, 1);
+    cb::fence_barrier_init();
+  }
+  if (warp == 2) {
+    cb::tmem_alloc(&sm.tmem_base, 512);
+    cb::tmem_relinquish();
+  }
+  cb::tc_fence_before();
+  __syncthreads();
+  cb::tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (cb::elect_one() && nq > 0) {
+      cb::mbar_arrive_expect_tx(&sm.r_full, TILE_BYTES);
+      cb::tma_load_2d(sm.r, &tm_r, &sm.r_full, h * DH, d0);
+      auto load_kv = [&](int kappa) {   // buffer kappa&1, its (kappa>>1)-th use
+        const int bi = kappa & 1;
+        const uint32_t use = (kappa >> 1) & 1;
+        cb::mbar_wait(&sm.kv_empty[bi], use ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.kv_full[bi], 2 * TILE_BYTES);
+        cb::tma_load_3d(sm.k[bi], &tm_k, &sm.kv_full[bi], h * DH, b, jw00 + TN * kappa);
+        cb::tma_load_3d(sm.v[bi], &tm_v, &sm.kv_full[bi], h * DH, b, jw00 + TN * kappa);
+      };
+      uint32_t q_phase = 0;
+      load_kv(0);
+      for (int n = 0; n < nq; ++n) {
+        const int i0 = (it_first + n) * TM;
+        cb::mbar_wait(&sm.q_empty, q_phase ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.q_full, 3 * TILE_BYTES);
+        cb::tma_load_3d(sm.qu, &tm_qu, &sm.q_full, h * DH, b, i0);
+        cb::tma_load_3d(sm.qv, &tm_qv, &sm.q_full, h * DH, b, i0);
+        cb::tma_load_3d(sm.dout, &tm_do, &sm.q_full, h * DH, b, i0);
+        q_phase ^= 1;
+        load_kv(n + 1);
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ==============================
+    if (cb::elect_one() && nq > 0) {
+      const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);
+      const uint32_t idesc_g = cb::umma_idesc_bf16(TN, DH, 1, 1);   // dR: MN-major A (dS'^T), MN-major B (q+v)
+      uint32_t q_phase = 0, s_phase = 0, bd_phase = 0, pds_phase = 0;
+      const uint32_t a_qu = cb::smem_u32(sm.qu), a_qv = cb::smem_u32(sm.qv), a_do = cb::smem_u32(sm.dout);
+      const uint32_t a_r = cb::smem_u32(sm.r);
+      cb::mbar_wait(&sm.r_full, 0);
+      auto issue_band = [&](uint32_t a_addr, uint32_t b_addr) {
+        cb::mbar_wait(&sm.bd_empty, bd_phase ^ 1);
+        cb::tc_fence_after();
+        const uint64_t ad = cb::umma_smem_desc(a_addr, 16, 1024);
+        const uint64_t bd = cb::umma_smem_desc(b_addr, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_BAND, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
+        cb::umma_commit(&sm.bd_full);
+        bd_phase ^= 1;
+      };
+      for (int n = 0; n < nq; ++n) {
+        const int lo_b = n & 1, hi_b = (n + 1) & 1;   // key blocks kappa = n ("lo") and n+1 ("hi")
+        cb::mbar_wait(&sm.q_full, q_phase);
+        cb::mbar_wait(&sm.s_empty, s_phase ^ 1);
+        cb::tc_fence_after();
+        {
+          const uint64_t aq = cb::umma_smem_desc(a_qv, 16, 1024), br = cb::umma_smem_desc(a_r, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_S, aq + 2 * k, br + 2 * k, idesc_s, k > 0);
+          cb::umma_commit(&sm.s_full);
+        }
+        cb::mbar_wait(&sm.kv_full[lo_b], (n >> 1) & 1);
+        issue_band(a_qu, cb::smem_u32(sm.k[lo_b]));          // AC "lo"
+        cb::mbar_wait(&sm.kv_full[hi_b], ((n + 1) >> 1) & 1);
+        issue_band(a_qu, cb::smem_u32(sm.k[hi_b]));          // AC "hi"
+        issue_band(a_do, cb::smem_u32(sm.v[lo_b]));          // dP "lo"
+        issue_band(a_do, cb::smem_u32(sm.v[hi_b]));          // dP "hi"
+        cb::umma_commit(&sm.kv_empty[lo_b]);                 // block kappa = n is dead after this tile
+        cb::mbar_wait(&sm.pds_full, pds_phase);
+        cb::tc_fence_after();
+        {
+          const uint64_t as = cb::umma_smem_desc(cb::smem_u32(sm.ds), TILE_BYTES, 1024);
+          const uint64_t bq = cb::umma_smem_desc(a_qv, 8192, 1024);
+#pragma unroll
+          for (int k = 0; k < TM / 16; ++k)
+            cb::umma_bf16_ss(tmem + COL_DR, as + (uint64_t)(k * 128), bq + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
+          cb::umma_commit(&sm.pds_empty);
+          cb::umma_commit(&sm.q_empty);
+        }
+        q_phase ^= 1;
+        s_phase ^= 1;
+        pds_phase ^= 1;
+      }
+      cb::umma_commit(&sm.acc_full);
+    }
+  } else if (warp >= 4) {
+    // ============================== softmax warpgroups ==============================
+    // thread = (query row li of the tile, 32-distance chunk g)
+    const int g = (warp - 4) >> 2;
+    const int wq = (warp - 4) & 3;
+    const int li = wq * 32 + lane;
+    const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
+    const uint32_t my_row = cb::smem_u32(sm.bd) + li * STAGE_ROW;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
+    const float* lse_p = p.lse + ((long long)b * p.H + h) * p.T;
+    const float* del_p = p.delta + ((long long)b * p.H + h) * p.T;
+
+    for (int n = 0; n < nq; ++n) {
+      const int i = (it_first + n) * TM + li;
+      const float lse2 = i < p.T ? lse_p[i] * 1.4426950408889634f : 0.f;
+      const float delta = i < p.T ? del_p[i] : 0.f;
+      const int lo_i = key_lo(i, p.M, p.same_length, p.shift, reset);
+      cb::mbar_wait(&sm.s_full, s_phase);
+      cb::tc_fence_after();
+      float s[32], dp[32];
+      {
+        uint32_t r0[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + g * 32, r0);
+        cb::tmem_ld_wait();
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.s_empty);
+        s_phase ^= 1;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          s[e] = __uint_as_float(r0[e]);
+          dp[e] = 0.f;
+        }
+      }
+      // four banded blocks, staged one at a time: AC lo, AC hi, dP lo, dP hi
+#pragma unroll
+      for (int blk = 0; blk < 4; ++blk) {
+        cb::mbar_wait(&sm.bd_full, bd_phase);
+        cb::tc_fence_after();
+        named_bar(1, SOFT);
+        stage32(lane_addr + COL_BAND + g * 32, my_row + g * 64);
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.bd_empty);
+        bd_phase ^= 1;
+        named_bar(2, SOFT);
+        if (blk == 0) band_add<0, true>(s, my_row, li, g, wq);
+        if (blk == 1) band_add<1, true>(s, my_row, li, g, wq);
+        if (blk == 2) band_add<0, true>(dp, my_row, li, g, wq);
+        if (blk == 3) band_add<1, true>(dp, my_row, li, g, wq);
+      }
+      // ---- P, dS' (columns are distances: key j = i + M - delta) ----
+      uint32_t dsk[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 2) {
+        const int dl = d0 + g * 32 + e;
+        const int j0k = i + p.M - dl;            // key of column e ; column e+1 is key j0k - 1
+        float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
+        if (i >= p.T || j0k < lo_i) p0 = 0.f;
+        if (i >= p.T || j0k - 1 < lo_i) p1 = 0.f;
+        dsk[e / 2] = cb::pack_bf16(p0 * (dp[e] - delta), p1 * (dp[e + 1] - delta));
+      }
+      cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
+      {
+        const uint32_t drow = cb::smem_u32(sm.ds) + (g >> 1) * TILE_BYTES;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)
+          sts_v4(drow + attn::swz(li, (g & 1) * 4 + c4), dsk[c4 * 4], dsk[c4 * 4 + 1], dsk[c4 * 4 + 2], dsk[c4 * 4 + 3]);
+      }
+      cb::fence_proxy_async();
+      cb::mbar_arrive(&sm.pds_full);
+      pds_phase ^= 1;
+    }
+    // ---- epilogue: dR rows (thread = distance row li, 16 of the 64 head dims), summed over batch with atomics ----
+    if (nq > 0) {
+      cb::mbar_wait(&sm.acc_full, 0);
+      cb::tc_fence_after();
+      uint32_t rr[16];
+      tmem_ld_32x32b_x16(lane_addr + COL_DR + g * 16, rr);
+      cb::tmem_ld_wait();
+      const int dl = d0 + li;
+      if (dl < p.Kr) {
+        float* dst = p.dr + (long long)dl * p.H * DH + h * DH + g * 16;
+#pragma unroll
+        for (int e = 0; e < 16; e += 4)
+          cb::red_add_v4(dst + e, __uint_as_float(rr[e]) * p.scale, __uint_as_float(rr[e + 1]) * p.scale,
+                         __uint_as_float(rr[e + 2]) * p.scale, __uint_as_float(rr[e + 3]) * p.scale);
+      }
+    }
+  }
+  cb::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    cb::tc_fence_after();
+    cb::tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+
+// dR of commu_relattn_bwd on tcgen05: dr fp32 [kr, H*64] accumulated (+=) over batch.  delta = rowsum(dO*O).
+extern "C" int commu_relattn_bwd_dr_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
+                                       int64_t ldkv, const void* r, int64_t ldr, int kr,
+                                       const unsigned char* reset, int T, int M, int B, int H, int same_length,
+                                       int shift, float scale, const float* lse, const void* dout, int64_t lddo,
+                                       const float* delta, float* dr, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  attn::Params p = {};
+  p.q = (const bf16*)qu; p.k = (const bf16*)k; p.v = (const bf16*)v; p.r = (const bf16*)r;
+  p.qu_s = (bf16*)const_cast<void*>(qu); p.qv_s = (bf16*)const_cast<void*>(qv);
+  static const float dummy = 0.f;
+  p.u = &dummy; p.vb = &dummy;
+  p.reset = reset;
+  p.ldq = ldq; p.ldkv = ldkv; p.ldr = ldr;
+  p.T = T; p.M = M; p.B = B; p.H = H; p.Kr = kr;
+  p.same_length = same_length; p.shift = shift; p.scale = scale;
+  p.lse = const_cast<float*>(lse); p.delta = delta;
+  p.dout = (const bf16*)dout; p.lddo = lddo;
+  p.dr = dr;
+  int rc = cb_host::check_attn_common(p, "relattn_bwd_dr_tc");
+  if (rc) return rc;
+  CB_REQUIRE(qv && lse && dout && delta && dr && lddo % 8 == 0, "relattn_bwd_dr_tc: bad args");
+  const int Ktot = T + M;
+  CUtensorMap tk, tv, tqu, tqv, tdo, tr;
+  if ((rc = make_tmap_rows3d(&tk, k, (uint64_t)H * 64, B, Ktot, ldkv))) return rc;
+  if ((rc = make_tmap_rows3d(&tv, v, (uint64_t)H * 64, B, Ktot, ldkv))) return rc;
+  if ((rc = make_tmap_rows3d(&tqu, qu, (uint64_t)H * 64, B, T, ldq))) return rc;
+  if ((rc = make_tmap_rows3d(&tqv, qv, (uint64_t)H * 64, B, T, ldq))) return rc;
+  if ((rc = make_tmap_rows3d(&tdo, dout, (uint64_t)H * 64, B, T, lddo))) return rc;
+  if ((rc = cb_host::make_tmap_bf16_2d(&tr, r, (uint64_t)H * 64, kr, ldr, 64, 128))) return rc;
+  static bool attr = false;
+  const int smem_bytes = (int)sizeof(Smem) + 1024;
+  if (!attr) {
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    attr = true;
+  }
+  dim3 grid(cb_host::ceil_div(Ktot, TN), H, B);
+  relattn_bwd_dr_tc_kernel<<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p);
+  cb_host::count_launch();
+  CB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -167,9 +167,17 @@ int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, const void* k
                       void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, float* dr, float* du,
                       float* dvb, void* stream);
 
+/* dR pass of commu_relattn_bwd on tcgen05 tensor cores (diagonal walk: one CTA per 128 distances, dR
+ * accumulated in TMEM, added to dr once per CTA).  Default dR pass of commu_relattn_bwd (COMMU_ATTN_BWD_DR=v1 selects the
+ * warp-MMA pass). */
+int commu_relattn_bwd_dr_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
+                            int64_t ldkv, const void* r, int64_t ldr, int kr, const unsigned char* reset,
+                            int T, int M, int B, int H, int same_length, int shift, float scale,
+                            const float* lse, const void* dout, int64_t lddo, const float* delta, float* dr,
+                            void* stream);
 /* dq / d r_w_bias / d r_r_bias pass of commu_relattn_bwd on tcgen05 tensor cores (dS fed to the dq MMA
- * from TMEM, the inverse relative shift written as a band tile in shared memory).  Selected inside
- * commu_relattn_bwd with COMMU_ATTN_BWD_DQ=tc. */
+ * from TMEM, the inverse relative shift written as a band tile in shared memory).  Default dq pass of
+ * commu_relattn_bwd (COMMU_ATTN_BWD_DQ=v1 selects the warp-MMA pass). */
 int commu_relattn_bwd_dq_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
                             int64_t ldkv, const void* r, int64_t ldr, int kr, const unsigned char* reset,
                             int T, int M, int B, int H, int same_length, int shift, float scale,
