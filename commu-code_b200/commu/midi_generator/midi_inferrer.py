@@ -8,12 +8,126 @@ Kept quirks: token 0 is never sampled (Q4); `calc_probs`
 logits by the temperature IN PLACE, so a re-used logits tensor is divided again (Q3); a sampling
 failure (all mass rejected) raises RuntimeError (Q5).
 """
+import math
 from typing import List, Tuple
 
 import torch
 
 from commu import _native as nv
 from commu.engine.decode import DecodeEngine, DecodeState
+from commu.preprocessor.encoder.event_tokens import TOKEN_OFFSET
+
+try:
+    from logger import logger
+except ImportError:  # pragma: no cover
+    import logging
+    logger = logging.getLogger("ComMU")
+
+_T = {k: v.value for k, v in TOKEN_OFFSET.__members__.items()}
+POSITION_RESOLUTION = 128   # commu/preprocessor/utils/constants.py:25
+
+
+class TeacherForceTask:
+    """Chord teacher forcing of the reference's generation loop (midi_inferrer.py:16-169), restated as a
+    queue of pending chords: every entry is (chord token, position token, is_inter) where is_inter marks a
+    chord that does not sit on the first position of a bar.  Public method names are the reference's,
+    because `generate_sequence` drives the task through them."""
+
+    def __init__(self, input_data):
+        self.input_data = input_data
+        self.next_tokens_forced: List[int] = []
+        self.wrong_tokens: List[int] = []
+        self.no_sequence_appended = False
+        self.is_incomplete = input_data.num_measures % 4 != 0
+        self.incomplete_filled = not self.is_incomplete
+        tokens, positions = input_data.chord_token_components.values()
+        assert len(tokens) == len(positions), "Wrong Chord Length"
+        self.pending = [(int(t), int(pos), int(pos) != _T["POSITION"]) for t, pos in zip(tokens, positions)]
+        self.chord_length = len(self.pending)
+
+    # views with the reference's attribute names
+    chord_token = property(lambda self: [c[0] for c in self.pending])
+    chord_position = property(lambda self: [c[1] for c in self.pending])
+    inter_chord_flags = property(lambda self: [c[2] for c in self.pending])
+
+    # ---- predicates -------------------------------------------------------------------------------
+    def check_remnant_chord(self):
+        return len(self.pending) > 0
+
+    def check_first_position(self, seq):
+        return self.incomplete_filled and seq[-1] == _T["BAR"]
+
+    def check_length_fit(self):
+        return self.chord_length == int(self.input_data.num_measures // 4 * 4)
+
+    def check_position_fit(self, seq):
+        return seq[-2] == _T["BAR"] and seq[-1] == _T["POSITION"]
+
+    def _chord_due(self, seq):
+        return self.check_remnant_chord() and self.incomplete_filled
+
+    def check_one_chord_per_bar_case(self, seq):
+        return self._chord_due(seq) and self.check_length_fit() and self.check_position_fit(seq)
+
+    def check_mul_chord_per_bar_case(self, seq):
+        if not self._chord_due(seq) or self.check_length_fit():
+            return False
+        if self.check_position_fit(seq):
+            return True
+        _, pos, inter = self.pending[0]
+        return seq[-1] == pos and inter
+
+    def check_chord_position_passed(self, token):
+        if not self.check_remnant_chord():
+            return False
+        _, pos, inter = self.pending[0]
+        passed = pos < token < _T["POSITION"] + POSITION_RESOLUTION or token == _T["BAR"]
+        return inter and passed
+
+    def check_wrong_chord_token_generated(self, token):
+        return _T["CHORD_START"] <= token <= _T["CHORD_END"]
+
+    def check_wrong_eos_generated(self, token):
+        return self.check_remnant_chord() and token == _T["EOS"]
+
+    def check_wrong_bar_token_generated(self, token):
+        return not self.check_remnant_chord() and token == _T["BAR"]
+
+    # ---- actions ----------------------------------------------------------------------------------
+    def teach_first_position(self):
+        self.next_tokens_forced.append(_T["POSITION"])
+
+    def teach_chord_token(self):
+        tok, _, _ = self.pending.pop(0)
+        self.next_tokens_forced.append(tok)
+        self.wrong_tokens = []
+
+    def teach_chord_position(self):
+        self.next_tokens_forced.append(self.pending[0][1])
+        self.wrong_tokens = []
+
+    def teach_wrong_chord_token(self, wrong_token):
+        self.no_sequence_appended = True
+        self.wrong_tokens.append(wrong_token)
+
+    def teach_remnant_chord(self):
+        _, pos, inter = self.pending[0]
+        self.next_tokens_forced.append(pos if inter else _T["BAR"])
+
+    def teach_eos(self):
+        self.next_tokens_forced.append(_T["EOS"])
+
+    def validate_teacher_forced_sequence(self, seq):
+        n_bars = seq.count(_T["BAR"])
+        n_chords = sum(1 for t in seq if _T["CHORD_START"] <= t <= _T["CHORD_END"])
+        if self.pending:
+            raise Exception(f"remnant chord length: {len(self.pending)} \nerror in teacher forcing")
+        if n_bars != int(math.ceil(self.input_data.num_measures)):
+            raise Exception(f"bar length: {n_bars} \nerror in bar length")
+        if n_chords != self.chord_length:
+            raise Exception(f"num_chord: {n_chords} vs {self.chord_length} \nerror in chord length")
+        logger.info(f"correct_length: {n_bars}")
+        logger.info(seq)
 
 
 class InferenceTask:
@@ -83,3 +197,84 @@ class InferenceTask:
         self._draws += 1
         nv.call("commu_sample", lg, V, 1, V, 1.0, 0, 0.0, None, self.seed, self._draws, tok, None, V, None)
         return int(tok.item())
+
+    # ------------------------------------------------------------------------------------------------
+    # host-side generation loop (reference midi_inferrer.py:239-354); quirks Q1-Q5 of SURVEY.md 3.2 kept
+    # ------------------------------------------------------------------------------------------------
+    def generate_sequence(self, seq, mems):
+        logits = None
+        teacher = TeacherForceTask(self.input_data)
+        first = True
+        for _ in range(self.inference_cfg.GENERATION.generation_length):
+            if seq[-1] == _T["EOS"]:
+                break
+            if teacher.next_tokens_forced:                       # forced tokens are fed right away (Q2)
+                seq.append(teacher.next_tokens_forced.pop(0))
+                logits, mems = self.calc_logits_and_mems(seq, mems)
+                continue
+            if teacher.no_sequence_appended:                     # rejected token: re-use the logits (Q3)
+                assert logits is not None
+                teacher.no_sequence_appended = False
+            elif first:                                          # the returned memory is dropped once (Q1)
+                logits, _ = self.calc_logits_and_mems(seq, mems)
+                first = False
+            else:
+                logits, mems = self.calc_logits_and_mems(seq, mems)
+            probs = self.apply_sampling(self.calc_probs(logits), teacher.wrong_tokens)
+            if not teacher.incomplete_filled:
+                teacher.incomplete_filled = seq.count(_T["BAR"]) > 1
+            if teacher.check_first_position(seq):
+                teacher.teach_first_position()
+                continue
+            if teacher.check_one_chord_per_bar_case(seq) or teacher.check_mul_chord_per_bar_case(seq):
+                teacher.teach_chord_token()
+                continue
+            try:
+                token = self.infer_token(probs)
+            except RuntimeError as e:
+                logger.error(f"Sampling Error: {e}")
+                seq = None
+                break
+            if teacher.check_chord_position_passed(token):
+                teacher.teach_chord_position()
+            elif teacher.check_wrong_chord_token_generated(token):
+                teacher.teach_wrong_chord_token(token)
+            elif teacher.check_wrong_eos_generated(token):
+                teacher.teach_remnant_chord()
+            elif teacher.check_wrong_bar_token_generated(token):
+                teacher.teach_eos()
+            else:
+                seq.append(token)
+        try:
+            teacher.validate_teacher_forced_sequence(seq)
+        except Exception as err:  # noqa: BLE001 - same catch-all as the reference
+            logger.error(err)
+            seq = None
+        return seq
+
+    def validate_generated_sequence(self, seq: List[int]) -> bool:
+        notes = 0
+        for k, tok in enumerate(seq):
+            if k + 2 > len(seq) - 1:
+                break
+            if _T["NOTE_VELOCITY"] <= tok < _T["CHORD_START"]:
+                if (_T["POSITION"] <= seq[k - 1] < _T["BPM"] and _T["PITCH"] <= seq[k + 1] < _T["NOTE_VELOCITY"]
+                        and _T["NOTE_DURATION"] <= seq[k + 2] < _T["POSITION"]):
+                    notes += 1
+        return notes > 0
+
+    def execute(self, encoded_meta) -> List[List[int]]:
+        n_cond = len(encoded_meta)
+        sequences = []
+        while len(sequences) != self.input_data.num_generate:
+            with torch.no_grad():
+                logger.info("Generating the idx: " + str(len(sequences) + 1))
+                seq, mems = self.init_seq_and_mems(encoded_meta, n_cond)
+                seq = self.generate_sequence(seq, mems)
+                if seq is None:
+                    continue
+                if not self.validate_generated_sequence(seq):
+                    logger.error("Empty sequence generated")
+                    continue
+            sequences.append(seq)
+        return sequences

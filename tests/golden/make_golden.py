@@ -255,6 +255,56 @@ def gen_dataset_case(name, seed):
     print("wrote", name)
 
 
+TEACHER_SCENARIOS = {
+    # name: (num_measures, chord tokens, chord positions, scripted "model wishes")
+    "one_per_bar": (4, [200, 210, 220, 230], [432, 432, 432, 432],
+                    [2, 440, 150, 60, 310, 2, 450, 140, 62, 320, 250, 2, 433, 160, 64, 330, 1, 2, 470, 135, 66, 340, 2, 1]),
+    "inter_chords": (4, [201, 211, 221, 231, 241, 251], [432, 496, 432, 432, 480, 432],
+                     [2, 440, 150, 60, 310, 500, 150, 61, 311, 2, 450, 140, 62, 320, 2, 260, 470, 160, 64, 330, 490, 2, 433, 135, 66, 340, 1, 2, 1]),
+    "incomplete": (5, [202, 212, 222, 232], [432, 432, 432, 432],
+                   [2, 436, 150, 60, 310, 2, 440, 150, 60, 310, 2, 450, 140, 62, 320, 2, 433, 160, 64, 330, 2, 470, 135, 66, 340, 2, 1]),
+}
+
+
+def fake_model_patch(task, script):
+    """Deterministic stand-in for the network + multinomial draw, shared by the golden generator and the
+    CPU test: logits favour the next scripted token (plus seeded noise); the draw is the arg-max."""
+    state = {"calls": 0, "ptr": 0}
+
+    def calc_logits_and_mems(seq, mems):
+        state["calls"] += 1
+        g = torch.Generator().manual_seed(1000 + state["calls"])
+        base = torch.randn(728, generator=g)
+        want = script[state["ptr"]] if state["ptr"] < len(script) else 1
+        base[want - 1] += 20.0
+        return base, (mems or 0) + 1
+
+    def infer_token(probs):
+        state["ptr"] += 1
+        return int(torch.argmax(probs))
+
+    task.calc_logits_and_mems = calc_logits_and_mems
+    task.infer_token = infer_token
+    return state
+
+
+def gen_teacher_case(name):
+    _stub_modules()
+    from commu.midi_generator.midi_inferrer import InferenceTask
+    out = {}
+    for sc, (nm, ctok, cpos, script) in TEACHER_SCENARIOS.items():
+        task = InferenceTask(torch.device("cpu"))
+        task.input_data = SimpleNamespace(num_measures=nm, temperature=0.95, top_k=32, num_generate=1,
+                                          chord_token_components={"chord_token": list(ctok), "chord_position": list(cpos)})
+        task.inference_cfg = SimpleNamespace(GENERATION=SimpleNamespace(generation_length=200))
+        fake_model_patch(task, script)
+        seq = task.generate_sequence([0, 574, 623, 627, 635, 639, 642, 651, 684, 694, 720, 727], 0)
+        out[sc] = np.array(seq if seq is not None else [-1], dtype=np.int64)
+        print(" teacher", sc, "->", None if seq is None else len(seq))
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def main():
     sys.path.insert(0, REF)
     torch.set_num_threads(4)
@@ -271,6 +321,7 @@ def main():
     gen_decode_case("decode_greedy", cfgC, n_token=97, B=2, n_ctx=6, n_new=40, seed=13, std=0.2)
     gen_sampler_case("sampler_probs", seed=14)
     gen_dataset_case("dataset_batches", seed=16)
+    gen_teacher_case("teacher_forcing")
     cfgE = dict(n_layer=2, n_head=2, d_model=32, d_inner=64, tgt_len=10, mem_len=10,
                 same_length=False, clamp_len=-1)
     gen_train_case("train_steps", cfgE, n_token=61, B=4, chunks=2, n_steps=6, seed=15, std=0.05,
