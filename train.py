@@ -40,6 +40,9 @@ def parse_args(argv=None):
     ap.add_argument("--work_dir", type=str, required=True, help="Base directory to save the trained model.")
     ap.add_argument("--opts", type=str, default="", help="config overrides: MODEL.num_layers=12,TRAIN.lr=0.001")
     ap.add_argument("--max_step", type=int, default=None)
+    ap.add_argument("--resume", type=str, default=None,
+                    help="checkpoint (.pt written by this script or by the reference) to continue from: model, "
+                         "Adam moments and step counter are restored (the reference only ever saves)")
     return ap.parse_args(argv)
 
 
@@ -170,6 +173,17 @@ def main(argv=None):
     logger.info("Start training")
 
     train_step, best_val = 0, np.inf
+    if args.resume:
+        ckpt = torch.load(args.resume, map_location=device, weights_only=False)   # pickled BaseVocab inside
+        model.load_state_dict(ckpt["model"], strict=False)
+        if ckpt.get("optimizer"):
+            trainer.load_optimizer_state_dict(ckpt["optimizer"])
+        train_step = int(ckpt.get("train_step", 0))
+        trainer.step = train_step
+        if ckpt.get("best_val_loss") is not None:
+            best_val = ckpt["best_val_loss"]
+        trainer.engine.refresh_shadow()
+        logger.info("Resumed from {} at step {}".format(args.resume, train_step))
     log_loss = torch.zeros((), device=device, dtype=torch.float64)
     log_gnorm = torch.zeros((), device=device, dtype=torch.float64)
     log_tok = 0
