@@ -534,6 +534,27 @@ extern "C" int commu_relattn_bwd_dkv_tc(const void* qu, const void* qv, int64_t 
                                         int shift, float scale, const float* lse, const void* dout, int64_t lddo,
                                         const float* delta, void* dk, void* dv, int64_t lddkv, void* stream_);
 
+namespace {
+// pass implementations: 1 = tcgen05 kernel, 0 = v1 warp-MMA kernel; -1 = not yet read from the environment
+int g_impl[3] = {-1, -1, -1};   // dq, dkv, dr
+int pass_impl(int which, const char* env) {
+  if (g_impl[which] < 0) {
+    const char* e = getenv(env);
+    g_impl[which] = (e && e[0] == 'v') ? 0 : 1;
+  }
+  return g_impl[which];
+}
+}  // namespace
+
+// Selects the implementation of each backward pass at run time (1 = tcgen05, 0 = v1 warp-MMA, <0 = keep).
+// Defaults come from COMMU_ATTN_BWD_{DQ,DKV,DR} (unset or "tc" = tcgen05, "v1" = warp-MMA).
+extern "C" int commu_relattn_bwd_set_impl(int dq_tc, int dkv_tc, int dr_tc) {
+  if (dq_tc >= 0) g_impl[0] = dq_tc ? 1 : 0;
+  if (dkv_tc >= 0) g_impl[1] = dkv_tc ? 1 : 0;
+  if (dr_tc >= 0) g_impl[2] = dr_tc ? 1 : 0;
+  return 0;
+}
+
 // Backward of commu_relattn_fwd.  Inputs are the forward's operands plus the saved (q+r_w_bias),
 // (q+r_r_bias) bf16 tensors (layout of q), the forward output `out`, its LSE and dout.
 //   dq   : bf16 [T*B, lddq]        (same column layout as q)
@@ -580,7 +601,7 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
         (const bf16*)out, ldo, (const bf16*)dout, lddo, T, B, H, delta_ws);
   }
   const int Ktot = T + M;
-  static const bool dq_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DQ"); return !(e && e[0] == 'v'); }();
+  const bool dq_tc = pass_impl(0, "COMMU_ATTN_BWD_DQ");
   if (dq_tc) {
     int rc3 = commu_relattn_bwd_dq_tc(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift, scale,
                                       lse, dout, lddo, delta_ws, dq, lddq, du, dvb, stream_);
@@ -589,7 +610,7 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
     relattn_bwd_dq_kernel<<<dim3(cb_host::ceil_div(T, attn::BM), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(p);
   }
   // dk / dv pass: tcgen05 kernel (default), or the warp-MMA pass with COMMU_ATTN_BWD_DKV=v1
-  static const bool dkv_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DKV"); return !(e && e[0] == 'v'); }();
+  const bool dkv_tc = pass_impl(1, "COMMU_ATTN_BWD_DKV");
   if (dkv_tc) {
     int rc2 = commu_relattn_bwd_dkv_tc(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift,
                                        scale, lse, dout, lddo, delta_ws, dk, dv, lddkv, stream_);
@@ -598,7 +619,7 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
     relattn_bwd_dkv_kernel<<<dim3(cb_host::ceil_div(Ktot, attn::BN), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(
         p, (bf16*)dk, (bf16*)dv, lddkv);
   }
-  static const bool dr_tc = [] { const char* e = getenv("COMMU_ATTN_BWD_DR"); return !(e && e[0] == 'v'); }();
+  const bool dr_tc = pass_impl(2, "COMMU_ATTN_BWD_DR");
   if (dr_tc) {
     int rc4 = commu_relattn_bwd_dr_tc(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift, scale,
                                       lse, dout, lddo, delta_ws, dr, stream_);

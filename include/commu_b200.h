@@ -167,6 +167,9 @@ int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, const void* k
                       void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, float* dr, float* du,
                       float* dvb, void* stream);
 
+/* Run-time choice of the implementation of each backward pass used by commu_relattn_bwd:
+ * 1 = tcgen05 kernel (default), 0 = v1 warp-MMA kernel, negative = leave unchanged. */
+int commu_relattn_bwd_set_impl(int dq_tc, int dkv_tc, int dr_tc);
 /* dR pass of commu_relattn_bwd on tcgen05 tensor cores (diagonal walk: one CTA per 128 distances, dR
  * accumulated in TMEM, added to dr once per CTA).  Default dR pass of commu_relattn_bwd (COMMU_ATTN_BWD_DR=v1 selects the
  * warp-MMA pass). */

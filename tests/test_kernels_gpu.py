@@ -80,9 +80,21 @@ def test_relattn_fwd(T, M, B, H, same_length, mem_len, with_reset, impl):
     assert lerr < 2e-3, lerr
 
 
-@pytest.mark.parametrize("T,M,B,H,same_length,mem_len,with_reset", ATT_CASES)
-def test_relattn_bwd(T, M, B, H, same_length, mem_len, with_reset):
+@pytest.mark.parametrize("T,M,B,H,same_length,mem_len,with_reset", ATT_CASES + [(300, 500, 2, 2, 0, 512, 1),
+                                                                         (384, 384, 1, 2, 1, 384, 0)])
+@pytest.mark.parametrize("impl", ["tc", "v1"])
+def test_relattn_bwd(T, M, B, H, same_length, mem_len, with_reset, impl):
     from commu import _native as nv
+    L = nv.lib()
+    flag = 1 if impl == "tc" else 0
+    L.commu_relattn_bwd_set_impl(flag, flag, flag)
+    try:
+        _relattn_bwd_case(nv, T, M, B, H, same_length, mem_len, with_reset)
+    finally:
+        L.commu_relattn_bwd_set_impl(1, 1, 1)
+
+
+def _relattn_bwd_case(nv, T, M, B, H, same_length, mem_len, with_reset):
     torch.manual_seed(T * 17 + M)
     dev = "cuda"
     K = T + M
