@@ -37,14 +37,14 @@ constexpr int COL_S = 0, COL_BAND = 128, COL_DR = 256;
 
 struct Smem {
   uint8_t r[TILE_BYTES];
-  uint8_t qu[TILE_BYTES];
-  uint8_t qv[TILE_BYTES];
-  uint8_t dout[TILE_BYTES];
+  uint8_t qu[2][TILE_BYTES];    // query-side tiles are double buffered
+  uint8_t qv[2][TILE_BYTES];
+  uint8_t dout[2][TILE_BYTES];
   uint8_t k[2][TILE_BYTES];
   uint8_t v[2][TILE_BYTES];
-  uint8_t ds[2 * TILE_BYTES];   // [2 distance atoms][128 q rows][128 B]
-  uint8_t bd[TM * STAGE_ROW];
-  uint64_t r_full, q_full, q_empty, kv_full[2], kv_empty[2];
+  uint8_t ds[2 * TILE_BYTES];   // [2 distance atoms][128 q rows][128 B]; ALSO the fp16 staging rows of the
+                                //   banded blocks (row li at ds + 256*li) earlier in the same iteration
+  uint64_t r_full, q_full[2], q_empty[2], kv_full[2], kv_empty[2];
   uint64_t s_full, s_empty, bd_full, bd_empty, pds_full, pds_empty, acc_full;
   uint32_t tmem_base;
 };
@@ -72,7 +72,7 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
 
   if (threadIdx.x == 0) {
     cb::mbar_init(&sm.r_full, 1);
-    cb::mbar_init(&sm.q_full, 1); cb::mbar_init(&sm.q_empty, 1);
+    for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.q_full[s], 1); cb::mbar_init(&sm.q_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.kv_full[s], 1); cb::mbar_init(&sm.kv_empty[s], 1); }
     cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_empty, SOFT);
     cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
@@ -102,17 +102,20 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
         cb::tma_load_3d(sm.k[bi], &tm_k, &sm.kv_full[bi], h * DH, b, jw00 + TN * kappa);
         cb::tma_load_3d(sm.v[bi], &tm_v, &sm.kv_full[bi], h * DH, b, jw00 + TN * kappa);
       };
-      uint32_t q_phase = 0;
-      load_kv(0);
-      for (int n = 0; n < nq; ++n) {
+      auto load_q = [&](int n) {   // buffer n&1, its (n>>1)-th use
+        const int bi = n & 1;
         const int i0 = (it_first + n) * TM;
-        cb::mbar_wait(&sm.q_empty, q_phase ^ 1);
-        cb::mbar_arrive_expect_tx(&sm.q_full, 3 * TILE_BYTES);
-        cb::tma_load_3d(sm.qu, &tm_qu, &sm.q_full, h * DH, b, i0);
-        cb::tma_load_3d(sm.qv, &tm_qv, &sm.q_full, h * DH, b, i0);
-        cb::tma_load_3d(sm.dout, &tm_do, &sm.q_full, h * DH, b, i0);
-        q_phase ^= 1;
+        cb::mbar_wait(&sm.q_empty[bi], ((n >> 1) & 1) ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.q_full[bi], 3 * TILE_BYTES);
+        cb::tma_load_3d(sm.qu[bi], &tm_qu, &sm.q_full[bi], h * DH, b, i0);
+        cb::tma_load_3d(sm.qv[bi], &tm_qv, &sm.q_full[bi], h * DH, b, i0);
+        cb::tma_load_3d(sm.dout[bi], &tm_do, &sm.q_full[bi], h * DH, b, i0);
+      };
+      load_kv(0);
+      load_q(0);
+      for (int n = 0; n < nq; ++n) {
         load_kv(n + 1);
+        if (n + 1 < nq) load_q(n + 1);
       }
     }
   } else if (warp == 1) {
@@ -120,8 +123,7 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     if (cb::elect_one() && nq > 0) {
       const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);
       const uint32_t idesc_g = cb::umma_idesc_bf16(TN, DH, 1, 1);   // dR: MN-major A (dS'^T), MN-major B (q+v)
-      uint32_t q_phase = 0, s_phase = 0, bd_phase = 0, pds_phase = 0;
-      const uint32_t a_qu = cb::smem_u32(sm.qu), a_qv = cb::smem_u32(sm.qv), a_do = cb::smem_u32(sm.dout);
+      uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
       const uint32_t a_r = cb::smem_u32(sm.r);
       cb::mbar_wait(&sm.r_full, 0);
       auto issue_band = [&](uint32_t a_addr, uint32_t b_addr) {
@@ -134,24 +136,31 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
         cb::umma_commit(&sm.bd_full);
         bd_phase ^= 1;
       };
-      for (int n = 0; n < nq; ++n) {
-        const int lo_b = n & 1, hi_b = (n + 1) & 1;   // key blocks kappa = n ("lo") and n+1 ("hi")
-        cb::mbar_wait(&sm.q_full, q_phase);
+      // "front" of query tile n: S' and the "lo" AC block; issued one tile ahead of the softmax threads
+      auto issue_front = [&](int n) {
+        const int qb = n & 1, lo_b = n & 1;
+        cb::mbar_wait(&sm.q_full[qb], (n >> 1) & 1);
         cb::mbar_wait(&sm.s_empty, s_phase ^ 1);
         cb::tc_fence_after();
-        {
-          const uint64_t aq = cb::umma_smem_desc(a_qv, 16, 1024), br = cb::umma_smem_desc(a_r, 16, 1024);
+        const uint64_t aq = cb::umma_smem_desc(cb::smem_u32(sm.qv[qb]), 16, 1024), br = cb::umma_smem_desc(a_r, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_S, aq + 2 * k, br + 2 * k, idesc_s, k > 0);
-          cb::umma_commit(&sm.s_full);
-        }
+        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_S, aq + 2 * k, br + 2 * k, idesc_s, k > 0);
+        cb::umma_commit(&sm.s_full);
+        s_phase ^= 1;
         cb::mbar_wait(&sm.kv_full[lo_b], (n >> 1) & 1);
-        issue_band(a_qu, cb::smem_u32(sm.k[lo_b]));          // AC "lo"
+        issue_band(cb::smem_u32(sm.qu[qb]), cb::smem_u32(sm.k[lo_b]));          // AC "lo"
+      };
+      issue_front(0);
+      for (int n = 0; n < nq; ++n) {
+        const int qb = n & 1;
+        const int lo_b = n & 1, hi_b = (n + 1) & 1;   // key blocks kappa = n ("lo") and n+1 ("hi")
+        const uint32_t a_qu = cb::smem_u32(sm.qu[qb]), a_qv = cb::smem_u32(sm.qv[qb]), a_do = cb::smem_u32(sm.dout[qb]);
         cb::mbar_wait(&sm.kv_full[hi_b], ((n + 1) >> 1) & 1);
         issue_band(a_qu, cb::smem_u32(sm.k[hi_b]));          // AC "hi"
         issue_band(a_do, cb::smem_u32(sm.v[lo_b]));          // dP "lo"
         issue_band(a_do, cb::smem_u32(sm.v[hi_b]));          // dP "hi"
         cb::umma_commit(&sm.kv_empty[lo_b]);                 // block kappa = n is dead after this tile
+        if (n + 1 < nq) issue_front(n + 1);
         cb::mbar_wait(&sm.pds_full, pds_phase);
         cb::tc_fence_after();
         {
@@ -161,10 +170,8 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
           for (int k = 0; k < TM / 16; ++k)
             cb::umma_bf16_ss(tmem + COL_DR, as + (uint64_t)(k * 128), bq + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
           cb::umma_commit(&sm.pds_empty);
-          cb::umma_commit(&sm.q_empty);
+          cb::umma_commit(&sm.q_empty[qb]);
         }
-        q_phase ^= 1;
-        s_phase ^= 1;
         pds_phase ^= 1;
       }
       cb::umma_commit(&sm.acc_full);
@@ -176,7 +183,8 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     const int wq = (warp - 4) & 3;
     const int li = wq * 32 + lane;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t my_row = cb::smem_u32(sm.bd) + li * STAGE_ROW;
+    const uint32_t my_row = cb::smem_u32(sm.ds) + li * 256;    // staging row (aliases the dS' tile)
+    const int rot = li & 7;
     const float sl2 = p.scale * 1.4426950408889634f;
     uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
     const float* lse_p = p.lse + ((long long)b * p.H + h) * p.T;
@@ -203,21 +211,23 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
           dp[e] = 0.f;
         }
       }
-      // four banded blocks, staged one at a time: AC lo, AC hi, dP lo, dP hi
+      // four banded blocks, staged one at a time: AC lo, AC hi, dP lo, dP hi.  The staging rows alias the
+      // dS' tile: the previous iteration's dR product must have consumed it first.
+      cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
 #pragma unroll
       for (int blk = 0; blk < 4; ++blk) {
         cb::mbar_wait(&sm.bd_full, bd_phase);
         cb::tc_fence_after();
-        named_bar(1, SOFT);
-        stage32(lane_addr + COL_BAND + g * 32, my_row + g * 64);
+        if (blk > 0) named_bar(1, SOFT);        // everyone finished reading the previously staged block
+        stage32_rot(lane_addr + COL_BAND + g * 32, my_row, g, rot);
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.bd_empty);
         bd_phase ^= 1;
         named_bar(2, SOFT);
-        if (blk == 0) band_add<0, true>(s, my_row, li, g, wq);
-        if (blk == 1) band_add<1, true>(s, my_row, li, g, wq);
-        if (blk == 2) band_add<0, true>(dp, my_row, li, g, wq);
-        if (blk == 3) band_add<1, true>(dp, my_row, li, g, wq);
+        if (blk == 0) band_add_rot<0>(s, my_row, li, g, wq, rot);
+        if (blk == 1) band_add_rot<1>(s, my_row, li, g, wq, rot);
+        if (blk == 2) band_add_rot<0>(dp, my_row, li, g, wq, rot);
+        if (blk == 3) band_add_rot<1>(dp, my_row, li, g, wq, rot);
       }
       // ---- P, dS' (columns are distances: key j = i + M - delta) ----
       uint32_t dsk[16];
@@ -230,7 +240,7 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
         if (i >= p.T || j0k - 1 < lo_i) p1 = 0.f;
         dsk[e / 2] = cb::pack_bf16(p0 * (dp[e] - delta), p1 * (dp[e + 1] - delta));
       }
-      cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
+      named_bar(1, SOFT);                       // every thread is done with the last staged block (dS' aliases it)
       {
         const uint32_t drow = cb::smem_u32(sm.ds) + (g >> 1) * TILE_BYTES;
 #pragma unroll

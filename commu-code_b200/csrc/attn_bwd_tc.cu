@@ -39,14 +39,13 @@ constexpr int COL_S = 0, COL_DP = 128, COL_BD = 256, COL_DV = 384, COL_DK = 448;
 struct Smem {
   uint8_t k[TILE_BYTES];
   uint8_t v[TILE_BYTES];
-  uint8_t qu[TILE_BYTES];
-  uint8_t qv[TILE_BYTES];
-  uint8_t dout[TILE_BYTES];
+  uint8_t qu[2][TILE_BYTES];    // query-side tiles are double buffered: the next query tile streams in while
+  uint8_t qv[2][TILE_BYTES];    // the current one is being processed
+  uint8_t dout[2][TILE_BYTES];
   uint8_t r[2][TILE_BYTES];
-  uint8_t p[2 * TILE_BYTES];    // [2 key atoms][128 q rows][128 B]
-  uint8_t ds[2 * TILE_BYTES];
-  uint8_t bd[TM * STAGE_ROW];
-  uint64_t kv_full, q_full, q_empty, r_full[2], r_empty[2];
+  uint8_t p[2 * TILE_BYTES];    // [2 key atoms][128 q rows][128 B]; ALSO the fp16 staging rows of the BD blocks
+  uint8_t ds[2 * TILE_BYTES];   //   (row li at p + 256*li) earlier in the same iteration
+  uint64_t kv_full, q_full[2], q_empty[2], r_full[2], r_empty[2];
   uint64_t s_full, s_empty, bd_full, bd_empty, pds_full, pds_empty, acc_full;
   uint32_t tmem_base;
 };
@@ -75,7 +74,7 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
 
   if (threadIdx.x == 0) {
     cb::mbar_init(&sm.kv_full, 1);
-    cb::mbar_init(&sm.q_full, 1); cb::mbar_init(&sm.q_empty, 1);
+    for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.q_full[s], 1); cb::mbar_init(&sm.q_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1); }
     cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_empty, SOFT);
     cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
@@ -99,23 +98,26 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
       cb::tma_load_3d(sm.k, &tm_k, &sm.kv_full, h * DH, b, j0);
       cb::tma_load_3d(sm.v, &tm_v, &sm.kv_full, h * DH, b, j0);
       Ring rr;
-      uint32_t q_phase = 0;
       auto load_r = [&](int gamma) {
         cb::mbar_wait(&sm.r_empty[rr.idx], rr.phase ^ 1);
         cb::mbar_arrive_expect_tx(&sm.r_full[rr.idx], TILE_BYTES);
         cb::tma_load_2d(sm.r[rr.idx], &tm_r, &sm.r_full[rr.idx], h * DH, dlo0 + TN * gamma);
         rr.advance();
       };
-      load_r(0);
-      for (int n = 0; n < nq; ++n) {
+      auto load_q = [&](int n) {   // buffer n&1, its (n>>1)-th use
+        const int bi = n & 1;
         const int i0 = (it_first + n) * TM;
-        cb::mbar_wait(&sm.q_empty, q_phase ^ 1);
-        cb::mbar_arrive_expect_tx(&sm.q_full, 3 * TILE_BYTES);
-        cb::tma_load_3d(sm.qu, &tm_qu, &sm.q_full, h * DH, b, i0);
-        cb::tma_load_3d(sm.qv, &tm_qv, &sm.q_full, h * DH, b, i0);
-        cb::tma_load_3d(sm.dout, &tm_do, &sm.q_full, h * DH, b, i0);
-        q_phase ^= 1;
+        cb::mbar_wait(&sm.q_empty[bi], ((n >> 1) & 1) ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.q_full[bi], 3 * TILE_BYTES);
+        cb::tma_load_3d(sm.qu[bi], &tm_qu, &sm.q_full[bi], h * DH, b, i0);
+        cb::tma_load_3d(sm.qv[bi], &tm_qv, &sm.q_full[bi], h * DH, b, i0);
+        cb::tma_load_3d(sm.dout[bi], &tm_do, &sm.q_full[bi], h * DH, b, i0);
+      };
+      load_r(0);
+      load_q(0);
+      for (int n = 0; n < nq; ++n) {
         load_r(n + 1);
+        if (n + 1 < nq) load_q(n + 1);
       }
     }
   } else if (warp == 1) {
@@ -124,9 +126,9 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
       const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);   // S, BD, dP: K-major x K-major
       const uint32_t idesc_g = cb::umma_idesc_bf16(TN, DH, 1, 1);   // dV, dK: MN-major A (tile^T), MN-major B
       Ring rr;
-      uint32_t q_phase = 0, s_phase = 0, bd_phase = 0, pds_phase = 0;
+      uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
       cb::mbar_wait(&sm.kv_full, 0);
-      const uint32_t a_qu = cb::smem_u32(sm.qu), a_qv = cb::smem_u32(sm.qv), a_do = cb::smem_u32(sm.dout);
+      uint32_t a_qu = 0, a_qv = 0, a_do = 0;
       const uint32_t a_k = cb::smem_u32(sm.k), a_v = cb::smem_u32(sm.v);
       auto issue_bd = [&](int ridx) {
         cb::mbar_wait(&sm.bd_empty, bd_phase ^ 1);
@@ -138,28 +140,37 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         cb::umma_commit(&sm.bd_full);
         bd_phase ^= 1;
       };
-      for (int n = 0; n < nq; ++n) {
-        cb::mbar_wait(&sm.q_full, q_phase);
-        // R blocks of this query tile: "lo" = gamma n (buffer n&1), "hi" = gamma n+1 (buffer (n+1)&1)
-        cb::mbar_wait(&sm.r_full[rr.idx], rr.phase);            // gamma = n   (loaded one iteration ago, or now)
+      // "front" of query tile n: S, dP and the "lo" BD block.  It is issued one tile ahead (software
+      // pipelining): front(n+1) goes to the tensor cores while the softmax threads still finish tile n.
+      auto issue_front = [&](int n) {
+        const int qb = n & 1;
+        const uint32_t f_qu = cb::smem_u32(sm.qu[qb]), f_do = cb::smem_u32(sm.dout[qb]);
+        a_qv = cb::smem_u32(sm.qv[qb]);
+        cb::mbar_wait(&sm.q_full[qb], (n >> 1) & 1);
+        cb::mbar_wait(&sm.r_full[rr.idx], rr.phase);            // gamma = n ("lo")
         cb::mbar_wait(&sm.s_empty, s_phase ^ 1);
         cb::tc_fence_after();
-        {  // S and dP
-          const uint64_t aq = cb::umma_smem_desc(a_qu, 16, 1024), bk = cb::umma_smem_desc(a_k, 16, 1024);
-          const uint64_t ad = cb::umma_smem_desc(a_do, 16, 1024), bv = cb::umma_smem_desc(a_v, 16, 1024);
+        const uint64_t aq = cb::umma_smem_desc(f_qu, 16, 1024), bk = cb::umma_smem_desc(a_k, 16, 1024);
+        const uint64_t ad = cb::umma_smem_desc(f_do, 16, 1024), bv = cb::umma_smem_desc(a_v, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_S, aq + 2 * k, bk + 2 * k, idesc_s, k > 0);
+        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_S, aq + 2 * k, bk + 2 * k, idesc_s, k > 0);
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_DP, ad + 2 * k, bv + 2 * k, idesc_s, k > 0);
-          cb::umma_commit(&sm.s_full);
-        }
-        issue_bd(rr.idx);                                        // BD "lo"
+        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_DP, ad + 2 * k, bv + 2 * k, idesc_s, k > 0);
+        cb::umma_commit(&sm.s_full);
+        s_phase ^= 1;
+        issue_bd(rr.idx);                                        // BD "lo" of tile n
+      };
+      issue_front(0);
+      for (int n = 0; n < nq; ++n) {
+        const int qb = n & 1;
+        a_qu = cb::smem_u32(sm.qu[qb]); a_qv = cb::smem_u32(sm.qv[qb]); a_do = cb::smem_u32(sm.dout[qb]);
+        // R blocks of this query tile: "lo" = gamma n (rr), "hi" = gamma n+1
         const int lo_idx = rr.idx;
         rr.advance();
         cb::mbar_wait(&sm.r_full[rr.idx], rr.phase);            // gamma = n+1
-        issue_bd(rr.idx);                                        // BD "hi"
+        issue_bd(rr.idx);                                        // BD "hi" (waits until "lo" has been staged)
         cb::umma_commit(&sm.r_empty[lo_idx]);                    // gamma n is dead after this tile
-        // (gamma n+1 stays: it is the next tile's "lo"; rr now points at it)
+        if (n + 1 < nq) issue_front(n + 1);                      // rr now points at gamma n+1 = next tile's "lo"
         // dV += P^T dO ; dK += dS^T (q+u)
         cb::mbar_wait(&sm.pds_full, pds_phase);
         cb::tc_fence_after();
@@ -174,10 +185,8 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
           for (int k = 0; k < TM / 16; ++k)
             cb::umma_bf16_ss(tmem + COL_DK, as + (uint64_t)(k * 128), bq + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
           cb::umma_commit(&sm.pds_empty);
-          cb::umma_commit(&sm.q_empty);
+          cb::umma_commit(&sm.q_empty[qb]);
         }
-        q_phase ^= 1;
-        s_phase ^= 1;
         pds_phase ^= 1;
       }
       cb::umma_commit(&sm.acc_full);
@@ -189,7 +198,8 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
     const int wq = (warp - 4) & 3;
     const int li = wq * 32 + lane;               // query row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t my_row = cb::smem_u32(sm.bd) + li * STAGE_ROW;
+    const uint32_t my_row = cb::smem_u32(sm.p) + li * 256;     // staging row (aliases the P tile)
+    const int rot = li & 7;
     const float sl2 = p.scale * 1.4426950408889634f;
     uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
     const float* lse_p = p.lse + ((long long)b * p.H + h) * p.T;
@@ -213,24 +223,25 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]);
       }
       // ---- relative shift, one 128-distance block at a time: pass 0 = "lo" (keys lj >= li), pass 1 = "hi" ----
+      // the staging rows alias the P tile: the previous iteration's dV product must have consumed it
+      cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
       cb::mbar_wait(&sm.bd_full, bd_phase);
       cb::tc_fence_after();
-      named_bar(1, SOFT);                       // everyone finished reading the previously staged block
-      stage32(lane_addr + COL_BD + g * 32, my_row + g * 64);
+      stage32_rot(lane_addr + COL_BD + g * 32, my_row, g, rot);
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.bd_empty);
       bd_phase ^= 1;
       named_bar(2, SOFT);                       // the whole staged block is visible
-      band_add<0, true>(s, my_row, li, g, wq);
+      band_add_rot<0>(s, my_row, li, g, wq, rot);
       cb::mbar_wait(&sm.bd_full, bd_phase);
       cb::tc_fence_after();
-      named_bar(1, SOFT);
-      stage32(lane_addr + COL_BD + g * 32, my_row + g * 64);
+      named_bar(1, SOFT);                       // everyone finished reading the "lo" block
+      stage32_rot(lane_addr + COL_BD + g * 32, my_row, g, rot);
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.bd_empty);
       bd_phase ^= 1;
       named_bar(2, SOFT);
-      band_add<1, true>(s, my_row, li, g, wq);
+      band_add_rot<1>(s, my_row, li, g, wq, rot);
       // ---- P = exp2(score*log2e - LSE), dS = P * (dP - Delta)  (the 1/sqrt(Dh) factor is applied to dK at the end)
       const int jc0 = j0 + g * 32;
       const bool full = (jc0 + 31 <= hi_i) && (jc0 >= lo_i);
@@ -255,7 +266,7 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         }
       }
       // ---- rows of the P / dS tiles: key atom g/2, query row li, chunks 4*(g&1) .. +3 (swizzled) ----
-      cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
+      named_bar(1, SOFT);                       // every thread is done with the staged "hi" block (P aliases it)
       {
         const uint32_t prow = cb::smem_u32(sm.p) + (g >> 1) * TILE_BYTES;
         const uint32_t drow = cb::smem_u32(sm.ds) + (g >> 1) * TILE_BYTES;

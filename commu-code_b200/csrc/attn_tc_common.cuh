@@ -112,6 +112,41 @@ __device__ __forceinline__ void band_add(float (&s)[32], uint32_t row, int li, i
   }
 }
 
+// Variants for an UNPADDED 256-byte staging row (so the 32 KB buffer can alias a 128x128 bf16 tile): the row
+// is rotated by rot = (li & 7) 16-byte chunks, which keeps the 16-byte stores of 8 consecutive rows on
+// distinct bank groups; element idx lives at byte (2*idx + 16*rot) mod 256.
+__device__ __forceinline__ void stage32_rot(uint32_t taddr, uint32_t row, int g, int rot) {
+  uint32_t r0[32];
+  cb::tmem_ld_32x32b_x32(taddr, r0);
+  cb::tmem_ld_wait();
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int e = c * 8;
+    sts_v4(row + (((g * 4 + c + rot) & 15) << 4), pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1])),
+           pack_f16(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3])),
+           pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
+           pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
+  }
+}
+template <int PASS>
+__device__ __forceinline__ void band_add_rot(float (&s)[32], uint32_t row, int li, int g, int wq, int rot) {
+  // byte offset of tile column lc = 32g + e inside the rotated row: (A - 2e) mod 256
+  const int A = (PASS == 0 ? 2 * (li + 127 - 32 * g) : 2 * (li - 1 - 32 * g)) + 16 * rot;
+  const bool all = PASS == 0 ? g > wq : g < wq;
+  if (all) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) s[e] += lds_f16(row + ((A - 2 * e) & 255));
+  } else if (g == wq) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      const int lc = g * 32 + e;
+      const bool use = PASS == 0 ? lc >= li : lc < li;
+      const float v = lds_f16(row + ((A - 2 * e) & 255));
+      if (use) s[e] += v;
+    }
+  }
+}
+
 struct Ring {  // stage / parity bookkeeping of a 2-deep mbarrier ring
   int idx = 0;
   uint32_t phase = 0;
