@@ -32,8 +32,8 @@ constexpr int NWG = 4;
 constexpr int SOFT = 128 * NWG;
 constexpr int NTHREADS = 128 + SOFT;
 constexpr int TILE_BYTES = 128 * DH * 2;
-constexpr int STAGE_ROW = 272;
-constexpr int COL_S = 0, COL_BAND = 128, COL_DR = 256;
+constexpr int BAND_THREADS = 32 * (NWG * (NWG + 1) / 2);   // threads (li, g) with g >= wq (or g <= wq): 320
+constexpr int COL_S = 0, COL_LO = 128, COL_HI = 256, COL_DR = 384;
 
 struct Smem {
   uint8_t r[TILE_BYTES];
@@ -42,10 +42,10 @@ struct Smem {
   uint8_t dout[2][TILE_BYTES];
   uint8_t k[2][TILE_BYTES];
   uint8_t v[2][TILE_BYTES];
-  uint8_t ds[2 * TILE_BYTES];   // [2 distance atoms][128 q rows][128 B]; ALSO the fp16 staging rows of the
-                                //   banded blocks (row li at ds + 256*li) earlier in the same iteration
+  uint8_t ds[TM * kStageRow];   // [2 distance atoms][128 q rows][128 B] (32 KB); ALSO the padded fp16 staging rows
+                                //   of the banded blocks (row li at ds + 272*li) earlier in the same iteration
   uint64_t r_full, q_full[2], q_empty[2], kv_full[2], kv_empty[2];
-  uint64_t s_full, s_empty, bd_full, bd_empty, pds_full, pds_empty, acc_full;
+  uint64_t s_full, s_empty, lo_full, lo_empty, hi_full, hi_empty, pds_full, pds_empty, acc_full;
   uint32_t tmem_base;
 };
 
@@ -75,7 +75,8 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.q_full[s], 1); cb::mbar_init(&sm.q_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.kv_full[s], 1); cb::mbar_init(&sm.kv_empty[s], 1); }
     cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_empty, SOFT);
-    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
+    cb::mbar_init(&sm.lo_full, 1); cb::mbar_init(&sm.lo_empty, BAND_THREADS);
+    cb::mbar_init(&sm.hi_full, 1); cb::mbar_init(&sm.hi_empty, BAND_THREADS);
     cb::mbar_init(&sm.pds_full, SOFT); cb::mbar_init(&sm.pds_empty, 1);
     cb::mbar_init(&sm.acc_full, 1);
     cb::fence_barrier_init();
@@ -123,18 +124,21 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     if (cb::elect_one() && nq > 0) {
       const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);
       const uint32_t idesc_g = cb::umma_idesc_bf16(TN, DH, 1, 1);   // dR: MN-major A (dS'^T), MN-major B (q+v)
-      uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
+      uint32_t s_phase = 0, lo_phase = 0, hi_phase = 0, pds_phase = 0;
       const uint32_t a_r = cb::smem_u32(sm.r);
       cb::mbar_wait(&sm.r_full, 0);
-      auto issue_band = [&](uint32_t a_addr, uint32_t b_addr) {
-        cb::mbar_wait(&sm.bd_empty, bd_phase ^ 1);
+      // banded products alternate between two accumulators: "lo" blocks (key block kappa = n) and "hi" blocks
+      // (kappa = n + 1); each may be overwritten once the threads that stage it have read the previous one
+      auto issue_band = [&](uint32_t a_addr, uint32_t b_addr, bool hi) {
+        if (hi) { cb::mbar_wait(&sm.hi_empty, hi_phase ^ 1); hi_phase ^= 1; }
+        else    { cb::mbar_wait(&sm.lo_empty, lo_phase ^ 1); lo_phase ^= 1; }
         cb::tc_fence_after();
         const uint64_t ad = cb::umma_smem_desc(a_addr, 16, 1024);
         const uint64_t bd = cb::umma_smem_desc(b_addr, 16, 1024);
+        const uint32_t col = tmem + (hi ? COL_HI : COL_LO);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_BAND, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
-        cb::umma_commit(&sm.bd_full);
-        bd_phase ^= 1;
+        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(col, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
+        cb::umma_commit(hi ? &sm.hi_full : &sm.lo_full);
       };
       // "front" of query tile n: S' and the "lo" AC block; issued one tile ahead of the softmax threads
       auto issue_front = [&](int n) {
@@ -148,7 +152,7 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
         cb::umma_commit(&sm.s_full);
         s_phase ^= 1;
         cb::mbar_wait(&sm.kv_full[lo_b], (n >> 1) & 1);
-        issue_band(cb::smem_u32(sm.qu[qb]), cb::smem_u32(sm.k[lo_b]));          // AC "lo"
+        issue_band(cb::smem_u32(sm.qu[qb]), cb::smem_u32(sm.k[lo_b]), false);   // AC "lo"
       };
       issue_front(0);
       for (int n = 0; n < nq; ++n) {
@@ -156,9 +160,9 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
         const int lo_b = n & 1, hi_b = (n + 1) & 1;   // key blocks kappa = n ("lo") and n+1 ("hi")
         const uint32_t a_qu = cb::smem_u32(sm.qu[qb]), a_qv = cb::smem_u32(sm.qv[qb]), a_do = cb::smem_u32(sm.dout[qb]);
         cb::mbar_wait(&sm.kv_full[hi_b], ((n + 1) >> 1) & 1);
-        issue_band(a_qu, cb::smem_u32(sm.k[hi_b]));          // AC "hi"
-        issue_band(a_do, cb::smem_u32(sm.v[lo_b]));          // dP "lo"
-        issue_band(a_do, cb::smem_u32(sm.v[hi_b]));          // dP "hi"
+        issue_band(a_qu, cb::smem_u32(sm.k[hi_b]), true);    // AC "hi"
+        issue_band(a_do, cb::smem_u32(sm.v[lo_b]), false);   // dP "lo"
+        issue_band(a_do, cb::smem_u32(sm.v[hi_b]), true);    // dP "hi"
         cb::umma_commit(&sm.kv_empty[lo_b]);                 // block kappa = n is dead after this tile
         if (n + 1 < nq) issue_front(n + 1);
         cb::mbar_wait(&sm.pds_full, pds_phase);
@@ -183,10 +187,9 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     const int wq = (warp - 4) & 3;
     const int li = wq * 32 + lane;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t my_row = cb::smem_u32(sm.ds) + li * 256;    // staging row (aliases the dS' tile)
-    const int rot = li & 7;
+    const uint32_t my_row = cb::smem_u32(sm.ds) + li * kStageRow;   // staging row (aliases the dS' tile)
     const float sl2 = p.scale * 1.4426950408889634f;
-    uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
+    uint32_t s_phase = 0, band_phase = 0, pds_phase = 0;
     const float* lse_p = p.lse + ((long long)b * p.H + h) * p.T;
     const float* del_p = p.delta + ((long long)b * p.H + h) * p.T;
 
@@ -211,23 +214,32 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
           dp[e] = 0.f;
         }
       }
-      // four banded blocks, staged one at a time: AC lo, AC hi, dP lo, dP hi.  The staging rows alias the
-      // dS' tile: the previous iteration's dR product must have consumed it first.
+      // two banded products (AC into s, dP into dp), each a "lo" and a "hi" block: a thread stages its 32 block
+      // columns from the block its row needs (both on the diagonal chunk) and reads the combined row circularly.
+      // The staging rows alias the dS' tile: the previous iteration's dR product must have consumed it first.
       cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
 #pragma unroll
-      for (int blk = 0; blk < 4; ++blk) {
-        cb::mbar_wait(&sm.bd_full, bd_phase);
-        cb::tc_fence_after();
-        if (blk > 0) named_bar(1, SOFT);        // everyone finished reading the previously staged block
-        stage32_rot(lane_addr + COL_BAND + g * 32, my_row, g, rot);
-        cb::tc_fence_before();
-        cb::mbar_arrive(&sm.bd_empty);
-        bd_phase ^= 1;
-        named_bar(2, SOFT);
-        if (blk == 0) band_add_rot<0>(s, my_row, li, g, wq, rot);
-        if (blk == 1) band_add_rot<1>(s, my_row, li, g, wq, rot);
-        if (blk == 2) band_add_rot<0>(dp, my_row, li, g, wq, rot);
-        if (blk == 3) band_add_rot<1>(dp, my_row, li, g, wq, rot);
+      for (int prod = 0; prod < 2; ++prod) {
+        if (prod) named_bar(2 + wq, NWG * 32);  // this row group finished reading the AC rows
+        if (g >= wq) {
+          cb::mbar_wait(&sm.lo_full, band_phase);
+          cb::tc_fence_after();
+          stage32_h(lane_addr + COL_LO + g * 32, my_row + 64 * g);
+          cb::tc_fence_before();
+          cb::mbar_arrive(&sm.lo_empty);
+        }
+        if (g <= wq) {
+          cb::mbar_wait(&sm.hi_full, band_phase);
+          cb::tc_fence_after();
+          if (g < wq) stage32_h(lane_addr + COL_HI + g * 32, my_row + 64 * g);
+          else stage32_diag_hi_h(lane_addr + COL_HI + g * 32, my_row + 64 * g, lane);
+          cb::tc_fence_before();
+          cb::mbar_arrive(&sm.hi_empty);
+        }
+        band_phase ^= 1;
+        named_bar(2 + wq, NWG * 32);            // the four chunks of this row group are staged
+        if (prod == 0) band_read(s, my_row, li, g, wq, lane);
+        else band_read(dp, my_row, li, g, wq, lane);
       }
       // ---- P, dS' (columns are distances: key j = i + M - delta) ----
       uint32_t dsk[16];

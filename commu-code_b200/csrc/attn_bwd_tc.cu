@@ -33,7 +33,7 @@ constexpr int NWG = 4;
 constexpr int SOFT = 128 * NWG;
 constexpr int NTHREADS = 128 + SOFT;
 constexpr int TILE_BYTES = 128 * DH * 2;      // 16 KB
-constexpr int STAGE_ROW = 272;                // one staged fp16 BD block row (256 B + 16 pad)
+constexpr int BAND_THREADS = 32 * (NWG * (NWG + 1) / 2) * 4 / NWG;   // threads (li, g) with g >= wq (or g <= wq): 320
 constexpr int COL_S = 0, COL_DP = 128, COL_BD = 256, COL_DV = 384, COL_DK = 448;
 
 struct Smem {
@@ -46,7 +46,7 @@ struct Smem {
   uint8_t p[2 * TILE_BYTES];    // [2 key atoms][128 q rows][128 B]; ALSO the fp16 staging rows of the BD blocks
   uint8_t ds[2 * TILE_BYTES];   //   (row li at p + 256*li) earlier in the same iteration
   uint64_t kv_full, q_full[2], q_empty[2], r_full[2], r_empty[2];
-  uint64_t s_full, s_empty, bd_full, bd_empty, pds_full, pds_empty, acc_full;
+  uint64_t s_full, s_empty, lo_full, lo_empty, hi_full, hi_empty, pds_full, pds_empty, acc_full;
   uint32_t tmem_base;
 };
 
@@ -77,7 +77,8 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
     for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.q_full[s], 1); cb::mbar_init(&sm.q_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1); }
     cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_empty, SOFT);
-    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
+    cb::mbar_init(&sm.lo_full, 1); cb::mbar_init(&sm.lo_empty, BAND_THREADS);
+    cb::mbar_init(&sm.hi_full, 1); cb::mbar_init(&sm.hi_empty, BAND_THREADS);
     cb::mbar_init(&sm.pds_full, SOFT); cb::mbar_init(&sm.pds_empty, 1);
     cb::mbar_init(&sm.acc_full, 1);
     cb::fence_barrier_init();
@@ -130,15 +131,18 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
       cb::mbar_wait(&sm.kv_full, 0);
       uint32_t a_qu = 0, a_qv = 0, a_do = 0;
       const uint32_t a_k = cb::smem_u32(sm.k), a_v = cb::smem_u32(sm.v);
-      auto issue_bd = [&](int ridx) {
-        cb::mbar_wait(&sm.bd_empty, bd_phase ^ 1);
+      // the BD accumulator is shared by the "lo" and the "hi" block: lo(n) may overwrite it once the threads
+      // that stage hi(n-1) are done, hi(n) once lo(n) has been staged
+      auto issue_bd = [&](int ridx, bool hi) {
+        if (hi) cb::mbar_wait(&sm.lo_empty, bd_phase);
+        else cb::mbar_wait(&sm.hi_empty, bd_phase ^ 1);
         cb::tc_fence_after();
         const uint64_t ad = cb::umma_smem_desc(a_qv, 16, 1024);
         const uint64_t bd = cb::umma_smem_desc(cb::smem_u32(sm.r[ridx]), 16, 1024);
 #pragma unroll
         for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_BD, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
-        cb::umma_commit(&sm.bd_full);
-        bd_phase ^= 1;
+        cb::umma_commit(hi ? &sm.hi_full : &sm.lo_full);
+        if (hi) bd_phase ^= 1;
       };
       // "front" of query tile n: S, dP and the "lo" BD block.  It is issued one tile ahead (software
       // pipelining): front(n+1) goes to the tensor cores while the softmax threads still finish tile n.
@@ -158,7 +162,7 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_DP, ad + 2 * k, bv + 2 * k, idesc_s, k > 0);
         cb::umma_commit(&sm.s_full);
         s_phase ^= 1;
-        issue_bd(rr.idx);                                        // BD "lo" of tile n
+        issue_bd(rr.idx, false);                                 // BD "lo" of tile n
       };
       issue_front(0);
       for (int n = 0; n < nq; ++n) {
@@ -168,7 +172,7 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         const int lo_idx = rr.idx;
         rr.advance();
         cb::mbar_wait(&sm.r_full[rr.idx], rr.phase);            // gamma = n+1
-        issue_bd(rr.idx);                                        // BD "hi" (waits until "lo" has been staged)
+        issue_bd(rr.idx, true);                                  // BD "hi" (waits until "lo" has been staged)
         cb::umma_commit(&sm.r_empty[lo_idx]);                    // gamma n is dead after this tile
         if (n + 1 < nq) issue_front(n + 1);                      // rr now points at gamma n+1 = next tile's "lo"
         // dV += P^T dO ; dK += dS^T (q+u)
@@ -198,8 +202,7 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
     const int wq = (warp - 4) & 3;
     const int li = wq * 32 + lane;               // query row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t my_row = cb::smem_u32(sm.p) + li * 256;     // staging row (aliases the P tile)
-    const int rot = li & 7;
+    const uint32_t my_row = cb::smem_u32(sm.p) + li * kStageRow;   // staging row (aliases the P / dS tiles)
     const float sl2 = p.scale * 1.4426950408889634f;
     uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
     const float* lse_p = p.lse + ((long long)b * p.H + h) * p.T;
@@ -222,26 +225,28 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
 #pragma unroll
         for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]);
       }
-      // ---- relative shift, one 128-distance block at a time: pass 0 = "lo" (keys lj >= li), pass 1 = "hi" ----
-      // the staging rows alias the P tile: the previous iteration's dV product must have consumed it
+      // ---- relative shift: each thread stages its 32 band-block columns from the block its row needs ("lo" for
+      // idx >= li, "hi" below; both on the diagonal chunk) and reads the combined row circularly.
+      // The staging rows alias the P / dS tiles: the previous iteration's dV / dK products must be done with them.
       cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
-      cb::mbar_wait(&sm.bd_full, bd_phase);
-      cb::tc_fence_after();
-      stage32_rot(lane_addr + COL_BD + g * 32, my_row, g, rot);
-      cb::tc_fence_before();
-      cb::mbar_arrive(&sm.bd_empty);
+      if (g >= wq) {
+        cb::mbar_wait(&sm.lo_full, bd_phase);
+        cb::tc_fence_after();
+        stage32(lane_addr + COL_BD + g * 32, my_row + 64 * g);
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.lo_empty);
+      }
+      if (g <= wq) {
+        cb::mbar_wait(&sm.hi_full, bd_phase);
+        cb::tc_fence_after();
+        if (g < wq) stage32(lane_addr + COL_BD + g * 32, my_row + 64 * g);
+        else stage32_diag_hi(lane_addr + COL_BD + g * 32, my_row + 64 * g, lane);
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.hi_empty);
+      }
       bd_phase ^= 1;
-      named_bar(2, SOFT);                       // the whole staged block is visible
-      band_add_rot<0>(s, my_row, li, g, wq, rot);
-      cb::mbar_wait(&sm.bd_full, bd_phase);
-      cb::tc_fence_after();
-      named_bar(1, SOFT);                       // everyone finished reading the "lo" block
-      stage32_rot(lane_addr + COL_BD + g * 32, my_row, g, rot);
-      cb::tc_fence_before();
-      cb::mbar_arrive(&sm.bd_empty);
-      bd_phase ^= 1;
-      named_bar(2, SOFT);
-      band_add_rot<1>(s, my_row, li, g, wq, rot);
+      named_bar(2 + wq, NWG * 32);              // the four chunks of this row group are staged
+      band_read(s, my_row, li, g, wq, lane);
       // ---- P = exp2(score*log2e - LSE), dS = P * (dP - Delta)  (the 1/sqrt(Dh) factor is applied to dK at the end)
       const int jc0 = j0 + g * 32;
       const bool full = (jc0 + 31 <= hi_i) && (jc0 >= lo_i);
@@ -266,7 +271,7 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         }
       }
       // ---- rows of the P / dS tiles: key atom g/2, query row li, chunks 4*(g&1) .. +3 (swizzled) ----
-      named_bar(1, SOFT);                       // every thread is done with the staged "hi" block (P aliases it)
+      named_bar(1, SOFT);                       // every thread is done with the staged rows (P / dS alias them)
       {
         const uint32_t prow = cb::smem_u32(sm.p) + (g >> 1) * TILE_BYTES;
         const uint32_t drow = cb::smem_u32(sm.ds) + (g >> 1) * TILE_BYTES;

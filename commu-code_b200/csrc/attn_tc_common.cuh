@@ -147,6 +147,73 @@ __device__ __forceinline__ void band_add_rot(float (&s)[32], uint32_t row, int l
   }
 }
 
+// ---- combined staging ----
+// Row li of a 128 x 128 tile needs band indices idx >= li from the "lo" block and idx < li from the "hi"
+// block (idx = the block column): together exactly one 128-entry row.  Thread (li, g) therefore stages
+// its 32 block columns c = 32g + e from ONE block (lo if g > wq, hi if g < wq) and only the diagonal
+// chunk g == wq from both, into a private padded fp16 row (kStageRow bytes apart), and the shear read
+// becomes a circular read of that row: tile column lc holds index (li + 127 - lc) mod 128.
+constexpr int kStageRow = 272;
+__device__ __forceinline__ void sts_u16(uint32_t addr, unsigned short v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+// "hi" part of the diagonal chunk: overwrite the entries with block column c = 32g + e < li, i.e. e < lane
+__device__ __forceinline__ void stage32_diag_hi(uint32_t taddr, uint32_t dst, int lane) {
+  uint32_t r0[32];
+  cb::tmem_ld_32x32b_x32(taddr, r0);
+  cb::tmem_ld_wait();
+#pragma unroll
+  for (int e = 0; e < 31; ++e) {
+    unsigned short hv;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(hv) : "f"(__uint_as_float(r0[e])));
+    if (e < lane) sts_u16(dst + 2 * e, hv);
+  }
+}
+// the same two helpers with 16-column TMEM reads (lower register peak, for the dR kernel)
+__device__ __forceinline__ void stage32_h(uint32_t taddr, uint32_t dst) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r0[16];
+    tmem_ld_32x32b_x16(taddr + half * 16, r0);
+    cb::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; e += 8)
+      sts_v4(dst + half * 32 + e * 2, pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1])),
+             pack_f16(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3])),
+             pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
+             pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
+  }
+}
+__device__ __forceinline__ void stage32_diag_hi_h(uint32_t taddr, uint32_t dst, int lane) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r0[16];
+    tmem_ld_32x32b_x16(taddr + half * 16, r0);
+    cb::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      unsigned short hv;
+      asm("cvt.rn.f16.f32 %0, %1;" : "=h"(hv) : "f"(__uint_as_float(r0[e])));
+      if (half * 16 + e < lane) sts_u16(dst + 2 * (half * 16 + e), hv);
+    }
+  }
+}
+// s[e] += band value of tile column lc = 32g + e out of the combined row
+__device__ __forceinline__ void band_read(float (&s)[32], uint32_t row, int li, int g, int wq, int lane) {
+  const uint32_t base1 = row + 2 * (li - 1) - 64 * g;     // idx = li - 1 - lc   (lc <  li)
+  const uint32_t base0 = base1 + 256;                     // idx = li + 127 - lc (lc >= li)
+  if (g > wq) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) s[e] += lds_f16(base0 - 2 * e);
+  } else if (g < wq) {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) s[e] += lds_f16(base1 - 2 * e);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 32; ++e) s[e] += lds_f16((e >= lane ? base0 : base1) - 2 * e);
+  }
+}
+
 struct Ring {  // stage / parity bookkeeping of a 2-deep mbarrier ring
   int idx = 0;
   uint32_t phase = 0;
