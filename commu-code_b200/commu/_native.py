@@ -116,7 +116,7 @@ SIGNATURES = {
     "commu_prof_arm": [U],
     "commu_prof_read": [I, P, P],
     "commu_relattn_bwd_set_impl": [I, I, I],
-    "commu_relattn_bwd_dr_tc": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, P],
+    "commu_relattn_bwd_dr_tc": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, P, P, P],
     "commu_relattn_bwd_dq_tc": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, L, P, P, P],
     "commu_relattn_bwd_dkv_tc": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, P, L, P],
     "commu_decode_linear": [P, L, P, L, I, P, I, P, L, P, L, I, I, I, P],

@@ -521,7 +521,7 @@ extern "C" int commu_relattn_bwd_dr_tc(const void* qu, const void* qv, int64_t l
                                        int64_t ldkv, const void* r, int64_t ldr, int kr,
                                        const unsigned char* reset, int T, int M, int B, int H, int same_length,
                                        int shift, float scale, const float* lse, const void* dout, int64_t lddo,
-                                       const float* delta, float* dr, void* stream_);
+                                       const float* delta, float* dr, float* du, float* dvb, void* stream_);
 extern "C" int commu_relattn_bwd_dq_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
                                        int64_t ldkv, const void* r, int64_t ldr, int kr,
                                        const unsigned char* reset, int T, int M, int B, int H, int same_length,
@@ -601,7 +601,8 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
         (const bf16*)out, ldo, (const bf16*)dout, lddo, T, B, H, delta_ws);
   }
   const int Ktot = T + M;
-  const bool dq_tc = pass_impl(0, "COMMU_ATTN_BWD_DQ");
+  // the tcgen05 dq and dR passes split d r_w_bias / d r_r_bias between them, so they are selected as a pair
+  const bool dq_tc = pass_impl(0, "COMMU_ATTN_BWD_DQ") && pass_impl(2, "COMMU_ATTN_BWD_DR");
   if (dq_tc) {
     int rc3 = commu_relattn_bwd_dq_tc(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift, scale,
                                       lse, dout, lddo, delta_ws, dq, lddq, du, dvb, stream_);
@@ -619,10 +620,10 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
     relattn_bwd_dkv_kernel<<<dim3(cb_host::ceil_div(Ktot, attn::BN), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(
         p, (bf16*)dk, (bf16*)dv, lddkv);
   }
-  const bool dr_tc = pass_impl(2, "COMMU_ATTN_BWD_DR");
+  const bool dr_tc = dq_tc;
   if (dr_tc) {
     int rc4 = commu_relattn_bwd_dr_tc(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift, scale,
-                                      lse, dout, lddo, delta_ws, dr, stream_);
+                                      lse, dout, lddo, delta_ws, dr, du, dvb, stream_);
     if (rc4) return rc4;
   } else {
     relattn_bwd_dr_kernel<<<dim3(cb_host::ceil_div(Ktot, attn::BN), H, B), NTHREADS, sizeof(BwdSmem), stream>>>(p);

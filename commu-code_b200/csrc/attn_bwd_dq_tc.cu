@@ -1,16 +1,24 @@
-// Relative-position attention backward on tcgen05 tensor cores: the dq pass (+ d r_w_bias, d r_r_bias).
+// Relative-position attention backward on tcgen05 tensor cores: the dq pass (+ the column sums for d r_w_bias).
 //
 // One CTA = 128 query rows of one (batch, head); it walks the key tiles like the forward kernel.  Per key
 // tile t six products run on the tensor cores (accumulators in TMEM):
 //     S      = (q+u) K_t^T                           [128 x 128]
-//     BD     = (q+v) R_blk^T   ("lo" then "hi" 128-distance block, staged one at a time)
-//     dP     = dO V_t^T                              [128 x 128]
-//     dq_ac += dS K_t                                [128 x 64]   A = dS (bf16) in TMEM, B = K tile (MN-major)
-//     dq_bd += dBD [R_lo ; R_hi]                     [128 x 64]   A = dBD band tile in shared memory
-// dBD is the inverse relative shift of dS: row li of the 128 x 256 band tile holds dS[li, lj] at band
-// column li + 127 - lj (every row owns a fixed run of 128 columns, the rest of the tile stays zero), so
-// the product with the two R blocks the band spans is the position-term gradient.
-// dq = scale * (dq_ac + dq_bd); d r_w_bias += colsum(scale * dq_ac); d r_r_bias += colsum(scale * dq_bd).
+//     BD     = (q+v) R_blk^T   "lo" block (beta = t+1) and "hi" block (beta = t) of the 255-distance band
+//     dP     = dO V_t^T                              [128 x 128]   (issued into the "hi" columns once they are staged)
+//     dq    += dS K_t                                [128 x 64]    A = dS (bf16) in TMEM, B = K tile (MN-major)
+//     dq    += C_beta R_beta                         [128 x 64]    A = band block beta in shared memory
+// Band blocks: dBD is the inverse relative shift of dS - row li holds dS[li, lj] at band column
+// c = li + 127 - lj of the 255-column band.  Columns c < 128 belong to distance block beta = t+1, the others to
+// beta = t, and every element of block beta is produced exactly once: by tile beta-1 if idx >= li, by tile
+// beta if idx < li.  The softmax threads therefore scatter dS straight into two 128 x 128 block buffers
+// (ring of 2) and ONE K=128 product per tile consumes the block that just became complete.  A block is kept
+// MN-major without swizzle ([16 groups of 8 rows][128 idx][8 rows x 2 B]), which makes the scatter address
+// linear in idx: `base - 16*e` with immediate offsets, one 16-bit store per element.
+// The software pipeline: S(t+1) / lo(t+1) / hi(t+1) are issued while the softmax threads still work on tile
+// t (as soon as they have copied S / staged lo / loaded dP of tile t); the staged fp16 rows of the relative
+// shift (attn_tc_common.cuh) alias the row group's piece of the block buffer that tile t starts to fill.
+// dq = scale * acc.  d r_w_bias + d r_r_bias = colsum(dq) is added to du here; the dR pass computes
+// d r_r_bias from the column sums of dBD and moves it from du to dvb (attn_bwd_dr_tc.cu).
 //
 // Autograd counterpart of commu/model/model.py:312-345 for d(queries) and the two global biases.
 #include "api_common.h"
@@ -33,20 +41,22 @@ constexpr int NWG = 4;
 constexpr int SOFT = 128 * NWG;
 constexpr int NTHREADS = 128 + SOFT;
 constexpr int TILE_BYTES = 128 * DH * 2;      // 16 KB
-constexpr int STAGE_ROW = 272;
-constexpr int COL_S = 0, COL_DP = 128, COL_BD = 256, COL_DQA = 384, COL_DQB = 448;
+constexpr int QG = 2576;                      // bytes between the 8-row groups of a band block (2048 used); 4 * QG >= kStageGroupBytes
+constexpr int CB_BYTES = 16 * QG;             // one band block buffer
+constexpr int BAND_THREADS = 32 * (NWG * (NWG + 1) / 2);   // threads (li, g) with g >= wq (or g <= wq): 320
+constexpr int COL_S = 0, COL_X = 128, COL_LO = 256, COL_DS = 384, COL_DQ = 448;
+static_assert(4 * QG >= kStageGroupBytes, "a row group's piece of a band block must hold its staged rows");
 
 struct Smem {
   uint8_t qu[TILE_BYTES];
   uint8_t qv[TILE_BYTES];
   uint8_t dout[TILE_BYTES];
-  uint8_t k[TILE_BYTES];
+  uint8_t k[2][TILE_BYTES];
   uint8_t v[TILE_BYTES];
-  uint8_t r[2][TILE_BYTES];
-  uint8_t dbd[4 * TILE_BYTES];  // band tile: 4 K-atoms of 64 band columns, [128 rows][128 B] each
-  uint8_t bd[TM * STAGE_ROW];
-  uint64_t q_full, k_full, k_empty, r_full[2], r_empty[2];
-  uint64_t s_full, s_empty, bd_full, bd_empty, ds_full, ds_empty, acc_full;
+  uint8_t r[3][TILE_BYTES];
+  uint8_t cb[2][CB_BYTES];      // band blocks beta (buffer beta & 1); ALSO the staged fp16 rows of tile t in buffer (t+1) & 1
+  uint64_t q_full, k_full[2], k_empty[2], v_full, v_empty, r_full[3], r_empty[3];
+  uint64_t s_full, s_free, lo_full, lo_free, hi_full, hi_done, dp_full, x_free, ds_full, ds_free, cb_free[2], acc_full;
   uint32_t tmem_base;
 };
 
@@ -70,11 +80,15 @@ relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
 
   if (threadIdx.x == 0) {
     cb::mbar_init(&sm.q_full, 1);
-    cb::mbar_init(&sm.k_full, 1); cb::mbar_init(&sm.k_empty, 1);
-    for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1); }
-    cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_empty, SOFT);
-    cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
-    cb::mbar_init(&sm.ds_full, SOFT); cb::mbar_init(&sm.ds_empty, 1);
+    for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.k_full[s], 1); cb::mbar_init(&sm.k_empty[s], 1); }
+    cb::mbar_init(&sm.v_full, 1); cb::mbar_init(&sm.v_empty, 1);
+    for (int s = 0; s < 3; ++s) { cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1); }
+    cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_free, SOFT);
+    cb::mbar_init(&sm.lo_full, 1); cb::mbar_init(&sm.lo_free, BAND_THREADS);
+    cb::mbar_init(&sm.hi_full, 1); cb::mbar_init(&sm.hi_done, BAND_THREADS);
+    cb::mbar_init(&sm.dp_full, 1); cb::mbar_init(&sm.x_free, SOFT);
+    cb::mbar_init(&sm.ds_full, SOFT); cb::mbar_init(&sm.ds_free, 1);
+    cb::mbar_init(&sm.cb_free[0], 1); cb::mbar_init(&sm.cb_free[1], 1);
     cb::mbar_init(&sm.acc_full, 1);
     cb::fence_barrier_init();
   }
@@ -94,216 +108,262 @@ relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
       cb::tma_load_3d(sm.qu, &tm_qu, &sm.q_full, h * DH, b, i0);
       cb::tma_load_3d(sm.qv, &tm_qv, &sm.q_full, h * DH, b, i0);
       cb::tma_load_3d(sm.dout, &tm_do, &sm.q_full, h * DH, b, i0);
-      auto load_r = [&](int beta) {   // buffer beta&1, its (beta>>1)-th use
-        const int bi = beta & 1;
-        const uint32_t use = (beta >> 1) & 1;
-        cb::mbar_wait(&sm.r_empty[bi], use ^ 1);
-        cb::mbar_arrive_expect_tx(&sm.r_full[bi], TILE_BYTES);
-        cb::tma_load_2d(sm.r[bi], &tm_r, &sm.r_full[bi], h * DH, dbase - TN * beta);
+      auto load_r = [&](int beta) {   // slot beta % 3, its (beta / 3)-th use
+        const int sl = beta % 3;
+        cb::mbar_wait(&sm.r_empty[sl], ((beta / 3) & 1) ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.r_full[sl], TILE_BYTES);
+        cb::tma_load_2d(sm.r[sl], &tm_r, &sm.r_full[sl], h * DH, dbase - TN * beta);
       };
-      load_r(0);
+      auto load_k = [&](int t) {      // buffer t & 1, its (t >> 1)-th use
+        const int bi = t & 1;
+        cb::mbar_wait(&sm.k_empty[bi], ((t >> 1) & 1) ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.k_full[bi], TILE_BYTES);
+        cb::tma_load_3d(sm.k[bi], &tm_k, &sm.k_full[bi], h * DH, b, (jt_first + t) * TN);
+      };
+      auto load_v = [&](int t) {
+        cb::mbar_wait(&sm.v_empty, (t & 1) ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.v_full, TILE_BYTES);
+        cb::tma_load_3d(sm.v, &tm_v, &sm.v_full, h * DH, b, (jt_first + t) * TN);
+      };
+      load_k(0);
       load_r(1);
-      uint32_t k_phase = 0;
-      for (int t = 0; t < nt; ++t) {
-        const int j0 = (jt_first + t) * TN;
-        if (t > 0) load_r(t + 1);
-        cb::mbar_wait(&sm.k_empty, k_phase ^ 1);
-        cb::mbar_arrive_expect_tx(&sm.k_full, 2 * TILE_BYTES);
-        cb::tma_load_3d(sm.k, &tm_k, &sm.k_full, h * DH, b, j0);
-        cb::tma_load_3d(sm.v, &tm_v, &sm.k_full, h * DH, b, j0);
-        k_phase ^= 1;
+      load_r(0);
+      load_v(0);
+      for (int t = 0; t + 1 < nt; ++t) {
+        load_k(t + 1);
+        load_r(t + 2);
+        load_v(t + 1);
       }
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ==============================
     if (cb::elect_one()) {
-      const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);   // S, BD, dP
-      const uint32_t idesc_q = cb::umma_idesc_bf16(TM, DH, 0, 1);   // dq: A K-major (TMEM / band tile), B MN-major
-      uint32_t k_phase = 0, s_phase = 0, bd_phase = 0, ds_phase = 0;
+      const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);   // S, BD, dP: K-major x K-major
+      const uint32_t idesc_a = cb::umma_idesc_bf16(TM, DH, 0, 1);   // dq += dS K : A K-major (TMEM), B MN-major
+      const uint32_t idesc_b = cb::umma_idesc_bf16(TM, DH, 1, 1);   // dq += C R  : A MN-major (no swizzle), B MN-major
       const uint32_t a_qu = cb::smem_u32(sm.qu), a_qv = cb::smem_u32(sm.qv), a_do = cb::smem_u32(sm.dout);
-      const uint32_t a_k = cb::smem_u32(sm.k), a_v = cb::smem_u32(sm.v), a_dbd = cb::smem_u32(sm.dbd);
-      cb::mbar_wait(&sm.q_full, 0);
-      auto issue_bd = [&](int bi) {
-        cb::mbar_wait(&sm.bd_empty, bd_phase ^ 1);
-        cb::tc_fence_after();
-        const uint64_t ad = cb::umma_smem_desc(a_qv, 16, 1024);
-        const uint64_t bd = cb::umma_smem_desc(cb::smem_u32(sm.r[bi]), 16, 1024);
+      const uint32_t a_v = cb::smem_u32(sm.v);
+      auto kmajor_128 = [&](uint32_t col, uint32_t a_addr, uint32_t b_addr) {
+        const uint64_t ad = cb::umma_smem_desc(a_addr, 16, 1024);
+        const uint64_t bd = cb::umma_smem_desc(b_addr, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_BD, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
-        cb::umma_commit(&sm.bd_full);
-        bd_phase ^= 1;
+        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + col, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
       };
+      // dq += C_beta R_beta: block buffer beta & 1, R slot beta % 3
+      auto issue_band = [&](int beta, bool first) {
+        const uint32_t a_cb = cb::smem_u32(sm.cb[beta & 1]);
+        const uint64_t br = cb::umma_smem_desc(cb::smem_u32(sm.r[beta % 3]), 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < TN / 16; ++k)
+          cb::umma_bf16_ss(tmem + COL_DQ, umma_smem_desc_nosw(a_cb + k * 256, 128, QG), br + (uint64_t)(k * 128), idesc_b,
+                           !(first && k == 0));
+      };
+      cb::mbar_wait(&sm.q_full, 0);
+      // front of tile 0
+      cb::mbar_wait(&sm.k_full[0], 0);
+      cb::tc_fence_after();
+      kmajor_128(COL_S, a_qu, cb::smem_u32(sm.k[0]));
+      cb::umma_commit(&sm.s_full);
+      cb::mbar_wait(&sm.r_full[1], 0);
+      kmajor_128(COL_LO, a_qv, cb::smem_u32(sm.r[1]));
+      cb::umma_commit(&sm.lo_full);
+      cb::mbar_wait(&sm.r_full[0], 0);
+      kmajor_128(COL_X, a_qv, cb::smem_u32(sm.r[0]));
+      cb::umma_commit(&sm.hi_full);
       for (int t = 0; t < nt; ++t) {
-        const int lo_b = (t + 1) & 1, hi_b = t & 1;
-        cb::mbar_wait(&sm.k_full, k_phase);
-        cb::mbar_wait(&sm.s_empty, s_phase ^ 1);
+        const uint32_t ph = t & 1;
+        // ---- dP(t) into the "hi" columns once every thread that needs them has staged them ----
+        cb::mbar_wait(&sm.hi_done, ph);
+        cb::mbar_wait(&sm.v_full, ph);
         cb::tc_fence_after();
-        {
-          const uint64_t aq = cb::umma_smem_desc(a_qu, 16, 1024), bk = cb::umma_smem_desc(a_k, 16, 1024);
-          const uint64_t ad = cb::umma_smem_desc(a_do, 16, 1024), bv = cb::umma_smem_desc(a_v, 16, 1024);
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_S, aq + 2 * k, bk + 2 * k, idesc_s, k > 0);
-#pragma unroll
-          for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_DP, ad + 2 * k, bv + 2 * k, idesc_s, k > 0);
+        kmajor_128(COL_X, a_do, a_v);
+        cb::umma_commit(&sm.dp_full);
+        cb::umma_commit(&sm.v_empty);
+        // ---- front of tile t+1 ----
+        if (t + 1 < nt) {
+          const int kb = (t + 1) & 1;
+          cb::mbar_wait(&sm.k_full[kb], ((t + 1) >> 1) & 1);
+          cb::mbar_wait(&sm.s_free, ph);
+          cb::tc_fence_after();
+          kmajor_128(COL_S, a_qu, cb::smem_u32(sm.k[kb]));
           cb::umma_commit(&sm.s_full);
+          cb::mbar_wait(&sm.r_full[(t + 2) % 3], ((t + 2) / 3) & 1);
+          cb::mbar_wait(&sm.lo_free, ph);
+          cb::tc_fence_after();
+          kmajor_128(COL_LO, a_qv, cb::smem_u32(sm.r[(t + 2) % 3]));
+          cb::umma_commit(&sm.lo_full);
+          cb::mbar_wait(&sm.x_free, ph);
+          cb::tc_fence_after();
+          kmajor_128(COL_X, a_qv, cb::smem_u32(sm.r[(t + 1) % 3]));
+          cb::umma_commit(&sm.hi_full);
         }
-        // beta = t+1 is the ((t+1)>>1)-th use of buffer lo_b; beta = t the (t>>1)-th use of hi_b
-        cb::mbar_wait(&sm.r_full[lo_b], ((t + 1) >> 1) & 1);
-        issue_bd(lo_b);
-        cb::mbar_wait(&sm.r_full[hi_b], (t >> 1) & 1);
-        issue_bd(hi_b);
-        // dq products
-        cb::mbar_wait(&sm.ds_full, ds_phase);
+        // ---- back of tile t: block beta = t is complete, dS(t) sits in TMEM ----
+        cb::mbar_wait(&sm.ds_full, ph);
         cb::tc_fence_after();
+        issue_band(t, t == 0);
+        cb::umma_commit(&sm.cb_free[t & 1]);
+        cb::umma_commit(&sm.r_empty[t % 3]);
         {
-          const uint64_t bk = cb::umma_smem_desc(a_k, 8192, 1024);
+          const uint64_t bk = cb::umma_smem_desc(cb::smem_u32(sm.k[t & 1]), 8192, 1024);
 #pragma unroll
           for (int k = 0; k < TN / 16; ++k)
-            umma_bf16_ts(tmem + COL_DQA, tmem + COL_BD + 8 * k, bk + (uint64_t)(k * 128), idesc_q, (t > 0 || k > 0));
-          const uint64_t blo = cb::umma_smem_desc(cb::smem_u32(sm.r[lo_b]), 8192, 1024);
-          const uint64_t bhi = cb::umma_smem_desc(cb::smem_u32(sm.r[hi_b]), 8192, 1024);
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const uint64_t ad = cb::umma_smem_desc(a_dbd + (k >> 2) * TILE_BYTES, 16, 1024) + 2 * (k & 3);
-            const uint64_t bd = (k < 8 ? blo : bhi) + (uint64_t)((k & 7) * 128);
-            cb::umma_bf16_ss(tmem + COL_DQB, ad, bd, idesc_q, (t > 0 || k > 0));
-          }
-          cb::umma_commit(&sm.k_empty);
-          cb::umma_commit(&sm.r_empty[hi_b]);
-          cb::umma_commit(&sm.ds_empty);
+            umma_bf16_ts(tmem + COL_DQ, tmem + COL_DS + 8 * k, bk + (uint64_t)(k * 128), idesc_a, 1);
         }
-        k_phase ^= 1;
-        s_phase ^= 1;
-        ds_phase ^= 1;
+        cb::umma_commit(&sm.ds_free);
+        cb::umma_commit(&sm.k_empty[t & 1]);
       }
+      // tail: block beta = nt holds the "lo" part of the last tile (its "hi" part was zeroed)
+      issue_band(nt, false);
       cb::umma_commit(&sm.acc_full);
     }
   } else if (warp >= 4) {
     // ============================== softmax warpgroups ==============================
+    // thread = (query row li, 32-key chunk g); the four warps of a row group (same wq) share one scheduler
     const int g = (warp - 4) >> 2;
     const int wq = (warp - 4) & 3;
     const int li = wq * 32 + lane;
     const int i = i0 + li;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t my_row = cb::smem_u32(sm.bd) + li * STAGE_ROW;
-    const uint32_t dbd_base = cb::smem_u32(sm.dbd);
+    const uint32_t cb0 = cb::smem_u32(sm.cb[0]);
+    const uint32_t piece = wq * 4 * QG;                               // this row group's piece of a block buffer
+    const uint32_t stg = piece + stage_row_off(lane) - 64 * wq;       // staged row: byte offset of position 0
+    const uint32_t rowoff = (li >> 3) * QG + (li & 7) * 2;            // (row li, idx 0) inside a block buffer
+    const int c0 = li + (TN - 1) - g * 32;                             // band column of this thread's first key
     const float sl2 = p.scale * 1.4426950408889634f;
-    uint32_t s_phase = 0, bd_phase = 0, ds_phase = 0;
     const float lse2 = i < p.T ? p.lse[((long long)b * p.H + h) * p.T + i] * 1.4426950408889634f : 0.f;
     const float delta = i < p.T ? p.delta[((long long)b * p.H + h) * p.T + i] : 0.f;
     const int hi_i = i < p.T ? i + p.M : -1;
     const int lo_i = key_lo(i, p.M, p.same_length, p.shift, reset);
-    // the band tile starts as zeros; each row only ever rewrites its own run of 128 band columns
-    for (int idx = threadIdx.x - 128; idx < 4 * TILE_BYTES / 16; idx += SOFT) sts_v4(dbd_base + idx * 16, 0, 0, 0, 0);
+    // block 0 only ever receives its "hi" part (from tile 0): its "lo" part starts as zeros
+    for (int x = (g * 32 + lane) * 16; x < 4 * QG; x += 128 * 16) sts_v4(cb0 + piece + x, 0, 0, 0, 0);
 
     for (int t = 0; t < nt; ++t) {
-      cb::mbar_wait(&sm.s_full, s_phase);
+      const uint32_t ph = t & 1;
+      const uint32_t buf_lo = cb0 + ((t + 1) & 1) * CB_BYTES;   // block t+1: staged rows now, "lo" scatter later
+      const uint32_t buf_hi = cb0 + (t & 1) * CB_BYTES;         // block t: "hi" scatter
+      const uint32_t row_v = buf_lo + stg;
+      // ---- scores of this thread's 32 key columns ----
+      cb::mbar_wait(&sm.s_full, ph);
       cb::tc_fence_after();
       float s[32];
       {
         uint32_t r0[32];
         cb::tmem_ld_32x32b_x32(lane_addr + COL_S + g * 32, r0);
         cb::tmem_ld_wait();
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.s_free);
 #pragma unroll
         for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]);
       }
-      cb::mbar_wait(&sm.bd_full, bd_phase);
-      cb::tc_fence_after();
-      named_bar(1, SOFT);
-      stage32(lane_addr + COL_BD + g * 32, my_row + g * 64);
-      cb::tc_fence_before();
-      cb::mbar_arrive(&sm.bd_empty);
-      bd_phase ^= 1;
-      named_bar(2, SOFT);
-      band_add<0, true>(s, my_row, li, g, wq);
-      cb::mbar_wait(&sm.bd_full, bd_phase);
-      cb::tc_fence_after();
-      named_bar(1, SOFT);
-      stage32(lane_addr + COL_BD + g * 32, my_row + g * 64);
-      cb::tc_fence_before();
-      cb::mbar_arrive(&sm.bd_empty);
-      bd_phase ^= 1;
-      named_bar(2, SOFT);     // also: every thread of the row has finished reading BD from TMEM (dS aliases it)
-      band_add<1, true>(s, my_row, li, g, wq);
-      const int jc0 = (jt_first + t) * TN + g * 32;
-      const bool full = (jc0 + 31 <= hi_i) && (jc0 >= lo_i);
-      float ds[32];
-      {
+      // ---- relative shift: stage the band columns this row group needs, read them back sheared.  The staged
+      // rows live in the buffer of block t+1, whose previous occupant (block t-1) must have been consumed.
+      if (t > 0) cb::mbar_wait(&sm.cb_free[(t + 1) & 1], ((t - 1) >> 1) & 1);
+      if (g >= wq) {
+        cb::mbar_wait(&sm.lo_full, ph);
+        cb::tc_fence_after();
         uint32_t r0[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_DP + g * 32, r0);
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_LO + g * 32, r0);
         cb::tmem_ld_wait();
         cb::tc_fence_before();
-        cb::mbar_arrive(&sm.s_empty);
-        s_phase ^= 1;
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float pv = ex2(fmaf(s[e], sl2, -lse2));
-          if (!full) {
-            const int j = jc0 + e;
-            if (j > hi_i || j < lo_i) pv = 0.f;
-          }
-          ds[e] = pv * (__uint_as_float(r0[e]) - delta);
-        }
+        cb::mbar_arrive(&sm.lo_free);
+        pack_store32(row_v + 64 * g, r0);
       }
-      // ---- dS -> TMEM (A operand of dq_ac) and, inverse-shifted, -> the band tile (A operand of dq_bd) ----
-      cb::mbar_wait(&sm.ds_empty, ds_phase ^ 1);
-      cb::tc_fence_after();
+      if (g <= wq) {
+        cb::mbar_wait(&sm.hi_full, ph);
+        cb::tc_fence_after();
+        uint32_t r0[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_X + g * 32, r0);
+        cb::tmem_ld_wait();
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.hi_done);
+        pack_store32(row_v + 256 + 64 * g, r0);
+      }
+      named_bar(2 + wq, NWG * 32);              // the positions of this row group are staged
+      shear_add32(s, row_v + 2 * c0);
+      // ---- P = exp2(score*log2e - LSE), dS = P * (dP - Delta) ----
+      const int jc0 = (jt_first + t) * TN + g * 32;
+      const bool full = (jc0 + 31 <= hi_i) && (jc0 >= lo_i);
+      uint32_t dsk[16];
       {
-        uint32_t pk[16];
+        cb::mbar_wait(&sm.dp_full, ph);
+        cb::tc_fence_after();
+        uint32_t r0[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_X + g * 32, r0);
+        cb::tmem_ld_wait();
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.x_free);
+        if (__all_sync(0xffffffffu, full)) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) pk[e / 2] = cb::pack_bf16(ds[e], ds[e + 1]);
-        tmem_st_32x32b_x16(lane_addr + COL_BD + g * 16, pk);
-        const int c0 = li + (TN - 1) - g * 32;       // band column of this thread's first key
-        const uint32_t rowb = dbd_base + li * 128;
-        const int sw = li & 7;
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
+            dsk[e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
+          }
+        } else {
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int c = c0 - e;                      // 0 .. 254
-          const uint32_t addr = rowb + (c >> 6) * TILE_BYTES + ((((c & 63) >> 3) ^ sw) << 4) + (c & 7) * 2;
-          const unsigned short hv = __bfloat16_as_ushort(__float2bfloat16_rn(ds[e]));
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(hv) : "memory");
+          for (int e = 0; e < 32; e += 2) {
+            const int j = jc0 + e;
+            float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
+            p0 = (j > hi_i || j < lo_i) ? 0.f : p0;
+            p1 = (j + 1 > hi_i || j + 1 < lo_i) ? 0.f : p1;
+            dsk[e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
+          }
         }
-        tmem_st_wait();
       }
+      // ---- dS -> TMEM (A operand of dq += dS K); the previous tile's product must be done with those columns ----
+      if (t > 0) {
+        cb::mbar_wait(&sm.ds_free, ph ^ 1);
+        cb::tc_fence_after();
+      }
+      tmem_st_32x32b_x16(lane_addr + COL_DS + g * 16, dsk);
+      named_bar(2 + wq, NWG * 32);              // the row group is done with its staged rows (block t+1 aliases them)
+      if (t == nt - 1) {                        // nobody will write the "hi" part of block nt: clear the piece first
+        for (int x = (g * 32 + lane) * 16; x < 4 * QG; x += 128 * 16) sts_v4(buf_lo + piece + x, 0, 0, 0, 0);
+        named_bar(2 + wq, NWG * 32);
+      }
+      // ---- inverse shift: dS[li, lj] -> band column c = c0 - e; c < 128: block t+1 at idx c, else block t at c - 128 ----
+      if (g != wq) {
+        const uint32_t base = (g > wq ? buf_lo + 16 * c0 : buf_hi + 16 * (c0 - 128)) + rowoff;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) sts_halves(base - 16 * e, base - 16 * (e + 1), dsk[e / 2]);
+      } else {                                  // diagonal chunk: e < lane -> "hi", e >= lane -> "lo"
+        const uint32_t base_lo = buf_lo + 16 * c0 + rowoff;
+        const uint32_t base_hi = buf_hi + 16 * (c0 - 128) + rowoff;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2)
+          sts_halves((e < lane ? base_hi : base_lo) - 16 * e, (e + 1 < lane ? base_hi : base_lo) - 16 * (e + 1), dsk[e / 2]);
+      }
+      tmem_st_wait();
       cb::fence_proxy_async();
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.ds_full);
-      ds_phase ^= 1;
     }
     // ---- epilogue ----
     cb::mbar_wait(&sm.acc_full, 0);
     cb::tc_fence_after();
-    uint32_t ra[16], rb[16];
-    tmem_ld_32x32b_x16(lane_addr + COL_DQA + g * 16, ra);
-    tmem_ld_32x32b_x16(lane_addr + COL_DQB + g * 16, rb);
+    uint32_t ra[16];
+    tmem_ld_32x32b_x16(lane_addr + COL_DQ + g * 16, ra);
     cb::tmem_ld_wait();
-    float fa[16], fb[16];
+    float fa[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      fa[e] = __uint_as_float(ra[e]) * p.scale;
-      fb[e] = __uint_as_float(rb[e]) * p.scale;
-    }
+    for (int e = 0; e < 16; ++e) fa[e] = __uint_as_float(ra[e]) * p.scale;
     if (i < p.T) {
       bf16* dqr = p.dq + ((long long)i * p.B + b) * p.lddq + h * DH + g * 16;
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
         uint4 q;
-        q.x = cb::pack_bf16(fa[ch * 8 + 0] + fb[ch * 8 + 0], fa[ch * 8 + 1] + fb[ch * 8 + 1]);
-        q.y = cb::pack_bf16(fa[ch * 8 + 2] + fb[ch * 8 + 2], fa[ch * 8 + 3] + fb[ch * 8 + 3]);
-        q.z = cb::pack_bf16(fa[ch * 8 + 4] + fb[ch * 8 + 4], fa[ch * 8 + 5] + fb[ch * 8 + 5]);
-        q.w = cb::pack_bf16(fa[ch * 8 + 6] + fb[ch * 8 + 6], fa[ch * 8 + 7] + fb[ch * 8 + 7]);
+        q.x = cb::pack_bf16(fa[ch * 8 + 0], fa[ch * 8 + 1]);
+        q.y = cb::pack_bf16(fa[ch * 8 + 2], fa[ch * 8 + 3]);
+        q.z = cb::pack_bf16(fa[ch * 8 + 4], fa[ch * 8 + 5]);
+        q.w = cb::pack_bf16(fa[ch * 8 + 6], fa[ch * 8 + 7]);
         *reinterpret_cast<uint4*>(dqr + ch * 8) = q;
       }
     }
-    // column sums over the 32 rows of this warp -> d r_w_bias / d r_r_bias (rows >= T hold exact zeros)
+    // column sums over the 32 rows of this warp -> d r_w_bias + d r_r_bias (rows >= T hold exact zeros); the dR
+    // pass later moves the d r_r_bias share from du to dvb
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
       const float sa = cb::warp_sum(fa[e]);
-      const float sb = cb::warp_sum(fb[e]);
-      if (lane == 0) {
-        atomicAdd(p.du + h * DH + g * 16 + e, sa);
-        atomicAdd(p.dvb + h * DH + g * 16 + e, sb);
-      }
+      if (lane == 0) atomicAdd(p.du + h * DH + g * 16 + e, sa);
     }
   }
   cb::tc_fence_before();
@@ -316,7 +376,9 @@ relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
 
 }  // namespace
 
-// dq / du / dvb of commu_relattn_bwd on tcgen05 (same operand contract).  delta = rowsum(dO * O) [B,H,T].
+// dq / (du + dvb) of commu_relattn_bwd on tcgen05 (same operand contract).  delta = rowsum(dO * O) [B,H,T].
+// du receives colsum(dq) = d r_w_bias + d r_r_bias; commu_relattn_bwd_dr_tc subtracts the d r_r_bias share and
+// adds it to dvb, so the two passes must run as a pair (commu_relattn_bwd does).
 extern "C" int commu_relattn_bwd_dq_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
                                        int64_t ldkv, const void* r, int64_t ldr, int kr,
                                        const unsigned char* reset, int T, int M, int B, int H, int same_length,

@@ -11,7 +11,11 @@
 // Window of query tile i0: keys jw0 .. jw0+255 with jw0 = i0 + M - d0 - 127; consecutive query tiles
 // share one 128-key block, which stays in shared memory.
 //
-// Autograd counterpart of commu/model/model.py:312-345 for d(r_head_k) (then d r_net.weight by a GEMM).
+//     g   += dS'^T 1                      column sums of dS' (N = 16 product against a tile of ones)
+// The column sums give d r_r_bias = scale * sum_delta g[delta] R[delta]; the dq pass has put
+// colsum(dq) = d r_w_bias + d r_r_bias into du, so this pass adds its share to dvb and subtracts it from du.
+//
+// Autograd counterpart of commu/model/model.py:312-345 for d(r_head_k) (then d r_net.weight by a GEMM) and r_r_bias.
 #include "api_common.h"
 #include "attn_common.cuh"
 #include "attn_tc_common.cuh"
@@ -33,7 +37,7 @@ constexpr int SOFT = 128 * NWG;
 constexpr int NTHREADS = 128 + SOFT;
 constexpr int TILE_BYTES = 128 * DH * 2;
 constexpr int BAND_THREADS = 32 * (NWG * (NWG + 1) / 2);   // threads (li, g) with g >= wq (or g <= wq): 320
-constexpr int COL_S = 0, COL_LO = 128, COL_HI = 256, COL_DR = 384;
+constexpr int COL_S = 0, COL_LO = 128, COL_HI = 256, COL_DR = 384, COL_G = 448;
 
 struct Smem {
   uint8_t r[TILE_BYTES];
@@ -42,8 +46,11 @@ struct Smem {
   uint8_t dout[2][TILE_BYTES];
   uint8_t k[2][TILE_BYTES];
   uint8_t v[2][TILE_BYTES];
-  uint8_t ds[TM * kStageRow];   // [2 distance atoms][128 q rows][128 B] (32 KB); ALSO the padded fp16 staging rows
-                                //   of the banded blocks (row li at ds + 272*li) earlier in the same iteration
+  uint8_t ds[16 * 3072];        // dS' tile: [16 groups of 8 q rows][distance atom0 | atom1 | spare][8 rows x 128 B];
+                                //   a row group (32 rows) owns 12 KB of it, which ALSO holds its staged fp16 rows
+                                //   of the banded blocks earlier in the same iteration (attn_tc_common.cuh)
+  uint8_t ones[512];            // bf16 1.0: B operand (K-major, no swizzle, N = 16) of the column-sum product
+  float gsum[TM];               // scale * column sums, for the d r_r_bias epilogue
   uint64_t r_full, q_full[2], q_empty[2], kv_full[2], kv_empty[2];
   uint64_t s_full, s_empty, lo_full, lo_empty, hi_full, hi_empty, pds_full, pds_empty, acc_full;
   uint32_t tmem_base;
@@ -80,6 +87,10 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     cb::mbar_init(&sm.pds_full, SOFT); cb::mbar_init(&sm.pds_empty, 1);
     cb::mbar_init(&sm.acc_full, 1);
     cb::fence_barrier_init();
+  }
+  if (warp == 3) {   // 512 bytes of bf16 ones
+    sts_v4(cb::smem_u32(sm.ones) + lane * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    cb::fence_proxy_async();
   }
   if (warp == 2) {
     cb::tmem_alloc(&sm.tmem_base, 512);
@@ -124,6 +135,8 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     if (cb::elect_one() && nq > 0) {
       const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);
       const uint32_t idesc_g = cb::umma_idesc_bf16(TN, DH, 1, 1);   // dR: MN-major A (dS'^T), MN-major B (q+v)
+      const uint32_t idesc_1 = cb::umma_idesc_bf16(TN, 16, 1, 0);   // g : MN-major A (dS'^T), K-major B (ones)
+      const uint64_t b_ones = umma_smem_desc_nosw(cb::smem_u32(sm.ones), 256, 128);
       uint32_t s_phase = 0, lo_phase = 0, hi_phase = 0, pds_phase = 0;
       const uint32_t a_r = cb::smem_u32(sm.r);
       cb::mbar_wait(&sm.r_full, 0);
@@ -168,11 +181,15 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
         cb::mbar_wait(&sm.pds_full, pds_phase);
         cb::tc_fence_after();
         {
-          const uint64_t as = cb::umma_smem_desc(cb::smem_u32(sm.ds), TILE_BYTES, 1024);
+          // MN-major A: 64-distance atoms 1024 B apart (LBO), 8-query-row groups 3072 B apart (SBO)
+          const uint64_t as = cb::umma_smem_desc(cb::smem_u32(sm.ds), 1024, 3072);
           const uint64_t bq = cb::umma_smem_desc(a_qv, 8192, 1024);
 #pragma unroll
           for (int k = 0; k < TM / 16; ++k)
-            cb::umma_bf16_ss(tmem + COL_DR, as + (uint64_t)(k * 128), bq + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
+            cb::umma_bf16_ss(tmem + COL_DR, as + (uint64_t)(k * 384), bq + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
+#pragma unroll
+          for (int k = 0; k < TM / 16; ++k)
+            cb::umma_bf16_ss(tmem + COL_G, as + (uint64_t)(k * 384), b_ones, idesc_1, (n > 0 || k > 0));
           cb::umma_commit(&sm.pds_empty);
           cb::umma_commit(&sm.q_empty[qb]);
         }
@@ -187,16 +204,30 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     const int wq = (warp - 4) & 3;
     const int li = wq * 32 + lane;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t my_row = cb::smem_u32(sm.ds) + li * kStageRow;   // staging row (aliases the dS' tile)
+    // staged row of this query row inside its row group's 12 KB piece; row_v = base of position 0
+    const uint32_t row_v = cb::smem_u32(sm.ds) + wq * 12288 + stage_row_off(lane) - 64 * wq;
+    const uint32_t shear0 = row_v + 2 * (li + 127 - 32 * g);
+    const uint32_t drow = cb::smem_u32(sm.ds) + (li >> 3) * 3072 + (g >> 1) * 1024 + (li & 7) * 128;
+    const int cx = ((g & 1) * 4) ^ (li & 7);
     const float sl2 = p.scale * 1.4426950408889634f;
     uint32_t s_phase = 0, band_phase = 0, pds_phase = 0;
     const float* lse_p = p.lse + ((long long)b * p.H + h) * p.T;
     const float* del_p = p.delta + ((long long)b * p.H + h) * p.T;
+    float lse_n = 0.f, del_n = 0.f;
+    {
+      const int i = it_first * TM + li;
+      if (nq > 0 && i < p.T) { lse_n = lse_p[i]; del_n = del_p[i]; }
+    }
 
     for (int n = 0; n < nq; ++n) {
       const int i = (it_first + n) * TM + li;
-      const float lse2 = i < p.T ? lse_p[i] * 1.4426950408889634f : 0.f;
-      const float delta = i < p.T ? del_p[i] : 0.f;
+      const float lse2 = lse_n * 1.4426950408889634f;
+      const float delta = del_n;
+      {
+        const int inext = i + TM;
+        lse_n = 0.f; del_n = 0.f;
+        if (n + 1 < nq && inext < p.T) { lse_n = lse_p[inext]; del_n = del_p[inext]; }
+      }
       const int lo_i = key_lo(i, p.M, p.same_length, p.shift, reset);
       cb::mbar_wait(&sm.s_full, s_phase);
       cb::tc_fence_after();
@@ -214,51 +245,55 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
           dp[e] = 0.f;
         }
       }
-      // two banded products (AC into s, dP into dp), each a "lo" and a "hi" block: a thread stages its 32 block
-      // columns from the block its row needs (both on the diagonal chunk) and reads the combined row circularly.
-      // The staging rows alias the dS' tile: the previous iteration's dR product must have consumed it first.
+      // two banded products (AC into s, dP into dp), each a "lo" and a "hi" block: the row group stages the block
+      // columns its rows need as fp16 positions and reads them back sheared.  The staged rows alias the dS' tile:
+      // the previous iteration's dR product must have consumed it first.
       cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
 #pragma unroll
       for (int prod = 0; prod < 2; ++prod) {
-        if (prod) named_bar(2 + wq, NWG * 32);  // this row group finished reading the AC rows
+        if (prod) named_bar(2 + wq, NWG * 32);  // this row group finished reading the AC positions
         if (g >= wq) {
           cb::mbar_wait(&sm.lo_full, band_phase);
           cb::tc_fence_after();
-          stage32_h(lane_addr + COL_LO + g * 32, my_row + 64 * g);
+          stage32_x16(lane_addr + COL_LO + g * 32, row_v + 64 * g);
           cb::tc_fence_before();
           cb::mbar_arrive(&sm.lo_empty);
         }
         if (g <= wq) {
           cb::mbar_wait(&sm.hi_full, band_phase);
           cb::tc_fence_after();
-          if (g < wq) stage32_h(lane_addr + COL_HI + g * 32, my_row + 64 * g);
-          else stage32_diag_hi_h(lane_addr + COL_HI + g * 32, my_row + 64 * g, lane);
+          stage32_x16(lane_addr + COL_HI + g * 32, row_v + 256 + 64 * g);
           cb::tc_fence_before();
           cb::mbar_arrive(&sm.hi_empty);
         }
         band_phase ^= 1;
-        named_bar(2 + wq, NWG * 32);            // the four chunks of this row group are staged
-        if (prod == 0) band_read(s, my_row, li, g, wq, lane);
-        else band_read(dp, my_row, li, g, wq, lane);
+        named_bar(2 + wq, NWG * 32);            // the positions of this row group are staged
+        if (prod == 0) shear_add32(s, shear0);
+        else shear_add32(dp, shear0);
       }
       // ---- P, dS' (columns are distances: key j = i + M - delta) ----
       uint32_t dsk[16];
+      const int jk0 = i + p.M - (d0 + g * 32);   // key of column 0; column e is key jk0 - e
+      const bool full = (i < p.T) && (jk0 - 31 >= lo_i);
+      if (__all_sync(0xffffffffu, full)) {
 #pragma unroll
-      for (int e = 0; e < 32; e += 2) {
-        const int dl = d0 + g * 32 + e;
-        const int j0k = i + p.M - dl;            // key of column e ; column e+1 is key j0k - 1
-        float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
-        if (i >= p.T || j0k < lo_i) p0 = 0.f;
-        if (i >= p.T || j0k - 1 < lo_i) p1 = 0.f;
-        dsk[e / 2] = cb::pack_bf16(p0 * (dp[e] - delta), p1 * (dp[e + 1] - delta));
-      }
-      named_bar(1, SOFT);                       // every thread is done with the last staged block (dS' aliases it)
-      {
-        const uint32_t drow = cb::smem_u32(sm.ds) + (g >> 1) * TILE_BYTES;
+        for (int e = 0; e < 32; e += 2) {
+          const float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
+          dsk[e / 2] = cb::pack_bf16(p0 * (dp[e] - delta), p1 * (dp[e + 1] - delta));
+        }
+      } else {
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-          sts_v4(drow + attn::swz(li, (g & 1) * 4 + c4), dsk[c4 * 4], dsk[c4 * 4 + 1], dsk[c4 * 4 + 2], dsk[c4 * 4 + 3]);
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
+          p0 = (i >= p.T || jk0 - e < lo_i) ? 0.f : p0;
+          p1 = (i >= p.T || jk0 - e - 1 < lo_i) ? 0.f : p1;
+          dsk[e / 2] = cb::pack_bf16(p0 * (dp[e] - delta), p1 * (dp[e + 1] - delta));
+        }
       }
+      named_bar(2 + wq, NWG * 32);              // the row group is done with its staged rows (dS' aliases them)
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4)
+        sts_v4(drow + ((cx ^ c4) << 4), dsk[c4 * 4], dsk[c4 * 4 + 1], dsk[c4 * 4 + 2], dsk[c4 * 4 + 3]);
       cb::fence_proxy_async();
       cb::mbar_arrive(&sm.pds_full);
       pds_phase ^= 1;
@@ -278,6 +313,26 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
           cb::red_add_v4(dst + e, __uint_as_float(rr[e]) * p.scale, __uint_as_float(rr[e + 1]) * p.scale,
                          __uint_as_float(rr[e + 2]) * p.scale, __uint_as_float(rr[e + 3]) * p.scale);
       }
+      // d r_r_bias share of this distance tile: scale * sum_li g[li] * R[d0 + li, :]  (rows >= Kr are zero-filled)
+      if (g == 0) {
+        uint32_t rg[16];
+        tmem_ld_32x32b_x16(lane_addr + COL_G, rg);
+        cb::tmem_ld_wait();
+        sm.gsum[li] = __uint_as_float(rg[0]) * p.scale;
+      }
+      named_bar(1, SOFT);
+      const int c = threadIdx.x - 128;
+      if (c < DH) {
+        float acc = 0.f;
+        const uint8_t* rt = sm.r;
+#pragma unroll 8
+        for (int rrow = 0; rrow < TN; ++rrow) {
+          const bf16 rv = *reinterpret_cast<const bf16*>(rt + attn::swz(rrow, c >> 3) + (c & 7) * 2);
+          acc = fmaf(sm.gsum[rrow], __bfloat162float(rv), acc);
+        }
+        atomicAdd(p.dvb + h * DH + c, acc);
+        atomicAdd(p.du + h * DH + c, -acc);
+      }
     }
   }
   cb::tc_fence_before();
@@ -291,11 +346,12 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
 }  // namespace
 
 // dR of commu_relattn_bwd on tcgen05: dr fp32 [kr, H*64] accumulated (+=) over batch.  delta = rowsum(dO*O).
+// Also moves the d r_r_bias share of colsum(dq) (left in du by commu_relattn_bwd_dq_tc) from du to dvb.
 extern "C" int commu_relattn_bwd_dr_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
                                        int64_t ldkv, const void* r, int64_t ldr, int kr,
                                        const unsigned char* reset, int T, int M, int B, int H, int same_length,
                                        int shift, float scale, const float* lse, const void* dout, int64_t lddo,
-                                       const float* delta, float* dr, void* stream_) {
+                                       const float* delta, float* dr, float* du, float* dvb, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   attn::Params p = {};
   p.q = (const bf16*)qu; p.k = (const bf16*)k; p.v = (const bf16*)v; p.r = (const bf16*)r;
@@ -308,10 +364,10 @@ extern "C" int commu_relattn_bwd_dr_tc(const void* qu, const void* qv, int64_t l
   p.same_length = same_length; p.shift = shift; p.scale = scale;
   p.lse = const_cast<float*>(lse); p.delta = delta;
   p.dout = (const bf16*)dout; p.lddo = lddo;
-  p.dr = dr;
+  p.dr = dr; p.du = du; p.dvb = dvb;
   int rc = cb_host::check_attn_common(p, "relattn_bwd_dr_tc");
   if (rc) return rc;
-  CB_REQUIRE(qv && lse && dout && delta && dr && lddo % 8 == 0, "relattn_bwd_dr_tc: bad args");
+  CB_REQUIRE(qv && lse && dout && delta && dr && du && dvb && lddo % 8 == 0, "relattn_bwd_dr_tc: bad args");
   const int Ktot = T + M;
   CUtensorMap tk, tv, tqu, tqv, tdo, tr;
   if ((rc = make_tmap_rows3d(&tk, k, (uint64_t)H * 64, B, Ktot, ldkv))) return rc;

@@ -10,7 +10,11 @@
 // The softmax threads (thread = query row x 64 key columns) recompute P = exp2(score*log2e - LSE),
 // form dS = P * (dP - Delta), and store both as bf16 rows of two shared-memory tiles whose layout is at
 // once the K-major [q][key] tile and the MN-major operand the dV / dK products need - no transpose.
-// The relative shift is the same private-row fp16 staging as in the forward kernel, one block at a time.
+// The relative shift: every row group (32 query rows = one TMEM lane quadrant = the four warps of one
+// scheduler) stages the band-block columns its rows need as fp16 "positions" (attn_tc_common.cuh) and reads
+// them back sheared with packed 32-bit loads + FHADD.  The P / dS tiles are laid out so that a row group owns
+// one contiguous 16 KB piece ([8-row group][P atom0 | P atom1 | dS atom0 | dS atom1]); the staged rows
+// alias that piece, so the softmax loop synchronises row groups only (128-thread named barriers).
 //
 // Autograd counterpart of commu/model/model.py:312-345 for d(keys), d(values).
 #include "api_common.h"
@@ -43,8 +47,8 @@ struct Smem {
   uint8_t qv[2][TILE_BYTES];    // the current one is being processed
   uint8_t dout[2][TILE_BYTES];
   uint8_t r[2][TILE_BYTES];
-  uint8_t p[2 * TILE_BYTES];    // [2 key atoms][128 q rows][128 B]; ALSO the fp16 staging rows of the BD blocks
-  uint8_t ds[2 * TILE_BYTES];   //   (row li at p + 256*li) earlier in the same iteration
+  uint8_t pds[4 * TILE_BYTES];  // [16 groups of 8 q rows][P atom0 | P atom1 | dS atom0 | dS atom1][8 rows x 128 B];
+                                //   ALSO the fp16 staging rows of the BD blocks (row group wq: pds + 16 KB * wq)
   uint64_t kv_full, q_full[2], q_empty[2], r_full[2], r_empty[2];
   uint64_t s_full, s_empty, lo_full, lo_empty, hi_full, hi_empty, pds_full, pds_empty, acc_full;
   uint32_t tmem_base;
@@ -179,15 +183,16 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         cb::mbar_wait(&sm.pds_full, pds_phase);
         cb::tc_fence_after();
         {
-          const uint64_t ap = cb::umma_smem_desc(cb::smem_u32(sm.p), TILE_BYTES, 1024);
-          const uint64_t as = cb::umma_smem_desc(cb::smem_u32(sm.ds), TILE_BYTES, 1024);
+          // MN-major A: 64-key atoms 1024 B apart (LBO), 8-query-row groups 4096 B apart (SBO); 16 rows per MMA
+          const uint64_t ap = cb::umma_smem_desc(cb::smem_u32(sm.pds), 1024, 4096);
+          const uint64_t as = cb::umma_smem_desc(cb::smem_u32(sm.pds) + 2048, 1024, 4096);
           const uint64_t bo = cb::umma_smem_desc(a_do, 8192, 1024), bq = cb::umma_smem_desc(a_qu, 8192, 1024);
 #pragma unroll
           for (int k = 0; k < TM / 16; ++k)
-            cb::umma_bf16_ss(tmem + COL_DV, ap + (uint64_t)(k * 128), bo + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
+            cb::umma_bf16_ss(tmem + COL_DV, ap + (uint64_t)(k * 512), bo + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
 #pragma unroll
           for (int k = 0; k < TM / 16; ++k)
-            cb::umma_bf16_ss(tmem + COL_DK, as + (uint64_t)(k * 128), bq + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
+            cb::umma_bf16_ss(tmem + COL_DK, as + (uint64_t)(k * 512), bq + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
           cb::umma_commit(&sm.pds_empty);
           cb::umma_commit(&sm.q_empty[qb]);
         }
@@ -202,16 +207,32 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
     const int wq = (warp - 4) & 3;
     const int li = wq * 32 + lane;               // query row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
-    const uint32_t my_row = cb::smem_u32(sm.p) + li * kStageRow;   // staging row (aliases the P / dS tiles)
+    // staged row of this query row inside its row group's 16 KB piece; row_v = base of position 0
+    const uint32_t row_v = cb::smem_u32(sm.pds) + wq * 16384 + stage_row_off(lane) - 64 * wq;
+    const uint32_t shear0 = row_v + 2 * (li + 127 - 32 * g);      // position of this thread's first key column
+    // rows of the P / dS tiles: 8-row group li>>3, key atom g>>1, chunks 4*(g&1)..+3 (128B swizzle)
+    const uint32_t prow = cb::smem_u32(sm.pds) + (li >> 3) * 4096 + (g >> 1) * 1024 + (li & 7) * 128;
+    const int cx = ((g & 1) * 4) ^ (li & 7);
     const float sl2 = p.scale * 1.4426950408889634f;
     uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
     const float* lse_p = p.lse + ((long long)b * p.H + h) * p.T;
     const float* del_p = p.delta + ((long long)b * p.H + h) * p.T;
+    // per-row constants of the next tile are fetched one tile ahead
+    float lse_n = 0.f, del_n = 0.f;
+    {
+      const int i = it_first * TM + li;
+      if (nq > 0 && i < p.T) { lse_n = lse_p[i]; del_n = del_p[i]; }
+    }
 
     for (int n = 0; n < nq; ++n) {
       const int i = (it_first + n) * TM + li;
-      const float lse2 = i < p.T ? lse_p[i] * 1.4426950408889634f : 0.f;
-      const float delta = i < p.T ? del_p[i] : 0.f;
+      const float lse2 = lse_n * 1.4426950408889634f;
+      const float delta = del_n;
+      {
+        const int inext = i + TM;
+        lse_n = 0.f; del_n = 0.f;
+        if (n + 1 < nq && inext < p.T) { lse_n = lse_p[inext]; del_n = del_p[inext]; }
+      }
       const int hi_i = i < p.T ? i + p.M : -1;
       const int lo_i = key_lo(i, p.M, p.same_length, p.shift, reset);
       // ---- scores of this thread's 32 key columns ----
@@ -225,28 +246,32 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
 #pragma unroll
         for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]);
       }
-      // ---- relative shift: each thread stages its 32 band-block columns from the block its row needs ("lo" for
-      // idx >= li, "hi" below; both on the diagonal chunk) and reads the combined row circularly.
-      // The staging rows alias the P / dS tiles: the previous iteration's dV / dK products must be done with them.
+      // ---- relative shift: stage the band-block columns this row group needs, then read them back sheared.
+      // The staged rows alias the P / dS tiles: the previous iteration's dV / dK products must be done with them.
       cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
       if (g >= wq) {
         cb::mbar_wait(&sm.lo_full, bd_phase);
         cb::tc_fence_after();
-        stage32(lane_addr + COL_BD + g * 32, my_row + 64 * g);
+        uint32_t r0[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 32, r0);
+        cb::tmem_ld_wait();
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.lo_empty);
+        pack_store32(row_v + 64 * g, r0);
       }
       if (g <= wq) {
         cb::mbar_wait(&sm.hi_full, bd_phase);
         cb::tc_fence_after();
-        if (g < wq) stage32(lane_addr + COL_BD + g * 32, my_row + 64 * g);
-        else stage32_diag_hi(lane_addr + COL_BD + g * 32, my_row + 64 * g, lane);
+        uint32_t r0[32];
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 32, r0);
+        cb::tmem_ld_wait();
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.hi_empty);
+        pack_store32(row_v + 256 + 64 * g, r0);
       }
       bd_phase ^= 1;
-      named_bar(2 + wq, NWG * 32);              // the four chunks of this row group are staged
-      band_read(s, my_row, li, g, wq, lane);
+      named_bar(2 + wq, NWG * 32);              // the positions of this row group are staged
+      shear_add32(s, shear0);
       // ---- P = exp2(score*log2e - LSE), dS = P * (dP - Delta)  (the 1/sqrt(Dh) factor is applied to dK at the end)
       const int jc0 = j0 + g * 32;
       const bool full = (jc0 + 31 <= hi_i) && (jc0 >= lo_i);
@@ -258,29 +283,31 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.s_empty);
         s_phase ^= 1;
+        if (__all_sync(0xffffffffu, full)) {
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
-          if (!full) {
-            const int j = jc0 + e;
-            if (j > hi_i || j < lo_i) p0 = 0.f;
-            if (j + 1 > hi_i || j + 1 < lo_i) p1 = 0.f;
+          for (int e = 0; e < 32; e += 2) {
+            const float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
+            pk[e / 2] = cb::pack_bf16(p0, p1);
+            dsk[e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
           }
-          pk[e / 2] = cb::pack_bf16(p0, p1);
-          dsk[e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const int j = jc0 + e;
+            float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
+            p0 = (j > hi_i || j < lo_i) ? 0.f : p0;
+            p1 = (j + 1 > hi_i || j + 1 < lo_i) ? 0.f : p1;
+            pk[e / 2] = cb::pack_bf16(p0, p1);
+            dsk[e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
+          }
         }
       }
-      // ---- rows of the P / dS tiles: key atom g/2, query row li, chunks 4*(g&1) .. +3 (swizzled) ----
-      named_bar(1, SOFT);                       // every thread is done with the staged rows (P / dS alias them)
-      {
-        const uint32_t prow = cb::smem_u32(sm.p) + (g >> 1) * TILE_BYTES;
-        const uint32_t drow = cb::smem_u32(sm.ds) + (g >> 1) * TILE_BYTES;
+      named_bar(2 + wq, NWG * 32);              // the row group is done with its staged rows (P / dS alias them)
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const uint32_t off = attn::swz(li, (g & 1) * 4 + c4);
-          sts_v4(prow + off, pk[c4 * 4], pk[c4 * 4 + 1], pk[c4 * 4 + 2], pk[c4 * 4 + 3]);
-          sts_v4(drow + off, dsk[c4 * 4], dsk[c4 * 4 + 1], dsk[c4 * 4 + 2], dsk[c4 * 4 + 3]);
-        }
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const uint32_t a = prow + ((cx ^ c4) << 4);
+        sts_v4(a, pk[c4 * 4], pk[c4 * 4 + 1], pk[c4 * 4 + 2], pk[c4 * 4 + 3]);
+        sts_v4(a + 2048, dsk[c4 * 4], dsk[c4 * 4 + 1], dsk[c4 * 4 + 2], dsk[c4 * 4 + 3]);
       }
       cb::fence_proxy_async();
       cb::mbar_arrive(&sm.pds_full);

@@ -214,6 +214,99 @@ __device__ __forceinline__ void band_read(float (&s)[32], uint32_t row, int li, 
   }
 }
 
+// ---- v3 shear: positions, packed reads, mixed-precision adds ----
+// A row group (the 32 query rows of TMEM lane quadrant wq) needs, for row li = 32*wq + l, the band indices
+// idx in [li, li+127]: idx < 128 comes from the "lo" 128-distance block, idx >= 128 from the "hi" block at
+// idx - 128.  Over the whole group that is the index window [32*wq, 32*wq + 160).  A staged row therefore
+// holds 160 fp16 POSITIONS (320 bytes, placed by stage_row_off): thread (li, g) copies its 32 block columns
+// 32g..32g+31 of "lo" to positions 32g (only if g >= wq) and of "hi" to positions 128 + 32g (only if
+// g <= wq).  The relative shift is then the plain descending read  pos = li + 127 - lc  with no select:
+// `row_v` below is the row's base minus 64*wq bytes, so that byte offset = 2 * pos.
+// Placement of the 32 staged rows (320 bytes each) of a row group inside its private piece (kStageGroupBytes):
+// row l = 8k + m sits in region m>>1 (a region = 8 rows + one 16-byte gap) at slot 2k + (m&1).  The 16-byte
+// stores of 8 consecutive lanes then start in 8 different 16-byte columns of a 128-byte line, and the sheared
+// 32-bit reads of 32 consecutive rows fall into 32 different banks: both directions are conflict-free.
+constexpr int kStageGroupBytes = 10288;
+__device__ __forceinline__ uint32_t stage_row_off(int l) {
+  return 16u * (161u * ((l & 7) >> 1) + 20u * (2u * (l >> 3) + (l & 1)));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// x0 += f16 low half of pr, x1 += f16 high half (FHADD: one instruction each, no separate convert)
+__device__ __forceinline__ void fhadd2(float& x0, float& x1, uint32_t pr) {
+  asm("{\n\t.reg .b16 l, h;\n\t"
+      "mov.b32 {l, h}, %2;\n\t"
+      "add.f32.f16 %0, l, %0;\n\t"
+      "add.f32.f16 %1, h, %1;\n\t}"
+      : "+f"(x0), "+f"(x1)
+      : "r"(pr));
+}
+// 32 TMEM values -> 32 fp16 at dst (64 bytes, 16-byte aligned)
+__device__ __forceinline__ void pack_store32(uint32_t dst, const uint32_t (&r0)[32]) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 8)
+    sts_v4(dst + e * 2, pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1])),
+           pack_f16(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3])),
+           pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
+           pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
+}
+// s[e] += fp16 at (addr0 - 2e), e = 0..31.  addr0 is only 2-byte aligned: 17 aligned 32-bit words cover the
+// 64-byte window and one PRMT per pair (selector by the alignment phase) puts (e, e+1) into (low, high).
+__device__ __forceinline__ void shear_add32(float (&s)[32], uint32_t addr0) {
+  const uint32_t aw = addr0 & ~3u;
+  const uint32_t sel = (addr0 & 2u) ? 0x1032u : 0x7610u;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {   // two halves of 8 pairs: 9 words in flight keeps the register peak low
+    uint32_t w[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) w[k] = lds_u32(aw - 4 * (half * 8 + k));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint32_t pr;
+      asm("prmt.b32 %0, %1, %2, %3;" : "=r"(pr) : "r"(w[q]), "r"(w[q + 1]), "r"(sel));
+      fhadd2(s[half * 16 + 2 * q], s[half * 16 + 2 * q + 1], pr);
+    }
+  }
+}
+// 16-column variant of the TMEM -> fp16 staging copy (lower register peak)
+__device__ __forceinline__ void stage32_x16(uint32_t taddr, uint32_t dst) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r0[16];
+    tmem_ld_32x32b_x16(taddr + half * 16, r0);
+    cb::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; e += 8)
+      sts_v4(dst + half * 32 + e * 2, pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1])),
+             pack_f16(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3])),
+             pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
+             pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
+  }
+}
+
+// Shared-memory matrix descriptor without swizzle (layout type 0): core matrices of 8 rows x 16 bytes.
+//   MN-major: a core matrix holds 8 MN-elements (16 B) x 8 K-rows (16 B apart, 128 B total); `k_group_bytes`
+//             strides 8-K-row groups (LBO field), `mn_group_bytes` strides 8-element MN groups (SBO field).
+//   K-major : a core matrix holds 8 MN-rows x 8 K-elements; LBO strides the K chunks, SBO the 8-row groups.
+__device__ __forceinline__ uint64_t umma_smem_desc_nosw(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version = 1
+  return d;
+}
+// the two bf16 halves of `packed` to two shared-memory addresses
+__device__ __forceinline__ void sts_halves(uint32_t addr_lo, uint32_t addr_hi, uint32_t packed) {
+  asm volatile("{\n\t.reg .b16 l, h;\n\t"
+               "mov.b32 {l, h}, %2;\n\t"
+               "st.shared.b16 [%0], l;\n\t"
+               "st.shared.b16 [%1], h;\n\t}" ::"r"(addr_lo), "r"(addr_hi), "r"(packed) : "memory");
+}
+
 struct Ring {  // stage / parity bookkeeping of a 2-deep mbarrier ring
   int idx = 0;
   uint32_t phase = 0;

@@ -171,16 +171,18 @@ int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, const void* k
  * 1 = tcgen05 kernel (default), 0 = v1 warp-MMA kernel, negative = leave unchanged. */
 int commu_relattn_bwd_set_impl(int dq_tc, int dkv_tc, int dr_tc);
 /* dR pass of commu_relattn_bwd on tcgen05 tensor cores (diagonal walk: one CTA per 128 distances, dR
- * accumulated in TMEM, added to dr once per CTA).  Default dR pass of commu_relattn_bwd (COMMU_ATTN_BWD_DR=v1 selects the
- * warp-MMA pass). */
+ * accumulated in TMEM, added to dr once per CTA).  It also computes d r_r_bias from the column sums of the
+ * position-term gradient: the share is added to dvb and subtracted from du, where commu_relattn_bwd_dq_tc
+ * left colsum(dq) = d r_w_bias + d r_r_bias - the two tcgen05 passes run as a pair (COMMU_ATTN_BWD_DR=v1 or
+ * COMMU_ATTN_BWD_DQ=v1 selects the warp-MMA passes for both). */
 int commu_relattn_bwd_dr_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
                             int64_t ldkv, const void* r, int64_t ldr, int kr, const unsigned char* reset,
                             int T, int M, int B, int H, int same_length, int shift, float scale,
                             const float* lse, const void* dout, int64_t lddo, const float* delta, float* dr,
-                            void* stream);
-/* dq / d r_w_bias / d r_r_bias pass of commu_relattn_bwd on tcgen05 tensor cores (dS fed to the dq MMA
- * from TMEM, the inverse relative shift written as a band tile in shared memory).  Default dq pass of
- * commu_relattn_bwd (COMMU_ATTN_BWD_DQ=v1 selects the warp-MMA pass). */
+                            float* du, float* dvb, void* stream);
+/* dq pass of commu_relattn_bwd on tcgen05 tensor cores (dS fed to the dq MMA from TMEM, the inverse relative
+ * shift scattered into 128 x 128 distance blocks in shared memory).  du += colsum(dq) = d r_w_bias + d r_r_bias;
+ * dvb is left to commu_relattn_bwd_dr_tc (see there). */
 int commu_relattn_bwd_dq_tc(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
                             int64_t ldkv, const void* r, int64_t ldr, int kr, const unsigned char* reset,
                             int T, int M, int B, int H, int same_length, int shift, float scale,
