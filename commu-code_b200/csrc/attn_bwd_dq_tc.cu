@@ -39,7 +39,7 @@ using namespace attn_tc;
 constexpr int TM = 128, TN = 128, DH = 64;
 constexpr int NWG = 4;
 constexpr int SOFT = 128 * NWG;
-constexpr int NTHREADS = 128 + SOFT;
+constexpr int NTHREADS = 64 + SOFT;        // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer, warps 2-17: softmax
 constexpr int TILE_BYTES = 128 * DH * 2;      // 16 KB
 constexpr int QG = 2576;                      // bytes between the 8-row groups of a band block (2048 used); 4 * QG >= kStageGroupBytes
 constexpr int CB_BYTES = 16 * QG;             // one band block buffer
@@ -92,7 +92,7 @@ relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     cb::mbar_init(&sm.acc_full, 1);
     cb::fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     cb::tmem_alloc(&sm.tmem_base, 512);
     cb::tmem_relinquish();
   }
@@ -216,11 +216,11 @@ relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
       issue_band(nt, false);
       cb::umma_commit(&sm.acc_full);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 2) {
     // ============================== softmax warpgroups ==============================
     // thread = (query row li, 32-key chunk g); the four warps of a row group (same wq) share one scheduler
-    const int g = (warp - 4) >> 2;
-    const int wq = (warp - 4) & 3;
+    const int g = (warp - 2) >> 2;
+    const int wq = warp & 3;                     // TMEM lane quadrant of this warp (hardware: warp id % 4)
     const int li = wq * 32 + lane;
     const int i = i0 + li;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
@@ -255,28 +255,31 @@ relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
 #pragma unroll
         for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]);
       }
-      // ---- relative shift: stage the band columns this row group needs, read them back sheared.  The staged
-      // rows live in the buffer of block t+1, whose previous occupant (block t-1) must have been consumed.
-      if (t > 0) cb::mbar_wait(&sm.cb_free[(t + 1) & 1], ((t - 1) >> 1) & 1);
+      // ---- relative shift: copy the band columns this row needs (fp16 in registers), stage them once the buffer
+      // of block t+1 is free (its previous occupant, block t-1, must have been consumed), read them back sheared.
+      uint32_t pk[16];
       if (g >= wq) {
         cb::mbar_wait(&sm.lo_full, ph);
         cb::tc_fence_after();
-        uint32_t r0[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_LO + g * 32, r0);
-        cb::tmem_ld_wait();
+        load_pack32(lane_addr + COL_LO + g * 32, pk);
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.lo_free);
-        pack_store32(row_v + 64 * g, r0);
-      }
-      if (g <= wq) {
+      } else {
         cb::mbar_wait(&sm.hi_full, ph);
         cb::tc_fence_after();
-        uint32_t r0[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_X + g * 32, r0);
-        cb::tmem_ld_wait();
+        load_pack32(lane_addr + COL_X + g * 32, pk);
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.hi_done);
-        pack_store32(row_v + 256 + 64 * g, r0);
+      }
+      if (t > 0) cb::mbar_wait(&sm.cb_free[(t + 1) & 1], ((t - 1) >> 1) & 1);
+      store_packed32(g >= wq ? row_v + 64 * g : row_v + 256 + 64 * g, pk);
+      if (g == wq) {                            // the diagonal chunk needs both blocks
+        cb::mbar_wait(&sm.hi_full, ph);
+        cb::tc_fence_after();
+        load_pack32(lane_addr + COL_X + g * 32, pk);
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.hi_done);
+        store_packed32(row_v + 256 + 64 * g, pk);
       }
       named_bar(2 + wq, NWG * 32);              // the positions of this row group are staged
       shear_add32(s, row_v + 2 * c0);
@@ -368,7 +371,7 @@ relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
   }
   cb::tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     cb::tc_fence_after();
     cb::tmem_dealloc(tmem, 512);
   }

@@ -34,7 +34,7 @@ using namespace attn_tc;
 constexpr int TM = 128, TN = 128, DH = 64;
 constexpr int NWG = 4;
 constexpr int SOFT = 128 * NWG;
-constexpr int NTHREADS = 128 + SOFT;
+constexpr int NTHREADS = 64 + SOFT;        // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer, warps 2-17: softmax
 constexpr int TILE_BYTES = 128 * DH * 2;
 constexpr int BAND_THREADS = 32 * (NWG * (NWG + 1) / 2);   // threads (li, g) with g >= wq (or g <= wq): 320
 constexpr int COL_S = 0, COL_LO = 128, COL_HI = 256, COL_DR = 384, COL_G = 448;
@@ -88,11 +88,11 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     cb::mbar_init(&sm.acc_full, 1);
     cb::fence_barrier_init();
   }
-  if (warp == 3) {   // 512 bytes of bf16 ones
+  if (warp == 1) {   // 512 bytes of bf16 ones
     sts_v4(cb::smem_u32(sm.ones) + lane * 16, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
     cb::fence_proxy_async();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     cb::tmem_alloc(&sm.tmem_base, 512);
     cb::tmem_relinquish();
   }
@@ -197,11 +197,11 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
       }
       cb::umma_commit(&sm.acc_full);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 2) {
     // ============================== softmax warpgroups ==============================
     // thread = (query row li of the tile, 32-distance chunk g)
-    const int g = (warp - 4) >> 2;
-    const int wq = (warp - 4) & 3;
+    const int g = (warp - 2) >> 2;
+    const int wq = warp & 3;                     // TMEM lane quadrant of this warp (hardware: warp id % 4)
     const int li = wq * 32 + lane;
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     // staged row of this query row inside its row group's 12 KB piece; row_v = base of position 0
@@ -321,8 +321,8 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
         sm.gsum[li] = __uint_as_float(rg[0]) * p.scale;
       }
       named_bar(1, SOFT);
-      const int c = threadIdx.x - 128;
-      if (c < DH) {
+      const int c = li;
+      if (g == 0 && c < DH) {
         float acc = 0.f;
         const uint8_t* rt = sm.r;
 #pragma unroll 8
@@ -337,7 +337,7 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
   }
   cb::tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     cb::tc_fence_after();
     cb::tmem_dealloc(tmem, 512);
   }

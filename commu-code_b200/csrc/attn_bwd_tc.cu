@@ -35,10 +35,10 @@ using namespace attn_tc;
 constexpr int TM = 128, TN = 128, DH = 64;
 constexpr int NWG = 4;
 constexpr int SOFT = 128 * NWG;
-constexpr int NTHREADS = 128 + SOFT;
+constexpr int NTHREADS = 64 + SOFT;        // warp 0: TMA producer + TMEM allocator, warp 1: MMA issuer, warps 2-17: softmax
 constexpr int TILE_BYTES = 128 * DH * 2;      // 16 KB
 constexpr int BAND_THREADS = 32 * (NWG * (NWG + 1) / 2) * 4 / NWG;   // threads (li, g) with g >= wq (or g <= wq): 320
-constexpr int COL_S = 0, COL_DP = 128, COL_BD = 256, COL_DV = 384, COL_DK = 448;
+constexpr int COL_S = 0, COL_X = 128, COL_LO = 256, COL_DV = 384, COL_DK = 448;   // X: BD "hi", then dP
 
 struct Smem {
   uint8_t k[TILE_BYTES];
@@ -50,7 +50,7 @@ struct Smem {
   uint8_t pds[4 * TILE_BYTES];  // [16 groups of 8 q rows][P atom0 | P atom1 | dS atom0 | dS atom1][8 rows x 128 B];
                                 //   ALSO the fp16 staging rows of the BD blocks (row group wq: pds + 16 KB * wq)
   uint64_t kv_full, q_full[2], q_empty[2], r_full[2], r_empty[2];
-  uint64_t s_full, s_empty, lo_full, lo_empty, hi_full, hi_empty, pds_full, pds_empty, acc_full;
+  uint64_t s_full, s_free, lo_full, lo_free, hi_full, hi_done, dp_full, x_free, pds_full[4], pds_empty[4], acc_full;
   uint32_t tmem_base;
 };
 
@@ -80,14 +80,15 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
     cb::mbar_init(&sm.kv_full, 1);
     for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.q_full[s], 1); cb::mbar_init(&sm.q_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1); }
-    cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_empty, SOFT);
-    cb::mbar_init(&sm.lo_full, 1); cb::mbar_init(&sm.lo_empty, BAND_THREADS);
-    cb::mbar_init(&sm.hi_full, 1); cb::mbar_init(&sm.hi_empty, BAND_THREADS);
-    cb::mbar_init(&sm.pds_full, SOFT); cb::mbar_init(&sm.pds_empty, 1);
+    cb::mbar_init(&sm.s_full, 1); cb::mbar_init(&sm.s_free, SOFT);
+    cb::mbar_init(&sm.lo_full, 1); cb::mbar_init(&sm.lo_free, BAND_THREADS);
+    cb::mbar_init(&sm.hi_full, 1); cb::mbar_init(&sm.hi_done, BAND_THREADS);
+    cb::mbar_init(&sm.dp_full, 1); cb::mbar_init(&sm.x_free, SOFT);
+    for (int s = 0; s < 4; ++s) { cb::mbar_init(&sm.pds_full[s], NWG * 32); cb::mbar_init(&sm.pds_empty[s], 1); }
     cb::mbar_init(&sm.acc_full, 1);
     cb::fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 0) {
     cb::tmem_alloc(&sm.tmem_base, 512);
     cb::tmem_relinquish();
   }
@@ -102,12 +103,11 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
       cb::mbar_arrive_expect_tx(&sm.kv_full, 2 * TILE_BYTES);
       cb::tma_load_3d(sm.k, &tm_k, &sm.kv_full, h * DH, b, j0);
       cb::tma_load_3d(sm.v, &tm_v, &sm.kv_full, h * DH, b, j0);
-      Ring rr;
-      auto load_r = [&](int gamma) {
-        cb::mbar_wait(&sm.r_empty[rr.idx], rr.phase ^ 1);
-        cb::mbar_arrive_expect_tx(&sm.r_full[rr.idx], TILE_BYTES);
-        cb::tma_load_2d(sm.r[rr.idx], &tm_r, &sm.r_full[rr.idx], h * DH, dlo0 + TN * gamma);
-        rr.advance();
+      auto load_r = [&](int gamma) {   // slot gamma & 1, its (gamma >> 1)-th use
+        const int sl = gamma & 1;
+        cb::mbar_wait(&sm.r_empty[sl], ((gamma >> 1) & 1) ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.r_full[sl], TILE_BYTES);
+        cb::tma_load_2d(sm.r[sl], &tm_r, &sm.r_full[sl], h * DH, dlo0 + TN * gamma);
       };
       auto load_q = [&](int n) {   // buffer n&1, its (n>>1)-th use
         const int bi = n & 1;
@@ -118,11 +118,12 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         cb::tma_load_3d(sm.qv[bi], &tm_qv, &sm.q_full[bi], h * DH, b, i0);
         cb::tma_load_3d(sm.dout[bi], &tm_do, &sm.q_full[bi], h * DH, b, i0);
       };
-      load_r(0);
       load_q(0);
-      for (int n = 0; n < nq; ++n) {
-        load_r(n + 1);
-        if (n + 1 < nq) load_q(n + 1);
+      load_r(0);
+      load_r(1);
+      for (int n = 0; n + 1 < nq; ++n) {
+        load_q(n + 1);
+        load_r(n + 2);
       }
     }
   } else if (warp == 1) {
@@ -130,81 +131,85 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
     if (cb::elect_one() && nq > 0) {
       const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);   // S, BD, dP: K-major x K-major
       const uint32_t idesc_g = cb::umma_idesc_bf16(TN, DH, 1, 1);   // dV, dK: MN-major A (tile^T), MN-major B
-      Ring rr;
-      uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
       cb::mbar_wait(&sm.kv_full, 0);
-      uint32_t a_qu = 0, a_qv = 0, a_do = 0;
       const uint32_t a_k = cb::smem_u32(sm.k), a_v = cb::smem_u32(sm.v);
-      // the BD accumulator is shared by the "lo" and the "hi" block: lo(n) may overwrite it once the threads
-      // that stage hi(n-1) are done, hi(n) once lo(n) has been staged
-      auto issue_bd = [&](int ridx, bool hi) {
-        if (hi) cb::mbar_wait(&sm.lo_empty, bd_phase);
-        else cb::mbar_wait(&sm.hi_empty, bd_phase ^ 1);
-        cb::tc_fence_after();
-        const uint64_t ad = cb::umma_smem_desc(a_qv, 16, 1024);
-        const uint64_t bd = cb::umma_smem_desc(cb::smem_u32(sm.r[ridx]), 16, 1024);
+      auto kmajor_128 = [&](uint32_t col, uint32_t a_addr, uint32_t b_addr) {
+        const uint64_t ad = cb::umma_smem_desc(a_addr, 16, 1024);
+        const uint64_t bd = cb::umma_smem_desc(b_addr, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_BD, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
-        cb::umma_commit(hi ? &sm.hi_full : &sm.lo_full);
-        if (hi) bd_phase ^= 1;
+        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + col, ad + 2 * k, bd + 2 * k, idesc_s, k > 0);
       };
-      // "front" of query tile n: S, dP and the "lo" BD block.  It is issued one tile ahead (software
-      // pipelining): front(n+1) goes to the tensor cores while the softmax threads still finish tile n.
-      auto issue_front = [&](int n) {
-        const int qb = n & 1;
-        const uint32_t f_qu = cb::smem_u32(sm.qu[qb]), f_do = cb::smem_u32(sm.dout[qb]);
-        a_qv = cb::smem_u32(sm.qv[qb]);
-        cb::mbar_wait(&sm.q_full[qb], (n >> 1) & 1);
-        cb::mbar_wait(&sm.r_full[rr.idx], rr.phase);            // gamma = n ("lo")
-        cb::mbar_wait(&sm.s_empty, s_phase ^ 1);
-        cb::tc_fence_after();
-        const uint64_t aq = cb::umma_smem_desc(f_qu, 16, 1024), bk = cb::umma_smem_desc(a_k, 16, 1024);
-        const uint64_t ad = cb::umma_smem_desc(f_do, 16, 1024), bv = cb::umma_smem_desc(a_v, 16, 1024);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_S, aq + 2 * k, bk + 2 * k, idesc_s, k > 0);
-#pragma unroll
-        for (int k = 0; k < DH / 16; ++k) cb::umma_bf16_ss(tmem + COL_DP, ad + 2 * k, bv + 2 * k, idesc_s, k > 0);
-        cb::umma_commit(&sm.s_full);
-        s_phase ^= 1;
-        issue_bd(rr.idx, false);                                 // BD "lo" of tile n
-      };
-      issue_front(0);
+      // R blocks of query tile n: "lo" = gamma n, "hi" = gamma n+1 (slot gamma & 1).
+      // "front" of a tile = S, BD "lo", BD "hi": all three are issued one tile ahead (software pipelining), each
+      // as soon as the softmax threads have copied the previous contents of its TMEM columns; dP follows into
+      // the "hi" columns once those are staged.
+      cb::mbar_wait(&sm.q_full[0], 0);
+      cb::tc_fence_after();
+      kmajor_128(COL_S, cb::smem_u32(sm.qu[0]), a_k);
+      cb::umma_commit(&sm.s_full);
+      cb::mbar_wait(&sm.r_full[0], 0);
+      kmajor_128(COL_LO, cb::smem_u32(sm.qv[0]), cb::smem_u32(sm.r[0]));
+      cb::umma_commit(&sm.lo_full);
+      cb::umma_commit(&sm.r_empty[0]);
+      cb::mbar_wait(&sm.r_full[1], 0);
+      kmajor_128(COL_X, cb::smem_u32(sm.qv[0]), cb::smem_u32(sm.r[1]));
+      cb::umma_commit(&sm.hi_full);
       for (int n = 0; n < nq; ++n) {
         const int qb = n & 1;
-        a_qu = cb::smem_u32(sm.qu[qb]); a_qv = cb::smem_u32(sm.qv[qb]); a_do = cb::smem_u32(sm.dout[qb]);
-        // R blocks of this query tile: "lo" = gamma n (rr), "hi" = gamma n+1
-        const int lo_idx = rr.idx;
-        rr.advance();
-        cb::mbar_wait(&sm.r_full[rr.idx], rr.phase);            // gamma = n+1
-        issue_bd(rr.idx, true);                                  // BD "hi" (waits until "lo" has been staged)
-        cb::umma_commit(&sm.r_empty[lo_idx]);                    // gamma n is dead after this tile
-        if (n + 1 < nq) issue_front(n + 1);                      // rr now points at gamma n+1 = next tile's "lo"
-        // dV += P^T dO ; dK += dS^T (q+u)
-        cb::mbar_wait(&sm.pds_full, pds_phase);
+        const uint32_t ph = n & 1;
+        const uint32_t a_qu = cb::smem_u32(sm.qu[qb]), a_do = cb::smem_u32(sm.dout[qb]);
+        // ---- dP(n) into the "hi" columns once every thread that needs them has copied them ----
+        cb::mbar_wait(&sm.hi_done, ph);
         cb::tc_fence_after();
+        kmajor_128(COL_X, a_do, a_v);
+        cb::umma_commit(&sm.dp_full);
+        // ---- front of tile n+1 ----
+        if (n + 1 < nq) {
+          const int qn = (n + 1) & 1;
+          cb::mbar_wait(&sm.q_full[qn], ((n + 1) >> 1) & 1);
+          cb::mbar_wait(&sm.s_free, ph);
+          cb::tc_fence_after();
+          kmajor_128(COL_S, cb::smem_u32(sm.qu[qn]), a_k);
+          cb::umma_commit(&sm.s_full);
+          cb::mbar_wait(&sm.lo_free, ph);
+          cb::tc_fence_after();
+          kmajor_128(COL_LO, cb::smem_u32(sm.qv[qn]), cb::smem_u32(sm.r[(n + 1) & 1]));   // gamma = n+1 (resident)
+          cb::umma_commit(&sm.lo_full);
+          cb::umma_commit(&sm.r_empty[(n + 1) & 1]);                                       // last use of gamma n+1
+          cb::mbar_wait(&sm.r_full[n & 1], ((n + 2) >> 1) & 1);                             // gamma = n+2
+          cb::mbar_wait(&sm.x_free, ph);
+          cb::tc_fence_after();
+          kmajor_128(COL_X, cb::smem_u32(sm.qv[qn]), cb::smem_u32(sm.r[n & 1]));
+          cb::umma_commit(&sm.hi_full);
+        }
+        // ---- back of tile n: dV += P^T dO ; dK += dS^T (q+u), row group by row group (16 query rows per MMA) ----
         {
-          // MN-major A: 64-key atoms 1024 B apart (LBO), 8-query-row groups 4096 B apart (SBO); 16 rows per MMA
+          // MN-major A: 64-key atoms 1024 B apart (LBO), 8-query-row groups 4096 B apart (SBO)
           const uint64_t ap = cb::umma_smem_desc(cb::smem_u32(sm.pds), 1024, 4096);
           const uint64_t as = cb::umma_smem_desc(cb::smem_u32(sm.pds) + 2048, 1024, 4096);
           const uint64_t bo = cb::umma_smem_desc(a_do, 8192, 1024), bq = cb::umma_smem_desc(a_qu, 8192, 1024);
 #pragma unroll
-          for (int k = 0; k < TM / 16; ++k)
-            cb::umma_bf16_ss(tmem + COL_DV, ap + (uint64_t)(k * 512), bo + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
+          for (int rg = 0; rg < 4; ++rg) {
+            cb::mbar_wait(&sm.pds_full[rg], ph);
+            cb::tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < TM / 16; ++k)
-            cb::umma_bf16_ss(tmem + COL_DK, as + (uint64_t)(k * 512), bq + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
-          cb::umma_commit(&sm.pds_empty);
+            for (int k = 2 * rg; k < 2 * rg + 2; ++k)
+              cb::umma_bf16_ss(tmem + COL_DV, ap + (uint64_t)(k * 512), bo + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
+#pragma unroll
+            for (int k = 2 * rg; k < 2 * rg + 2; ++k)
+              cb::umma_bf16_ss(tmem + COL_DK, as + (uint64_t)(k * 512), bq + (uint64_t)(k * 128), idesc_g, (n > 0 || k > 0));
+            cb::umma_commit(&sm.pds_empty[rg]);
+          }
           cb::umma_commit(&sm.q_empty[qb]);
         }
-        pds_phase ^= 1;
       }
       cb::umma_commit(&sm.acc_full);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 2) {
     // ============================== softmax warpgroups ==============================
     // thread = (query row li of the tile, 32-key chunk g)
-    const int g = (warp - 4) >> 2;
-    const int wq = (warp - 4) & 3;
+    const int g = (warp - 2) >> 2;
+    const int wq = warp & 3;                     // TMEM lane quadrant of this warp (hardware: warp id % 4)
     const int li = wq * 32 + lane;               // query row inside the tile == TMEM lane
     const uint32_t lane_addr = tmem + (static_cast<uint32_t>(wq * 32) << 16);
     // staged row of this query row inside its row group's 16 KB piece; row_v = base of position 0
@@ -214,7 +219,6 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
     const uint32_t prow = cb::smem_u32(sm.pds) + (li >> 3) * 4096 + (g >> 1) * 1024 + (li & 7) * 128;
     const int cx = ((g & 1) * 4) ^ (li & 7);
     const float sl2 = p.scale * 1.4426950408889634f;
-    uint32_t s_phase = 0, bd_phase = 0, pds_phase = 0;
     const float* lse_p = p.lse + ((long long)b * p.H + h) * p.T;
     const float* del_p = p.delta + ((long long)b * p.H + h) * p.T;
     // per-row constants of the next tile are fetched one tile ahead
@@ -235,41 +239,47 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
       }
       const int hi_i = i < p.T ? i + p.M : -1;
       const int lo_i = key_lo(i, p.M, p.same_length, p.shift, reset);
+      const uint32_t ph = n & 1;
       // ---- scores of this thread's 32 key columns ----
-      cb::mbar_wait(&sm.s_full, s_phase);
+      cb::mbar_wait(&sm.s_full, ph);
       cb::tc_fence_after();
       float s[32];
       {
         uint32_t r0[32];
         cb::tmem_ld_32x32b_x32(lane_addr + COL_S + g * 32, r0);
         cb::tmem_ld_wait();
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.s_free);
 #pragma unroll
         for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]);
       }
-      // ---- relative shift: stage the band-block columns this row group needs, then read them back sheared.
-      // The staged rows alias the P / dS tiles: the previous iteration's dV / dK products must be done with them.
-      cb::mbar_wait(&sm.pds_empty, pds_phase ^ 1);
+      // ---- relative shift: copy the band-block columns this row needs (fp16, in registers), then - once the
+      // previous iteration's dV / dK products are done with the P / dS rows that the staged rows alias - put
+      // them into the row group's staging piece and read them back sheared.
+      uint32_t sg[16];
       if (g >= wq) {
-        cb::mbar_wait(&sm.lo_full, bd_phase);
+        cb::mbar_wait(&sm.lo_full, ph);
         cb::tc_fence_after();
-        uint32_t r0[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 32, r0);
-        cb::tmem_ld_wait();
+        load_pack32(lane_addr + COL_LO + g * 32, sg);
         cb::tc_fence_before();
-        cb::mbar_arrive(&sm.lo_empty);
-        pack_store32(row_v + 64 * g, r0);
-      }
-      if (g <= wq) {
-        cb::mbar_wait(&sm.hi_full, bd_phase);
+        cb::mbar_arrive(&sm.lo_free);
+      } else {
+        cb::mbar_wait(&sm.hi_full, ph);
         cb::tc_fence_after();
-        uint32_t r0[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_BD + g * 32, r0);
-        cb::tmem_ld_wait();
+        load_pack32(lane_addr + COL_X + g * 32, sg);
         cb::tc_fence_before();
-        cb::mbar_arrive(&sm.hi_empty);
-        pack_store32(row_v + 256 + 64 * g, r0);
+        cb::mbar_arrive(&sm.hi_done);
       }
-      bd_phase ^= 1;
+      if (n > 0) cb::mbar_wait(&sm.pds_empty[wq], ph ^ 1);
+      store_packed32(g >= wq ? row_v + 64 * g : row_v + 256 + 64 * g, sg);
+      if (g == wq) {                            // the diagonal chunk needs both blocks
+        cb::mbar_wait(&sm.hi_full, ph);
+        cb::tc_fence_after();
+        load_pack32(lane_addr + COL_X + g * 32, sg);
+        cb::tc_fence_before();
+        cb::mbar_arrive(&sm.hi_done);
+        store_packed32(row_v + 256 + 64 * g, sg);
+      }
       named_bar(2 + wq, NWG * 32);              // the positions of this row group are staged
       shear_add32(s, shear0);
       // ---- P = exp2(score*log2e - LSE), dS = P * (dP - Delta)  (the 1/sqrt(Dh) factor is applied to dK at the end)
@@ -277,12 +287,13 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
       const bool full = (jc0 + 31 <= hi_i) && (jc0 >= lo_i);
       uint32_t pk[16], dsk[16];
       {
+        cb::mbar_wait(&sm.dp_full, ph);
+        cb::tc_fence_after();
         uint32_t r0[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_DP + g * 32, r0);
+        cb::tmem_ld_32x32b_x32(lane_addr + COL_X + g * 32, r0);
         cb::tmem_ld_wait();
         cb::tc_fence_before();
-        cb::mbar_arrive(&sm.s_empty);
-        s_phase ^= 1;
+        cb::mbar_arrive(&sm.x_free);
         if (__all_sync(0xffffffffu, full)) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
@@ -310,8 +321,7 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         sts_v4(a + 2048, dsk[c4 * 4], dsk[c4 * 4 + 1], dsk[c4 * 4 + 2], dsk[c4 * 4 + 3]);
       }
       cb::fence_proxy_async();
-      cb::mbar_arrive(&sm.pds_full);
-      pds_phase ^= 1;
+      cb::mbar_arrive(&sm.pds_full[wq]);
     }
     // ---- epilogue: dV, dK rows (thread = key row li, 16 of the 64 head dims) ----
     const int j = j0 + li;
@@ -350,7 +360,7 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
   }
   cb::tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     cb::tc_fence_after();
     cb::tmem_dealloc(tmem, 512);
   }

@@ -253,6 +253,22 @@ __device__ __forceinline__ void pack_store32(uint32_t dst, const uint32_t (&r0)[
            pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
            pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
 }
+// 32 TMEM columns -> 16 registers of fp16 pairs (the TMEM read completes here)
+__device__ __forceinline__ void load_pack32(uint32_t taddr, uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {   // two 16-column reads: lower register peak
+    uint32_t r0[16];
+    tmem_ld_32x32b_x16(taddr + half * 16, r0);
+    cb::tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; e += 2)
+      pk[half * 8 + e / 2] = pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1]));
+  }
+}
+__device__ __forceinline__ void store_packed32(uint32_t dst, const uint32_t (&pk)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) sts_v4(dst + 16 * c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+}
 // s[e] += fp16 at (addr0 - 2e), e = 0..31.  addr0 is only 2-byte aligned: 17 aligned 32-bit words cover the
 // 64-byte window and one PRMT per pair (selector by the alignment phase) puts (e, e+1) into (low, high).
 __device__ __forceinline__ void shear_add32(float (&s)[32], uint32_t addr0) {
