@@ -242,73 +242,74 @@ relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
       const uint32_t buf_lo = cb0 + ((t + 1) & 1) * CB_BYTES;   // block t+1: staged rows now, "lo" scatter later
       const uint32_t buf_hi = cb0 + (t & 1) * CB_BYTES;         // block t: "hi" scatter
       const uint32_t row_v = buf_lo + stg;
-      // ---- scores of this thread's 32 key columns ----
-      cb::mbar_wait(&sm.s_full, ph);
-      cb::tc_fence_after();
-      float s[32];
-      {
-        uint32_t r0[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_S + g * 32, r0);
-        cb::tmem_ld_wait();
-        cb::tc_fence_before();
-        cb::mbar_arrive(&sm.s_free);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]);
-      }
       // ---- relative shift: copy the band columns this row needs (fp16 in registers), stage them once the buffer
-      // of block t+1 is free (its previous occupant, block t-1, must have been consumed), read them back sheared.
-      uint32_t pk[16];
+      // of block t+1 is free (its previous occupant, block t-1, must have been consumed); read back sheared below.
+      uint32_t sg[16], sg2[16];
       if (g >= wq) {
         cb::mbar_wait(&sm.lo_full, ph);
         cb::tc_fence_after();
-        load_pack32(lane_addr + COL_LO + g * 32, pk);
+        load_pack32(lane_addr + COL_LO + g * 32, sg);
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.lo_free);
-      } else {
+      }
+      if (g <= wq) {                            // the diagonal chunk (g == wq) needs both blocks
         cb::mbar_wait(&sm.hi_full, ph);
         cb::tc_fence_after();
-        load_pack32(lane_addr + COL_X + g * 32, pk);
+        if (g < wq) load_pack32(lane_addr + COL_X + g * 32, sg);
+        else load_pack32(lane_addr + COL_X + g * 32, sg2);
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.hi_done);
       }
       if (t > 0) cb::mbar_wait(&sm.cb_free[(t + 1) & 1], ((t - 1) >> 1) & 1);
-      store_packed32(g >= wq ? row_v + 64 * g : row_v + 256 + 64 * g, pk);
-      if (g == wq) {                            // the diagonal chunk needs both blocks
-        cb::mbar_wait(&sm.hi_full, ph);
-        cb::tc_fence_after();
-        load_pack32(lane_addr + COL_X + g * 32, pk);
-        cb::tc_fence_before();
-        cb::mbar_arrive(&sm.hi_done);
-        store_packed32(row_v + 256 + 64 * g, pk);
-      }
+      store_packed32(g >= wq ? row_v + 64 * g : row_v + 256 + 64 * g, sg);
+      if (g == wq) store_packed32(row_v + 256 + 64 * g, sg2);
       named_bar(2 + wq, NWG * 32);              // the positions of this row group are staged
-      shear_add32(s, row_v + 2 * c0);
-      // ---- P = exp2(score*log2e - LSE), dS = P * (dP - Delta) ----
+      // ---- P = exp2(score*log2e - LSE), dS = P * (dP - Delta), in two halves of 16 key columns (register peak) ----
       const int jc0 = (jt_first + t) * TN + g * 32;
-      const bool full = (jc0 + 31 <= hi_i) && (jc0 >= lo_i);
+      const bool full = __all_sync(0xffffffffu, (jc0 + 31 <= hi_i) && (jc0 >= lo_i));
       uint32_t dsk[16];
-      {
-        cb::mbar_wait(&sm.dp_full, ph);
-        cb::tc_fence_after();
-        uint32_t r0[32];
-        cb::tmem_ld_32x32b_x32(lane_addr + COL_X + g * 32, r0);
-        cb::tmem_ld_wait();
-        cb::tc_fence_before();
-        cb::mbar_arrive(&sm.x_free);
-        if (__all_sync(0xffffffffu, full)) {
+      cb::mbar_wait(&sm.s_full, ph);
+      cb::tc_fence_after();
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
+      for (int hf = 0; hf < 2; ++hf) {
+        float s[16];
+        {
+          uint32_t r0[16];
+          tmem_ld_32x32b_x16(lane_addr + COL_S + g * 32 + hf * 16, r0);
+          cb::tmem_ld_wait();
+          if (hf == 1) {
+            cb::tc_fence_before();
+            cb::mbar_arrive(&sm.s_free);
+          }
+#pragma unroll
+          for (int e = 0; e < 16; ++e) s[e] = __uint_as_float(r0[e]);
+        }
+        shear_add16(s, row_v + 2 * c0 - 32 * hf);
+        if (hf == 0) {
+          cb::mbar_wait(&sm.dp_full, ph);
+          cb::tc_fence_after();
+        }
+        uint32_t r0[16];
+        tmem_ld_32x32b_x16(lane_addr + COL_X + g * 32 + hf * 16, r0);
+        cb::tmem_ld_wait();
+        if (hf == 1) {
+          cb::tc_fence_before();
+          cb::mbar_arrive(&sm.x_free);
+        }
+        if (full) {
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
             const float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
-            dsk[e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
+            dsk[hf * 8 + e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
           }
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const int j = jc0 + e;
+          for (int e = 0; e < 16; e += 2) {
+            const int j = jc0 + hf * 16 + e;
             float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
             p0 = (j > hi_i || j < lo_i) ? 0.f : p0;
             p1 = (j + 1 > hi_i || j + 1 < lo_i) ? 0.f : p1;
-            dsk[e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
+            dsk[hf * 8 + e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
           }
         }
       }

@@ -258,7 +258,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     stage_bd(0);  // beta = 0
     for (int t = 0; t < nt; ++t) {
       stage_bd((t + 1) & 1);  // beta = t+1 = "lo" of this tile; "hi" = beta t sits in half t&1
-      named_bar(1, SOFT);     // every column quarter of the staged rows is visible
+      named_bar(2 + wq, NWG * 32);   // every column quarter of this row group's staged rows is visible
       // band column of key lj is idx = li + 127 - lj: idx < 128 -> "lo" block [idx], else "hi" block [idx-128]
       const uint32_t lo_base = my_row + ((t + 1) & 1) * 256 + 2 * (li + TN - 1);
       const uint32_t hi_base = my_row + (t & 1) * 256 + 2 * (li - 1);
@@ -275,15 +275,15 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
         rs.advance();
         // this thread's 32-key chunk is chunk g; the warp's rows are 32*wq .. 32*wq+31, so
         // g < wq: every lj < li -> "hi" block; g > wq: "lo" block; g == wq: per element  (warp-uniform)
-        if (g != wq) {
-          const uint32_t base = g < wq ? hi_base : lo_base;
 #pragma unroll
-          for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]) + lds_f16(base - 2 * (g * 32 + e));
+        for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]);
+        if (g != wq) {                 // packed 32-bit reads of the sheared window + FHADD (attn_tc_common.cuh)
+          shear_add32(s, (g < wq ? hi_base : lo_base) - 2 * (g * 32));
         } else {
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int lj = g * 32 + e;
-            s[e] = __uint_as_float(r0[e]) + lds_f16((lj < li ? hi_base : lo_base) - 2 * lj);
+            fhadd1(s[e], lds_u16((lj < li ? hi_base : lo_base) - 2 * lj));
           }
         }
       }
@@ -298,7 +298,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
 #pragma unroll
       for (int e = 0; e < CPT; ++e) mx = fmaxf(mx, s[e]);
       sm.xch[g][li] = mx;
-      named_bar(2, SOFT);
+      named_bar(2 + wq, NWG * 32);
       mx = fmaxf(fmaxf(sm.xch[0][li], sm.xch[1][li]), fmaxf(sm.xch[2][li], sm.xch[3][li]));
       mx = fmaxf(mx * sl2, m_run);
       const float msafe = mx == -INFINITY ? 0.f : mx;
@@ -346,7 +346,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     cb::mbar_arrive(&sm.o_empty);
     // ---- finalize: the column quarters add their partial sums ----
     sm.xsum[g][li] = l_run;
-    named_bar(2, SOFT);
+    named_bar(2 + wq, NWG * 32);
     const float l_tot = (sm.xsum[0][li] + sm.xsum[1][li]) + (sm.xsum[2][li] + sm.xsum[3][li]);
     if (i < p.T) {
       const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;

@@ -235,6 +235,14 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ unsigned short lds_u16(uint32_t addr) {
+  unsigned short h;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+  return h;
+}
+__device__ __forceinline__ void fhadd1(float& x, unsigned short h) {
+  asm("add.f32.f16 %0, %1, %0;" : "+f"(x) : "h"(h));
+}
 // x0 += f16 low half of pr, x1 += f16 high half (FHADD: one instruction each, no separate convert)
 __device__ __forceinline__ void fhadd2(float& x0, float& x1, uint32_t pr) {
   asm("{\n\t.reg .b16 l, h;\n\t"
@@ -285,6 +293,20 @@ __device__ __forceinline__ void shear_add32(float (&s)[32], uint32_t addr0) {
       asm("prmt.b32 %0, %1, %2, %3;" : "=r"(pr) : "r"(w[q]), "r"(w[q + 1]), "r"(sel));
       fhadd2(s[half * 16 + 2 * q], s[half * 16 + 2 * q + 1], pr);
     }
+  }
+}
+// 16-column variant: s[e] += fp16 at (addr0 - 2e), e = 0..15
+__device__ __forceinline__ void shear_add16(float (&s)[16], uint32_t addr0) {
+  const uint32_t aw = addr0 & ~3u;
+  const uint32_t sel = (addr0 & 2u) ? 0x1032u : 0x7610u;
+  uint32_t w[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) w[k] = lds_u32(aw - 4 * k);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint32_t pr;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(pr) : "r"(w[q]), "r"(w[q + 1]), "r"(sel));
+    fhadd2(s[2 * q], s[2 * q + 1], pr);
   }
 }
 // 16-column variant of the TMEM -> fp16 staging copy (lower register peak)
