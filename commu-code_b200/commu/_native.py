@@ -116,6 +116,8 @@ SIGNATURES = {
     "commu_prof_arm": [U],
     "commu_prof_read": [I, P, P],
     "commu_relattn_bwd_set_impl": [I, I, I],
+    "commu_relattn_set_dropout": [F, ctypes.c_uint64],
+    "commu_dropout": [P, I, L, P, L, L, I, F, ctypes.c_uint64, P, L, P, L, P],
     "commu_relattn_bwd_dr_tc": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, P, P, P],
     "commu_relattn_bwd_dq_tc": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, L, P, P, P],
     "commu_relattn_bwd_dkv_tc": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, P, L, P],

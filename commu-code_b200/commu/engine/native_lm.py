@@ -25,6 +25,32 @@ def _ceil(a, b):
     return (a + b - 1) // b * b
 
 
+_M64 = (1 << 64) - 1
+
+
+def _mix64(x):
+    """splitmix64 finaliser: seeds of the individual dropout sites from (base seed, layer, site)."""
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
+# dropout sites (reference model.py): embedding :585, positional table :586, attention probabilities :337,
+# attention output :349, FF hidden :166, FF output :168, final hidden :600
+SITE_EMB, SITE_POS, SITE_ATT, SITE_ATTN_OUT, SITE_FF_HID, SITE_FF_OUT, SITE_FINAL = range(7)
+
+
+def site_seed(base, layer, site):
+    return _mix64((base * 0x2545F4914F6CDD1D + layer * 16 + site) & _M64)
+
+
+def keep_prob(p):
+    """Effective keep probability of the kernels' 15-bit threshold (dropout.cuh)."""
+    thr = min(32767, max(0, int(p * 32768.0 + 0.5)))
+    return 1.0 - thr / 32768.0
+
+
 class Mems:
     """Opaque stand-in for the reference's `mems` tensor [L+1, M, B, d] (model.py:498-538).
     Callers only store it and pass it back; `.shape`, `.size()`, `len()`, `[i]` and `.float()` work."""
@@ -156,8 +182,16 @@ class NativeLM:
 
     # ------------------------------------------------------------------ forward --------------------
     @torch.no_grad()
-    def hidden_forward(self, data, reset, mems, mem_len, same_length, clamp_len, save):
-        """Runs embedding + L layers.  Returns (xL_f32 [T*B, dp], xL_bf16, new_mems, ctx)."""
+    def _drop(self, x, rows, cols, p, seed, res=None, out_f32=None, out_bf16=None):
+        """out = res + keep(x) / (1 - p)   (commu_dropout; x fp32 or bf16, in place allowed)."""
+        nv.call("commu_dropout", x, int(x.dtype == torch.bfloat16), x.stride(0), res,
+                res.stride(0) if res is not None else 0, rows, cols, float(p), seed,
+                out_f32, out_f32.stride(0) if out_f32 is not None else 0,
+                out_bf16, out_bf16.stride(0) if out_bf16 is not None else 0)
+
+    def hidden_forward(self, data, reset, mems, mem_len, same_length, clamp_len, save, dropout=None):
+        """Runs embedding + L layers.  Returns (xL_f32 [T*B, dp], xL_bf16, new_mems, ctx).
+        dropout: None or (p, p_att, base_seed) - the reference's nn.Dropout sites in training mode."""
         T, B = data.shape
         rows = T * B
         dev, bf = self.dev, torch.bfloat16
@@ -175,6 +209,13 @@ class NativeLM:
         pos = self.pos_table(K, clamp_len)
         scale = 1.0 / math.sqrt(self.Dh)
         tok = data.reshape(-1).contiguous()
+        pd, patt, dbase = dropout if dropout is not None else (0.0, 0.0, 0)
+        if patt > 0 and self.attn_fwd_impl != "commu_relattn_fwd_tc":
+            raise RuntimeError("commu_b200: attention dropout needs the tcgen05 attention kernels (COMMU_ATTN_FWD=tc)")
+        if pd > 0:   # pos_emb = self.drop(pos_emb)  (model.py:586)
+            pos_d = torch.empty_like(pos)
+            self._drop(pos, K, self.dp, pd, site_seed(dbase, 0, SITE_POS), out_bf16=pos_d)
+            pos = pos_d
 
         def new_cat(l):
             c = torch.empty(krows, self.dp, device=dev, dtype=bf)
@@ -186,6 +227,8 @@ class NativeLM:
         x = torch.empty(rows, self.dp, device=dev)
         nv.call("commu_embed_fwd", tok, self.P["word_emb.emb_layers.0.weight"], self.d, self.dp,
                 math.sqrt(self.d), rows, x, self.dp, cats[0][M * B:], self.dp)
+        if pd > 0:   # core_out = self.drop(word_emb)  (model.py:585); the dropped embedding is what enters the memory
+            self._drop(x, rows, self.dp, pd, site_seed(dbase, 0, SITE_EMB), out_f32=x, out_bf16=cats[0][M * B:])
         layers_ctx = []
         for l in range(self.L):
             s = S["layers"][l]
@@ -201,11 +244,16 @@ class NativeLM:
             lse = torch.empty(B, self.H, T, device=dev)
             qu = torch.empty(rows, self.hd, device=dev, dtype=bf) if save else None
             qv = torch.empty(rows, self.hd, device=dev, dtype=bf) if save else None
+            nv.call("commu_relattn_set_dropout", float(patt), site_seed(dbase, l, SITE_ATT))
             nv.call(self.attn_fwd_impl, q, self.hd, kv, kv[:, self.hd:], 2 * self.hd, r, self.hd, K,
                     S["u"], S["vb"], reset_u8, T, M, B, self.H, int(bool(same_length)), shift, scale,
                     av, self.hd, lse, qu, qv)
             z1 = torch.empty(rows, self.dp, device=dev)
-            nv.gemm(av, s["wo"], m=rows, n=self.dp, k=self.hd, add_f32=x, out_f32=z1)
+            if pd > 0:   # attn_out = self.drop(self.o_net(attn_vec)); w + attn_out  (model.py:348-352)
+                nv.gemm(av, s["wo"], m=rows, n=self.dp, k=self.hd, out_f32=z1)
+                self._drop(z1, rows, self.dp, pd, site_seed(dbase, l, SITE_ATTN_OUT), res=x, out_f32=z1)
+            else:
+                nv.gemm(av, s["wo"], m=rows, n=self.dp, k=self.hd, add_f32=x, out_f32=z1)
             pre = "layers.%d." % l
             y1 = torch.empty(rows, self.dp, device=dev)
             y1b = torch.empty(rows, self.dp, device=dev, dtype=bf)
@@ -217,7 +265,12 @@ class NativeLM:
             hdn = torch.empty(rows, self.dip, device=dev, dtype=bf)
             nv.gemm(y1b, s["w1"], m=rows, n=self.dip, k=self.dp, bias=s["b1"], relu=True, out_bf16=hdn)
             z2 = torch.empty(rows, self.dp, device=dev)
-            nv.gemm(hdn, s["w2"], m=rows, n=self.dp, k=self.dip, bias=s["b2"], add_f32=y1, out_f32=z2)
+            if pd > 0:   # Linear, ReLU, Dropout, Linear, Dropout; inp + core_out  (model.py:163-179)
+                self._drop(hdn, rows, self.dip, pd, site_seed(dbase, l, SITE_FF_HID), out_bf16=hdn)
+                nv.gemm(hdn, s["w2"], m=rows, n=self.dp, k=self.dip, bias=s["b2"], out_f32=z2)
+                self._drop(z2, rows, self.dp, pd, site_seed(dbase, l, SITE_FF_OUT), res=y1, out_f32=z2)
+            else:
+                nv.gemm(hdn, s["w2"], m=rows, n=self.dp, k=self.dip, bias=s["b2"], add_f32=y1, out_f32=z2)
             nxt = new_cat(l + 1) if l + 1 < self.L else torch.empty(krows, self.dp, device=dev, dtype=bf)
             if l + 1 == self.L and M > 0:
                 nxt[: M * B].copy_(mems.bufs[self.L])
@@ -237,17 +290,23 @@ class NativeLM:
         if mem_len > 0:
             keep = min(K, mem_len)
             new_mems = Mems([c[(K - keep) * B:] for c in cats], keep, B, self.d, self.dp)
+        nv.call("commu_relattn_set_dropout", 0.0, 0)
         ctx = None
         if save:
             ctx = dict(T=T, B=B, M=M, K=K, shift=shift, same_length=int(bool(same_length)), scale=scale,
-                       reset_u8=reset_u8, pos=pos, tok=tok, cats=cats, layers=layers_ctx)
-        return x, cats[self.L][M * B:], new_mems, ctx
+                       reset_u8=reset_u8, pos=pos, tok=tok, cats=cats, layers=layers_ctx, drop=(pd, patt, dbase))
+        xb_out = cats[self.L][M * B:]
+        if pd > 0:   # core_out = self.drop(core_out) before the loss (model.py:600); the memory keeps the undropped rows
+            xb_out = torch.empty(rows, self.dp, device=dev, dtype=bf)
+            self._drop(x, rows, self.dp, pd, site_seed(dbase, 0, SITE_FINAL), out_bf16=xb_out)
+        return x, xb_out, new_mems, ctx
 
     @torch.no_grad()
-    def forward_loss(self, data, target, reset, mems, mem_len, same_length, clamp_len, save=True):
+    def forward_loss(self, data, target, reset, mems, mem_len, same_length, clamp_len, save=True, dropout=None):
         T, B = data.shape
         rows = T * B
-        xf, xb, new_mems, ctx = self.hidden_forward(data, reset, mems, mem_len, same_length, clamp_len, save)
+        xf, xb, new_mems, ctx = self.hidden_forward(data, reset, mems, mem_len, same_length, clamp_len, save,
+                                                    dropout=dropout)
         S = self.shadow()
         logits = torch.empty(rows, self.vp, device=self.dev)
         nv.gemm(xb, S["emb"], m=rows, n=self.V, k=self.dp, bias=S["lbias"], out_f32=logits)
@@ -316,6 +375,11 @@ class NativeLM:
         grads["crit.out_layers.0.bias"].add_(lb[:V])
         dx = torch.empty(rows, self.dp, device=dev)
         nv.gemm(dlogits, S["emb"], m=rows, n=self.dp, k=V, b_mn=True, out_f32=dx)
+        pd, patt, dbase = c.get("drop", (0.0, 0.0, 0))
+        if patt > 0 and not all(os.environ.get(e, "tc") == "tc" for e in ("COMMU_ATTN_BWD_DQ", "COMMU_ATTN_BWD_DKV", "COMMU_ATTN_BWD_DR")):
+            raise RuntimeError("commu_b200: attention dropout needs the tcgen05 backward passes")
+        if pd > 0:
+            self._drop(dx, rows, self.dp, pd, site_seed(dbase, 0, SITE_FINAL), out_f32=dx)
         du = torch.zeros(H, 64, device=dev)
         dvb = torch.zeros(H, 64, device=dev)
         delta = torch.empty(B, H, T, device=dev)
@@ -331,10 +395,14 @@ class NativeLM:
             nv.call("commu_layernorm_bwd", dx, self.dp, a["z2"], self.dp, a["mean2"], a["rstd2"],
                     self.P[pre + "pos_ff.layer_norm.weight"], d, self.dp, rows, dz2, self.dp, dz2b, self.dp,
                     grads[pre + "pos_ff.layer_norm.weight"], grads[pre + "pos_ff.layer_norm.bias"])
+            if pd > 0:   # gradient through the FF output dropout (the residual branch keeps dz2)
+                self._drop(dz2, rows, self.dp, pd, site_seed(dbase, l, SITE_FF_OUT), out_bf16=dz2b)
             nv.call("commu_colsum_bf16", dz2b, self.dp, d, rows, grads[pre + "pos_ff.CoreNet.3.bias"])
             self._wgrad(dz2b, a["hdn"], self.dp, self.dip, rows, grads[pre + "pos_ff.CoreNet.3.weight"])
             dpre = torch.empty(rows, self.dip, device=dev, dtype=bf)
-            nv.gemm(dz2b, s["w2"], m=rows, n=self.dip, k=self.dp, b_mn=True, relu_mask=a["hdn"], out_bf16=dpre)
+            # hidden dropout: the saved (dropped) hidden is > 0 exactly where ReLU and the mask passed
+            nv.gemm(dz2b, s["w2"], m=rows, n=self.dip, k=self.dp, b_mn=True, relu_mask=a["hdn"], out_bf16=dpre,
+                    alpha=(1.0 / keep_prob(pd)) if pd > 0 else 1.0)
             nv.call("commu_colsum_bf16", dpre, self.dip, Di, rows, grads[pre + "pos_ff.CoreNet.0.bias"])
             self._wgrad(dpre, a["y1b"], self.dip, self.dp, rows, grads[pre + "pos_ff.CoreNet.0.weight"])
             dy1 = torch.empty(rows, self.dp, device=dev)
@@ -345,6 +413,8 @@ class NativeLM:
             nv.call("commu_layernorm_bwd", dy1, self.dp, a["z1"], self.dp, a["mean1"], a["rstd1"],
                     self.P[pre + "dec_attn.layer_norm.weight"], d, self.dp, rows, dz1, self.dp, dz1b, self.dp,
                     grads[pre + "dec_attn.layer_norm.weight"], grads[pre + "dec_attn.layer_norm.bias"])
+            if pd > 0:   # gradient through the attention output dropout (the residual branch keeps dz1)
+                self._drop(dz1, rows, self.dp, pd, site_seed(dbase, l, SITE_ATTN_OUT), out_bf16=dz1b)
             self._wgrad(dz1b, a["av"], self.dp, self.hd, rows, grads[pre + "dec_attn.o_net.weight"],
                         cseg=Dh, cseg_pad=64)
             dav = torch.empty(rows, self.hd, device=dev, dtype=bf)
@@ -352,6 +422,7 @@ class NativeLM:
             dq = torch.empty(rows, self.hd, device=dev, dtype=bf)
             dkv = torch.empty(krows, 2 * self.hd, device=dev, dtype=bf)
             dr = torch.zeros(K, self.hd, device=dev)
+            nv.call("commu_relattn_set_dropout", float(patt), site_seed(dbase, l, SITE_ATT))
             nv.call("commu_relattn_bwd", a["qu"], a["qv"], self.hd, a["kv"], a["kv"][:, self.hd:], 2 * self.hd,
                     a["r"], self.hd, K, c["reset_u8"], T, M, B, H, c["same_length"], c["shift"], c["scale"],
                     a["av"], self.hd, a["lse"], dav, self.hd, delta, dq, self.hd, dkv, dkv[:, self.hd:],
@@ -366,6 +437,9 @@ class NativeLM:
             # gradient of the layer input: residual + through Wq (all rows) + through Wkv (segment rows)
             nv.gemm(dq, s["wq"], m=rows, n=self.dp, k=self.hd, b_mn=True, add_f32=dz1, out_f32=dx)
             nv.gemm(dkv[M * B:], s["wkv"], m=rows, n=self.dp, k=2 * self.hd, b_mn=True, add_f32=dx, out_f32=dx)
+        nv.call("commu_relattn_set_dropout", 0.0, 0)
+        if pd > 0:
+            self._drop(dx, rows, self.dp, pd, site_seed(dbase, 0, SITE_EMB), out_f32=dx)
         nv.call("commu_embed_bwd", c["tok"], dx, self.dp, d, math.sqrt(d), rows, g_emb)
         grads["r_w_bias"].add_(du[:, :Dh])
         grads["r_r_bias"].add_(dvb[:, :Dh])

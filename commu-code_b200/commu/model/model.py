@@ -75,7 +75,7 @@ class _NativeLoss(torch.autograd.Function):
         eng = model._engine()
         need = model._need_save   # grad mode is always off inside Function.forward; decided by the caller
         loss, new_mems = eng.forward_loss(data, target, reset, mems, model.mem_len, model.same_length,
-                                          model.clamp_len, save=need)
+                                          model.clamp_len, save=need, dropout=model._dropout_arg())
         model._last_mems = new_mems
         ctx.model = model
         ctx.saved_ctx = eng.saved
@@ -119,7 +119,6 @@ class MemTransformerLM(nn.Module):
         self.r_r_bias = nn.Parameter(torch.zeros(self.n_head, self.d_head))
         self._eng = None
         self._last_mems = None
-        self._warned_dropout = False
 
     # ---- reference surface -------------------------------------------------------------------------
     def reset_length(self, tgt_len, mem_len):
@@ -131,7 +130,6 @@ class MemTransformerLM(nn.Module):
     def forward(self, data, target, reset_mems, mems):
         """-> (per-token NLL [T,B] fp32, new_mems)   (reference model.py:678-693)"""
         self._check_inputs(data, mems)
-        self._note_dropout()
         plist = self._params()
         self._need_save = torch.is_grad_enabled() and any(p.requires_grad for p in plist)
         loss = _NativeLoss.apply(self, data, target, reset_mems, mems, *plist)
@@ -153,11 +151,14 @@ class MemTransformerLM(nn.Module):
                 return
             raise TypeError("commu_b200: `mems` must be None or the handle returned by a previous call")
 
-    def _note_dropout(self):
-        if self.training and (self.dropout_p > 0 or self.dropatt_p > 0) and not self._warned_dropout:
-            _log.warning("commu_b200: dropout=%.2f / attention_dropout=%.2f are NOT applied by the native "
-                         "kernels yet (runs as dropout=0)", self.dropout_p, self.dropatt_p)
-            self._warned_dropout = True
+    def _dropout_arg(self):
+        """(p, p_att, seed) of this forward in training mode (reference: nn.Dropout modules, model.py:166-168,
+        210-211, 454), else None.  Every forward draws a fresh 63-bit seed from torch's CPU generator, so
+        `torch.manual_seed` makes runs repeatable; masks themselves come from the kernels' counter-based RNG."""
+        if not self.training or (self.dropout_p <= 0 and self.dropatt_p <= 0):
+            return None
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        return (self.dropout_p, self.dropatt_p, seed)
 
     def _params(self):
         named = [(n, p) for n, p in self.named_parameters() if n != "crit.out_layers.0.weight"]

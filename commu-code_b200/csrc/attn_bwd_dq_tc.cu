@@ -60,6 +60,7 @@ struct Smem {
   uint32_t tmem_base;
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                          const __grid_constant__ CUtensorMap tm_qu, const __grid_constant__ CUtensorMap tm_qv,
@@ -230,8 +231,11 @@ relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
     const uint32_t rowoff = (li >> 3) * QG + (li & 7) * 2;            // (row li, idx 0) inside a block buffer
     const int c0 = li + (TN - 1) - g * 32;                             // band column of this thread's first key
     const float sl2 = p.scale * 1.4426950408889634f;
-    const float lse2 = i < p.T ? p.lse[((long long)b * p.H + h) * p.T + i] * 1.4426950408889634f : 0.f;
-    const float delta = i < p.T ? p.delta[((long long)b * p.H + h) * p.T + i] : 0.f;
+    // under dropout P is scaled by 1 / keep (folded into the exponent) and Delta by keep: dS = (P / keep) * (m * dP - keep * Delta)
+    const float lse2 = (i < p.T ? p.lse[((long long)b * p.H + h) * p.T + i] * 1.4426950408889634f : 0.f) +
+                       (DROP ? log2f(p.drop_keep) : 0.f);
+    const float delta = (i < p.T ? p.delta[((long long)b * p.H + h) * p.T + i] : 0.f) * (DROP ? p.drop_keep : 1.f);
+    const drop::Keys dkeys = drop::row_keys(p.drop_ka, p.drop_kb, (uint32_t)((b * p.H + h) * p.T + i));
     const int hi_i = i < p.T ? i + p.M : -1;
     const int lo_i = key_lo(i, p.M, p.same_length, p.shift, reset);
     // block 0 only ever receives its "hi" part (from tile 0): its "lo" part starts as zeros
@@ -296,22 +300,10 @@ relattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
           cb::tc_fence_before();
           cb::mbar_arrive(&sm.x_free);
         }
-        if (full) {
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            const float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
-            dsk[hf * 8 + e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 16; e += 2) {
-            const int j = jc0 + hf * 16 + e;
-            float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
-            p0 = (j > hi_i || j < lo_i) ? 0.f : p0;
-            p1 = (j + 1 > hi_i || j + 1 < lo_i) ? 0.f : p1;
-            dsk[hf * 8 + e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
-          }
-        }
+        if (full)
+          pds16<DROP, false, false>(s, r0, sl2, lse2, delta, jc0 + hf * 16, hi_i, lo_i, dkeys, p.drop_thr2, nullptr, dsk + hf * 8);
+        else
+          pds16<DROP, true, false>(s, r0, sl2, lse2, delta, jc0 + hf * 16, hi_i, lo_i, dkeys, p.drop_thr2, nullptr, dsk + hf * 8);
       }
       // ---- dS -> TMEM (A operand of dq += dS K); the previous tile's product must be done with those columns ----
       if (t > 0) {
@@ -402,6 +394,7 @@ extern "C" int commu_relattn_bwd_dq_tc(const void* qu, const void* qv, int64_t l
   p.lse = const_cast<float*>(lse); p.delta = delta;
   p.dout = (const bf16*)dout; p.lddo = lddo;
   p.dq = (bf16*)dq; p.lddq = lddq; p.du = du; p.dvb = dvb;
+  apply_drop_state(p);
   int rc = cb_host::check_attn_common(p, "relattn_bwd_dq_tc");
   if (rc) return rc;
   CB_REQUIRE(qv && lse && dout && delta && dq && du && dvb && lddq % 8 == 0 && lddo % 8 == 0, "relattn_bwd_dq_tc: bad args");
@@ -416,11 +409,13 @@ extern "C" int commu_relattn_bwd_dq_tc(const void* qu, const void* qv, int64_t l
   static bool attr = false;
   const int smem_bytes = (int)sizeof(Smem) + 1024;
   if (!attr) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dq_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dq_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr = true;
   }
   dim3 grid(cb_host::ceil_div(T, TM), H, B);
-  relattn_bwd_dq_tc_kernel<<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p);
+  if (p.drop_thr2) relattn_bwd_dq_tc_kernel<true><<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p);
+  else relattn_bwd_dq_tc_kernel<false><<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -56,6 +56,7 @@ struct Smem {
   uint32_t tmem_base;
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                          const __grid_constant__ CUtensorMap tm_qu, const __grid_constant__ CUtensorMap tm_qv,
@@ -221,8 +222,10 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
 
     for (int n = 0; n < nq; ++n) {
       const int i = (it_first + n) * TM + li;
-      const float lse2 = lse_n * 1.4426950408889634f;
-      const float delta = del_n;
+      // under dropout P is scaled by 1 / keep (folded into the exponent) and Delta by keep
+      const float lse2 = lse_n * 1.4426950408889634f + (DROP ? log2f(p.drop_keep) : 0.f);
+      const float delta = DROP ? del_n * p.drop_keep : del_n;
+      const drop::Keys dkeys = drop::row_keys(p.drop_ka, p.drop_kb, (uint32_t)((b * p.H + h) * p.T + i));
       {
         const int inext = i + TM;
         lse_n = 0.f; del_n = 0.f;
@@ -275,6 +278,18 @@ relattn_bwd_dr_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_
       uint32_t dsk[16];
       const int jk0 = i + p.M - (d0 + g * 32);   // key of column 0; column e is key jk0 - e
       const bool full = (i < p.T) && (jk0 - 31 >= lo_i);
+      if (DROP) {   // dP of a dropped probability does not reach dS': mask it with the forward's keep flags
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t fl[4];
+          drop_flags_desc8(fl, jk0, c, dkeys, p.drop_thr2);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            dp[8 * c + 2 * q] = __uint_as_float(__float_as_uint(dp[8 * c + 2 * q]) & drop::mask32_hi(fl[q]));
+            dp[8 * c + 2 * q + 1] = __uint_as_float(__float_as_uint(dp[8 * c + 2 * q + 1]) & drop::mask32_lo(fl[q]));
+          }
+        }
+      }
       if (__all_sync(0xffffffffu, full)) {
 #pragma unroll
         for (int e = 0; e < 32; e += 2) {
@@ -365,6 +380,7 @@ extern "C" int commu_relattn_bwd_dr_tc(const void* qu, const void* qv, int64_t l
   p.lse = const_cast<float*>(lse); p.delta = delta;
   p.dout = (const bf16*)dout; p.lddo = lddo;
   p.dr = dr; p.du = du; p.dvb = dvb;
+  apply_drop_state(p);
   int rc = cb_host::check_attn_common(p, "relattn_bwd_dr_tc");
   if (rc) return rc;
   CB_REQUIRE(qv && lse && dout && delta && dr && du && dvb && lddo % 8 == 0, "relattn_bwd_dr_tc: bad args");
@@ -379,11 +395,13 @@ extern "C" int commu_relattn_bwd_dr_tc(const void* qu, const void* qv, int64_t l
   static bool attr = false;
   const int smem_bytes = (int)sizeof(Smem) + 1024;
   if (!attr) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dr_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dr_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr = true;
   }
   dim3 grid(cb_host::ceil_div(Ktot, TN), H, B);
-  relattn_bwd_dr_tc_kernel<<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p);
+  if (p.drop_thr2) relattn_bwd_dr_tc_kernel<true><<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p);
+  else relattn_bwd_dr_tc_kernel<false><<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -54,6 +54,7 @@ struct Smem {
   uint32_t tmem_base;
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                           const __grid_constant__ CUtensorMap tm_qu, const __grid_constant__ CUtensorMap tm_qv,
@@ -230,8 +231,10 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
 
     for (int n = 0; n < nq; ++n) {
       const int i = (it_first + n) * TM + li;
-      const float lse2 = lse_n * 1.4426950408889634f;
-      const float delta = del_n;
+      // under dropout P is scaled by 1 / keep (folded into the exponent) and Delta by keep
+      const float lse2 = lse_n * 1.4426950408889634f + (DROP ? log2f(p.drop_keep) : 0.f);
+      const float delta = DROP ? del_n * p.drop_keep : del_n;
+      const drop::Keys dkeys = drop::row_keys(p.drop_ka, p.drop_kb, (uint32_t)((b * p.H + h) * p.T + i));
       {
         const int inext = i + TM;
         lse_n = 0.f; del_n = 0.f;
@@ -295,22 +298,11 @@ relattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid
         cb::tc_fence_before();
         cb::mbar_arrive(&sm.x_free);
         if (__all_sync(0xffffffffu, full)) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
-            pk[e / 2] = cb::pack_bf16(p0, p1);
-            dsk[e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
-          }
+          pds16<DROP, false, true>(s, r0, sl2, lse2, delta, jc0, hi_i, lo_i, dkeys, p.drop_thr2, pk, dsk);
+          pds16<DROP, false, true>(s + 16, r0 + 16, sl2, lse2, delta, jc0 + 16, hi_i, lo_i, dkeys, p.drop_thr2, pk + 8, dsk + 8);
         } else {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const int j = jc0 + e;
-            float p0 = ex2(fmaf(s[e], sl2, -lse2)), p1 = ex2(fmaf(s[e + 1], sl2, -lse2));
-            p0 = (j > hi_i || j < lo_i) ? 0.f : p0;
-            p1 = (j + 1 > hi_i || j + 1 < lo_i) ? 0.f : p1;
-            pk[e / 2] = cb::pack_bf16(p0, p1);
-            dsk[e / 2] = cb::pack_bf16(p0 * (__uint_as_float(r0[e]) - delta), p1 * (__uint_as_float(r0[e + 1]) - delta));
-          }
+          pds16<DROP, true, true>(s, r0, sl2, lse2, delta, jc0, hi_i, lo_i, dkeys, p.drop_thr2, pk, dsk);
+          pds16<DROP, true, true>(s + 16, r0 + 16, sl2, lse2, delta, jc0 + 16, hi_i, lo_i, dkeys, p.drop_thr2, pk + 8, dsk + 8);
         }
       }
       named_bar(2 + wq, NWG * 32);              // the row group is done with its staged rows (P / dS alias them)
@@ -387,6 +379,7 @@ extern "C" int commu_relattn_bwd_dkv_tc(const void* qu, const void* qv, int64_t 
   p.same_length = same_length; p.shift = shift; p.scale = scale;
   p.lse = const_cast<float*>(lse); p.delta = delta;
   p.dout = (const bf16*)dout; p.lddo = lddo;
+  apply_drop_state(p);
   int rc = cb_host::check_attn_common(p, "relattn_bwd_dkv_tc");
   if (rc) return rc;
   CB_REQUIRE(qv && lse && dout && delta && dk && dv && lddkv % 8 == 0 && lddo % 8 == 0, "relattn_bwd_dkv_tc: bad args");
@@ -401,11 +394,15 @@ extern "C" int commu_relattn_bwd_dkv_tc(const void* qu, const void* qv, int64_t 
   static bool attr = false;
   const int smem_bytes = (int)sizeof(Smem) + 1024;
   if (!attr) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dkv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_dkv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr = true;
   }
   dim3 grid(cb_host::ceil_div(Ktot, TN), H, B);
-  relattn_bwd_dkv_tc_kernel<<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p, (bf16*)dk, (bf16*)dv, lddkv);
+  if (p.drop_thr2)
+    relattn_bwd_dkv_tc_kernel<true><<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p, (bf16*)dk, (bf16*)dv, lddkv);
+  else
+    relattn_bwd_dkv_tc_kernel<false><<<grid, NTHREADS, smem_bytes, stream>>>(tk, tv, tqu, tqv, tdo, tr, p, (bf16*)dk, (bf16*)dv, lddkv);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

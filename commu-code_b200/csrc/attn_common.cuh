@@ -38,6 +38,10 @@ struct Params {
   int T, M, B, H, Kr;
   int same_length, shift;  // shift = mask_shift_len (valid iff j > i - shift)
   float scale;             // 1/sqrt(real Dh)
+  // dropout on the attention probabilities (dropout.cuh); drop_thr2 == 0 -> none.  Set by commu_relattn_set_dropout.
+  uint32_t drop_thr2;      // 15-bit threshold replicated in both halves
+  uint32_t drop_ka, drop_kb;
+  float drop_keep;         // effective keep probability 1 - thr15 / 32768
   // forward outputs
   bf16* out;  // [T*B, ldo]
   long long ldo;

@@ -64,6 +64,7 @@ struct Smem {
   uint32_t tmem_base;
 };
 
+template <bool DROP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
                       const __grid_constant__ CUtensorMap tm_r, const Params p) {
@@ -252,6 +253,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     for (int e = 0; e < OPT; ++e) o[e] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     const float sl2 = p.scale * 1.4426950408889634f;
+    const drop::Keys dkeys = drop::row_keys(p.drop_ka, p.drop_kb, (uint32_t)((b * p.H + h) * p.T + i));
     const int hi_i = i < p.T ? i + p.M : -1;
     const int lo_i = key_lo(i, p.M, p.same_length, p.shift, reset);
 
@@ -312,6 +314,14 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
         rsum += p0 + p1;
         pk[e / 2] = cb::pack_bf16(p0, p1);
       }
+      if (DROP) {   // dropped probabilities feed P V only; the normaliser keeps every term (model.py:336-337)
+#pragma unroll
+        for (int q4 = 0; q4 < CPT / 4; ++q4) {
+          const uint2 rnd = drop::rand64((uint32_t)(jc0 >> 2) + q4, dkeys);
+          pk[2 * q4] &= drop::mask16x2(drop::keep_flags(rnd.x, p.drop_thr2));
+          pk[2 * q4 + 1] &= drop::mask16x2(drop::keep_flags(rnd.y, p.drop_thr2));
+        }
+      }
       l_run = l_run * corr + rsum;
       // ---- fold the previous tile's partial O (scale of the previous max), then rescale ----
       if (t > 0) {
@@ -349,7 +359,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     named_bar(2 + wq, NWG * 32);
     const float l_tot = (sm.xsum[0][li] + sm.xsum[1][li]) + (sm.xsum[2][li] + sm.xsum[3][li]);
     if (i < p.T) {
-      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      const float inv = l_tot > 0.f ? 1.f / (DROP ? l_tot * p.drop_keep : l_tot) : 0.f;
       bf16* orow = p.out + ((long long)i * p.B + b) * p.ldo + h * DH + g * OPT;
 #pragma unroll
       for (int ch = 0; ch < OPT / 8; ++ch) {
@@ -374,6 +384,22 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
 
 }  // namespace
 
+namespace {
+attn_tc::DropState g_drop = {0.f, 0ull};
+}
+namespace attn_tc {
+DropState drop_state() { return g_drop; }
+}
+// Dropout on the attention probabilities (reference: self.dropatt, commu/model/model.py:211, 337) for the
+// subsequent tcgen05 attention calls of this process: p in [0, 1), p == 0 switches it off.  The forward and
+// the backward of one layer must run under the same (p, seed); masks are recomputed, never stored.
+extern "C" int commu_relattn_set_dropout(float p, unsigned long long seed) {
+  CB_REQUIRE(p >= 0.f && p < 1.f, "relattn_set_dropout: p must be in [0, 1)");
+  g_drop.p = p;
+  g_drop.seed = seed;
+  return 0;
+}
+
 // Same contract as commu_relattn_fwd (the v1 warp-MMA kernel); this is the tcgen05 implementation.
 extern "C" int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                                     const void* r, int64_t ldr, int kr, const float* r_w_bias,
@@ -388,6 +414,7 @@ extern "C" int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, c
   p.T = T; p.M = M; p.B = B; p.H = H; p.Kr = kr;
   p.same_length = same_length; p.shift = shift; p.scale = scale;
   p.out = (bf16*)out; p.ldo = ldo; p.lse = lse;
+  apply_drop_state(p);
   int rc = cb_host::check_attn_common(p, "relattn_fwd_tc");
   if (rc) return rc;
   CB_REQUIRE(out && (ldo % 8 == 0), "relattn_fwd_tc: bad output");
@@ -405,12 +432,14 @@ extern "C" int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, c
   static bool attr = false;
   const int smem_bytes = (int)sizeof(Smem) + 1024;
   if (!attr) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr = true;
   }
   dim3 grid(cb_host::ceil_div(T, TM), H, B);
   cb_host::ProfScope prof(cb_host::PROF_ATTN_FWD, (cudaStream_t)stream);
-  relattn_fwd_tc_kernel<<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(tk, tv, tr, p);
+  if (p.drop_thr2) relattn_fwd_tc_kernel<true><<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(tk, tv, tr, p);
+  else relattn_fwd_tc_kernel<false><<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(tk, tv, tr, p);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

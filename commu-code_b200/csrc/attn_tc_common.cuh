@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 #include "api_common.h"
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace attn_tc {
 
@@ -345,6 +346,72 @@ __device__ __forceinline__ void sts_halves(uint32_t addr_lo, uint32_t addr_hi, u
                "st.shared.b16 [%1], h;\n\t}" ::"r"(addr_lo), "r"(addr_hi), "r"(packed) : "memory");
 }
 
+// ---- backward: probabilities and score gradients of 16 consecutive key columns of one query row ----
+//   P  = exp2(s * sl2 - lse2)                       (lse2 already holds -log2(1/keep) under dropout: P / keep)
+//   dS = P * (keep-masked dP - delta)                (delta already scaled by keep under dropout)
+// s: scores (AC + BD), dpr: raw dP bits from TMEM, j_first: key index of column 0 (multiple of 4).
+// MASKED applies the analytic attention mask (boundary tiles), WANT_P also emits the (dropped) P pairs.
+template <bool DROP, bool MASKED, bool WANT_P>
+__device__ __forceinline__ void pds16(const float* s, const uint32_t* dpr, float sl2, float lse2, float delta, int j_first,
+                                      int hi_i, int lo_i, drop::Keys dk, uint32_t thr2, uint32_t* pk8, uint32_t* dsk8) {
+#pragma unroll
+  for (int e = 0; e < 16; e += 4) {
+    uint32_t f0 = 0, f1 = 0;
+    if (DROP) {
+      const uint2 rnd = drop::rand64((uint32_t)((j_first + e) >> 2), dk);
+      f0 = drop::keep_flags(rnd.x, thr2);
+      f1 = drop::keep_flags(rnd.y, thr2);
+    }
+    float pv[4], dsv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      pv[u] = ex2(fmaf(s[e + u], sl2, -lse2));
+      if (MASKED) {
+        const int j = j_first + e + u;
+        pv[u] = (j > hi_i || j < lo_i) ? 0.f : pv[u];
+      }
+      uint32_t dbits = dpr[e + u];
+      if (DROP) dbits &= (u == 0 ? drop::mask32_lo(f0) : u == 1 ? drop::mask32_hi(f0) : u == 2 ? drop::mask32_lo(f1) : drop::mask32_hi(f1));
+      dsv[u] = pv[u] * (__uint_as_float(dbits) - delta);
+    }
+    if (WANT_P) {
+      uint32_t p01 = cb::pack_bf16(pv[0], pv[1]), p23 = cb::pack_bf16(pv[2], pv[3]);
+      if (DROP) {
+        p01 &= drop::mask16x2(f0);
+        p23 &= drop::mask16x2(f1);
+      }
+      pk8[e / 2] = p01;
+      pk8[e / 2 + 1] = p23;
+    }
+    dsk8[e / 2] = cb::pack_bf16(dsv[0], dsv[1]);
+    dsk8[e / 2 + 1] = cb::pack_bf16(dsv[2], dsv[3]);
+  }
+}
+
+// Keep flags for keys in DESCENDING order (the dR pass walks distances): element e of this thread is key
+// jk0 - e.  Returns the flags of the 8 elements 8c .. 8c+7 as 4 words, element 2q in the HIGH half and 2q+1 in
+// the low half (mask32_hi / mask32_lo).  The fields are the same bits the ascending kernels use: key j is field
+// j & 3 of rand64(j >> 2); in descending order a group contributes [y.hi, y.lo, x.hi, x.lo].
+__device__ __forceinline__ void drop_flags_desc8(uint32_t (&fl)[4], int jk0, int c, drop::Keys dk, uint32_t thr2) {
+  const int sk = 3 - (jk0 & 3);          // stream position of element 0 (16-bit fields, high half first)
+  const int g0 = jk0 >> 2;
+  uint32_t st[6];                        // stream words 4c .. 4c+5 (three groups)
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const uint2 rnd = drop::rand64((uint32_t)(g0 - 2 * c - q), dk);
+    st[2 * q] = rnd.y;
+    st[2 * q + 1] = rnd.x;
+  }
+  const bool woff = (sk >> 1) != 0;
+  const uint32_t sh = (sk & 1) ? 16u : 0u;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t w0 = woff ? st[q + 1] : st[q];
+    const uint32_t w1 = woff ? st[q + 2] : st[q + 1];
+    fl[q] = drop::keep_flags(__funnelshift_l(w1, w0, sh), thr2);
+  }
+}
+
 struct Ring {  // stage / parity bookkeeping of a 2-deep mbarrier ring
   int idx = 0;
   uint32_t phase = 0;
@@ -354,6 +421,19 @@ struct Ring {  // stage / parity bookkeeping of a 2-deep mbarrier ring
   }
 };
 
+
+// current attention-dropout setting (commu_relattn_set_dropout, attn_fwd_tc.cu); copied into Params by the tcgen05 entry points
+struct DropState { float p; unsigned long long seed; };
+DropState drop_state();
+template <class ParamsT>
+inline void apply_drop_state(ParamsT& p) {
+  const DropState d = drop_state();
+  const uint32_t thr = d.p > 0.f ? drop::thr15_of(d.p) : 0u;
+  p.drop_thr2 = thr * 0x00010001u;
+  p.drop_ka = (uint32_t)d.seed;
+  p.drop_kb = (uint32_t)(d.seed >> 32);
+  p.drop_keep = 1.f - (float)thr / 32768.f;
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -157,6 +157,19 @@ int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* 
                          const unsigned char* reset, int T, int M, int B, int H, int same_length, int shift,
                          float scale, void* out, int64_t ldo, float* lse, void* qu_save, void* qv_save,
                          void* stream);
+/* Dropout on the attention probabilities (reference: self.dropatt, commu/model/model.py:211, 337) for the
+ * subsequent tcgen05 attention calls of this process (forward and the three backward passes): p in [0, 1),
+ * 0 = off.  Masks are a pure function of (seed, batch, head, query, key) and are recomputed in the backward, so
+ * the forward and the backward of a layer must run under the same (p, seed).  Not supported by the v1 kernels. */
+int commu_relattn_set_dropout(float p, unsigned long long seed);
+/* Elementwise dropout with optional residual add - the remaining nn.Dropout sites of the reference
+ * (commu/model/model.py:166-168, 349, 585-586, 600): out = res + keep(x) / (1 - p) over [rows, cols].
+ * x is fp32 or bf16 (x_is_bf16), res (fp32) may be NULL, out_f32 / out_bf16: at least one, in place allowed.
+ * cols and all leading dimensions are multiples of 4.  The keep decision of (seed, row, column) is reproducible:
+ * the backward applies the same call to the incoming gradient. */
+int commu_dropout(const void* x, int x_is_bf16, int64_t ldx, const float* res, int64_t ldres, int64_t rows,
+                  int cols, float p, uint64_t seed, float* out_f32, int64_t ldo, void* out_bf16, int64_t ldob,
+                  void* stream);
 /* Backward of the above (the reference uses torch autograd).  dq: bf16 [T*B, lddq]; dk, dv: bf16
  * [K*B, lddkv] (every key row written); dr: fp32 [kr, H*64] and du, dvb: fp32 [H,64] are accumulated
  * (+=, caller zeroes); delta_ws: fp32 [B,H,T] workspace. */

@@ -113,7 +113,8 @@ def visible_mask(T, M, mem_len, same_length, reset, device=None):
     return ok
 
 
-def _layer(cfg, P, pre, x, mem, pos, valid):
+def _layer(cfg, P, pre, x, mem, pos, valid, drop=None, l=0):
+    dr = drop if drop is not None else (lambda site, layer, t: t)
     T, B, d = x.shape
     H, Dh = cfg.n_head, cfg.d_head
     M = mem.shape[0]
@@ -134,19 +135,22 @@ def _layer(cfg, P, pre, x, mem, pos, valid):
     BD = QR.gather(3, dist[None, None].expand(B, H, T, K))
     score = (AC + BD) * (1.0 / math.sqrt(Dh))
     score = score.masked_fill(~valid[:, None], float("-inf"))
-    prob = torch.softmax(score, dim=-1)
+    prob = dr("att", l, torch.softmax(score, dim=-1))                     # self.dropatt (model.py:337)
     av = torch.einsum("bhij,jbhd->ibhd", prob, v).reshape(T, B, H * Dh)
-    a_out = av @ P[pre + "dec_attn.o_net.weight"].t()
+    a_out = dr("attn_out", l, av @ P[pre + "dec_attn.o_net.weight"].t())   # self.drop (model.py:349)
     y = F.layer_norm(x + a_out, (d,), P[pre + "dec_attn.layer_norm.weight"],
                      P[pre + "dec_attn.layer_norm.bias"], 1e-5)
-    h = torch.relu(y @ P[pre + "pos_ff.CoreNet.0.weight"].t() + P[pre + "pos_ff.CoreNet.0.bias"])
-    f = h @ P[pre + "pos_ff.CoreNet.3.weight"].t() + P[pre + "pos_ff.CoreNet.3.bias"]
+    h = dr("ff_hid", l, torch.relu(y @ P[pre + "pos_ff.CoreNet.0.weight"].t() + P[pre + "pos_ff.CoreNet.0.bias"]))
+    f = dr("ff_out", l, h @ P[pre + "pos_ff.CoreNet.3.weight"].t() + P[pre + "pos_ff.CoreNet.3.bias"])   # model.py:163-169
     return F.layer_norm(y + f, (d,), P[pre + "pos_ff.layer_norm.weight"],
                         P[pre + "pos_ff.layer_norm.bias"], 1e-5)
 
 
-def hidden_forward(cfg, P, data, reset=None, mems=None):
-    """Returns (hidden [T,B,d], new_mems [L+1, min(M+T, mem_len), B, d] or None)."""
+def hidden_forward(cfg, P, data, reset=None, mems=None, drop=None):
+    """Returns (hidden [T,B,d], new_mems [L+1, min(M+T, mem_len), B, d] or None).
+    drop: optional callable (site, layer, tensor) -> tensor standing in for the reference's nn.Dropout modules
+    in training mode (sites "emb", "pos", "att", "attn_out", "ff_hid", "ff_out", "final"); the caller owns the
+    masks, which lets the tests hand the oracle the very masks the CUDA kernels use."""
     T, B = data.shape
     dtype = P["r_w_bias"].dtype
     E = P["word_emb.emb_layers.0.weight"]
@@ -156,10 +160,13 @@ def hidden_forward(cfg, P, data, reset=None, mems=None):
         reset = torch.zeros(B, dtype=torch.bool)
     valid = visible_mask(T, M, cfg.mem_len, cfg.same_length, reset)
     pos = sinusoid_by_distance(T + M, cfg.d_model, cfg.clamp_len, dtype)
+    if drop is not None:                                                   # model.py:585-586
+        x = drop("emb", 0, x)
+        pos = drop("pos", 0, pos)
     hids = [x]
     for l in range(cfg.n_layer):
         mem = mems[l] if M > 0 else x.new_zeros(0, B, cfg.d_model)
-        x = _layer(cfg, P, "layers.%d." % l, x, mem, pos, valid)
+        x = _layer(cfg, P, "layers.%d." % l, x, mem, pos, valid, drop, l)
         hids.append(x)
     new_mems = None
     if cfg.mem_len > 0:
@@ -169,6 +176,8 @@ def hidden_forward(cfg, P, data, reset=None, mems=None):
             end = M + T
             beg = max(0, end - cfg.mem_len)
             new_mems = allh[:, beg:end].clone()
+    if drop is not None:
+        x = drop("final", 0, x)                                            # model.py:600 (memory keeps the undropped rows)
     return x, new_mems
 
 
@@ -176,9 +185,9 @@ def logits_of(cfg, P, hidden):
     return hidden @ P["word_emb.emb_layers.0.weight"].t() + P["crit.out_layers.0.bias"]
 
 
-def forward_loss(cfg, P, data, target, reset=None, mems=None):
+def forward_loss(cfg, P, data, target, reset=None, mems=None, drop=None):
     """MemTransformerLM.forward (model.py:678-693): per-token NLL [T,B] (pad not masked)."""
-    hidden, new_mems = hidden_forward(cfg, P, data, reset, mems)
+    hidden, new_mems = hidden_forward(cfg, P, data, reset, mems, drop)
     T, B = target.shape
     lg = logits_of(cfg, P, hidden[-T:]).reshape(T * B, -1)
     nll = -torch.log_softmax(lg, dim=-1).gather(1, target.reshape(-1, 1)).squeeze(1)

@@ -46,7 +46,9 @@ def dr_():
             T, M, B, H, 0, T, sc, lse, dout, H * Dh, delta, dr, du, dvb)
 
 
-res = {"B": B}
+PD = float(os.environ.get("DROPATT", "0"))
+nv.call("commu_relattn_set_dropout", PD, 12345678901234567)
+res = {"B": B, "dropatt": PD}
 fwd()
 for name, fn in (("fwd", fwd), ("dq", dq_), ("dkv", dkv_), ("dr", dr_)):
     fn(); torch.cuda.synchronize()
