@@ -124,7 +124,7 @@ def run_native(args):
             return CFG["n_token"]
 
     cfg = NS(MODEL=NS(num_layers=CFG["n_layer"], num_heads=CFG["n_head"], units=CFG["d_model"],
-                      inner_size=CFG["d_inner"], dropout=0.0, attention_dropout=0.0, same_length=False,
+                      inner_size=CFG["d_inner"], dropout=args.dropout, attention_dropout=args.dropout, same_length=False,
                       clamp_len=-1),
              TRAIN=NS(tgt_length=CFG["tgt_len"], mem_length=CFG["mem_len"]))
     torch.manual_seed(1111)
@@ -235,7 +235,8 @@ def run_native(args):
             "warmup": W, "ms_per_step": round(ms_dev / K, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: 12L d512 H8 Di2048 T=2048 M=2048 V=729 train step "
-                                   "(fwd+bwd+clip+Adam), dropout 0, batch_chunk 1",
+                                   "(fwd+bwd+clip+Adam), dropout %g / attention_dropout %g (reference default 0.1), "
+                                   "batch_chunk 1" % (args.dropout, args.dropout),
                        "global_batch": B * world, "per_gpu_batch": B, "seq_len": T, "mem_len": CFG["mem_len"],
                        "parallelism": "dp%d" % world,
                        "l2": "per-step working set (activations ~%d MB/GPU) >> 126 MB L2" % int(0.64 * 12 * B / 16 * 1000)},
@@ -256,7 +257,7 @@ def run_native(args):
             except Exception as e:      # the decode arm must never hide the training metric
                 out["decode"] = {"error": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(1, 1)
+            out["cpu_baseline"] = cpu_baseline(1, 1, args.dropout)
         print(json.dumps(out), flush=True)
     if comm is not None:
         comm.close()
@@ -362,7 +363,7 @@ def pick_cpu_threads():
     return best
 
 
-def cpu_baseline(steps, warmup):
+def cpu_baseline(steps, warmup, p_drop=0.1):
     """Reference algorithm on the host cores: oracle port (torch CPU fp32, auto-calibrated thread count),
     bounded sample = B=1 sequence of 2048 tokens per step with the memory carried over."""
     from oracle import transfoxl_oracle as orc
@@ -375,17 +376,21 @@ def cpu_baseline(steps, warmup):
     mems = [None]
     T = CFG["tgt_len"]
     times = []
+    drop = None
+    if p_drop > 0:                                     # the reference's nn.Dropout modules (train mode)
+        def drop(site, layer, t):
+            return torch.nn.functional.dropout(t, p_drop, True)
     for s in range(warmup + steps):
         tok = torch.randint(2, 560, (T + 1, 1), generator=gen)
         t0 = time.time()
         _, _, mems, _ = orc.train_step(cfg, P, opt, [(tok[:-1], tok[1:], torch.zeros(1, dtype=torch.bool))],
-                                       mems, lr=1e-4)
+                                       mems, lr=1e-4, drop=drop)
         if s >= warmup:
             times.append(time.time() - t0)
     tot = sum(times)
     return {"value": round(T * len(times) / tot, 2), "unit": "tokens/s", "cores": torch.get_num_threads(),
-            "kind": "port", "sample": "%d step(s) of B=1 x T=2048 (M=2048) fwd+bwd+clip+Adam, %.1f s" %
-                                      (len(times), tot)}
+            "kind": "port", "sample": "%d step(s) of B=1 x T=2048 (M=2048) fwd+bwd+clip+Adam, dropout %g, %.1f s" %
+                                      (len(times), p_drop, tot)}
 
 
 def run_reference(args):
@@ -394,13 +399,13 @@ def run_reference(args):
         return
     K, W = args.steps, args.warmup
     t0 = time.time()
-    cb = cpu_baseline(K, W)
+    cb = cpu_baseline(K, W, args.dropout)
     out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tokens/s",
            "n_gpus": args.gpus, "steps": K, "warmup": W,
            "ms_per_step": round(CFG["tgt_len"] / cb["value"] * 1e3, 1), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "BASELINE configs[1] on CPU (oracle port of the reference algorithm): 12L d512 "
-                                  "H8 Di2048 T=2048 M=2048, bounded sample B=1 per step", "global_batch": 1,
+                                  "H8 Di2048 T=2048 M=2048, dropout %g, bounded sample B=1 per step" % args.dropout, "global_batch": 1,
                       "seq_len": CFG["tgt_len"], "parallelism": "cpu"},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -414,6 +419,8 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--dropout", type=float, default=0.1,
+                    help="MODEL.dropout = MODEL.attention_dropout (reference default 0.1, config_helper.py:11-12)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
     args = ap.parse_args()

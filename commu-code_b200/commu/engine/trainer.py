@@ -121,7 +121,7 @@ class Trainer:
             d_i, t_i = dcs[i].contiguous(), tcs[i].contiguous()
             r_i = rcs[i].contiguous() if rcs[i] is not None else None
             nll, self.mems[i] = eng.forward_loss(d_i, t_i, r_i, self.mems[i], m.mem_len, m.same_length,
-                                                 m.clamp_len, save=True)
+                                                 m.clamp_len, save=True, dropout=m._dropout_arg())
             mask = (t_i != self.pad_id).float()
             w = mask / (mask.sum() * C)
             total += (nll * w).sum()

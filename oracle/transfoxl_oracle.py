@@ -219,7 +219,7 @@ class AdamState:
 
 
 def train_step(cfg, P, opt, batches, mems, lr, clip=1.0, betas=(0.9, 0.999), eps=1e-8,
-               pad_id=0, world=1):
+               pad_id=0, world=1, drop=None):
     """One optimizer step over `batches` = list of (data, target, reset) micro-batches
     (the reference's batch_chunk loop).  Updates P / opt in place.
     Returns (sum of the per-chunk mean losses (already / n_chunks), grad_norm, new mems list)."""
@@ -229,7 +229,7 @@ def train_step(cfg, P, opt, batches, mems, lr, clip=1.0, betas=(0.9, 0.999), eps
     n_chunks = len(batches)
     new_mems = []
     for c, (data, target, reset) in enumerate(batches):
-        nll, nm = forward_loss(cfg, leaves, data, target, reset, mems[c])
+        nll, nm = forward_loss(cfg, leaves, data, target, reset, mems[c], drop=drop)
         loss = nll[target != pad_id].float().mean() / n_chunks
         loss.backward()
         total += float(loss.detach())

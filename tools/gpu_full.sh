@@ -12,3 +12,5 @@ try:
 except Exception as e: print("bench parse failed", e)
 PY
 tail -3 gpurun_out/bench_default.err
+timeout 600 python bench.py --dropout 0 --no-decode --no-cpu-baseline > gpurun_out/bench_drop0.json 2> gpurun_out/bench_drop0.err; cut -c1-400 gpurun_out/bench_drop0.json; python -c "
+import json; j=json.load(open('gpurun_out/bench_drop0.json')); print(j['value'], j['ms_per_step'], j['kernel_time_ms_per_step'])"

@@ -1,16 +1,6 @@
 #!/bin/bash
-# usage: gpu_quick.sh "<pytest -k expr or empty>" [extra bench args]
 set +e
 mkdir -p gpurun_out
-if [ -n "$1" ]; then
-timeout 600 python -m pytest tests/test_kernels_gpu.py tests/test_decode_gpu.py tests/test_model_gpu.py -q -m gpu -k "$1" 2>&1 | tail -25 > gpurun_out/tests_q.log; tail -6 gpurun_out/tests_q.log
-fi
-if grep -q "failed\|error" gpurun_out/tests_q.log 2>/dev/null; then echo "TESTS FAILED - skipping bench"; exit 0; fi
-timeout 900 python bench.py --steps 4 --warmup 3 --no-cpu-baseline $2 > gpurun_out/bench_q.json 2> gpurun_out/bench_q.err
-python - <<'PY'
-import json
-try:
-    j=json.load(open('gpurun_out/bench_q.json')); print({k:j[k] for k in ("value","ms_per_step","kernel_time_ms_per_step","final_loss")}); print(j.get("decode"))
-except Exception as e: print("bench parse failed", e)
-PY
-tail -3 gpurun_out/bench_q.err
+timeout 600 python -m pytest tests/test_dropout_gpu.py -q -m gpu 2>&1 | tail -15 > gpurun_out/tests_drop.log; tail -8 gpurun_out/tests_drop.log
+timeout 600 python bench.py --no-decode --no-cpu-baseline > gpurun_out/bench_drop01.json 2> gpurun_out/bench_drop01.err; python -c "
+import json; j=json.load(open('gpurun_out/bench_drop01.json')); print(j['value'], j['ms_per_step'], j['kernel_time_ms_per_step'], j['gpu_launches'], j['config']['workload'])"; tail -3 gpurun_out/bench_drop01.err
