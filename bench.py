@@ -138,6 +138,9 @@ def run_native(args):
             else:
                 p.normal_(0.0, 0.01)
     model = model.to(dev)
+    if args.decode_only:           # development aid: only the BASELINE configs[3] decode arm
+        print(json.dumps({"decode": decode_bench(model, dev, peaks())}), flush=True)
+        return
     model.train()
     tr = Trainer(model, lr=0.004 / world, warmup_step=100, lr_min=1e-4, clip=1.0, batch_chunk=1, world=world,
                  comm=comm)
@@ -278,6 +281,9 @@ def decode_bench(model, dev, pk, n_new=256, batch=64, mem_len=2048, precision="b
     gen = torch.Generator().manual_seed(5)
     state = DecodeState()
     fill = torch.randint(2, 560, (mem_len + 8, batch), generator=gen).to(dev)
+    if os.environ.get("COMMU_BENCH_FAST_PREFILL") == "1":   # profiling aid (ncu): pretend the ring is already full
+        state = DecodeState(mem_len, mem_len - 1)
+        fill = fill[:4]
     for t in range(fill.shape[0]):                      # pre-fill the ring cache
         logits, state = eng.step(fill[t].contiguous(), state)
     cur, _ = eng.sample(logits, 0.95, 0, 0.9, None, 1, 0)
@@ -423,6 +429,7 @@ def main():
                     help="MODEL.dropout = MODEL.attention_dropout (reference default 0.1, config_helper.py:11-12)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--decode-only", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3

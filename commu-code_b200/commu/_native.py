@@ -34,6 +34,44 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+class DecLinearArgs(ctypes.Structure):
+    """CommuDecLinear of include/commu_b200.h."""
+    _fields_ = [
+        ("prologue", c_int), ("epilogue", c_int),
+        ("B", c_int), ("K", c_int), ("N", c_int), ("d_true", c_int),
+        ("split_k", c_int), ("pdl", c_int),
+        ("tokens", c_void_p), ("emb", c_void_p), ("emb_scale", c_float),
+        ("z", c_void_p), ("ldz", c_int64), ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float),
+        ("a_bf16", c_void_p), ("lda", c_int64),
+        ("x_out", c_void_p), ("ldx", c_int64),
+        ("w", c_void_p), ("ldw", c_int64), ("bias", c_void_p),
+        ("res", c_void_p), ("ldr", c_int64),
+        ("out_f32", c_void_p), ("ldo", c_int64),
+        ("out_bf16", c_void_p), ("ldob", c_int64),
+        ("q_out", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p),
+        ("H", c_int), ("C", c_int), ("slot", c_int),
+        ("dev_state", c_void_p),
+    ]
+
+
+PRO_EMBED, PRO_LN, PRO_BF16 = 0, 1, 2
+EPI_QKV, EPI_RES, EPI_RELU, EPI_LOGITS = 0, 1, 2, 3
+
+
+def dec_linear_args(**kw):
+    """Builds a DecLinearArgs; tensors become device pointers (a prepared struct can be reused every step)."""
+    a = DecLinearArgs()
+    for k, v in kw.items():
+        if hasattr(v, "data_ptr"):
+            v = v.data_ptr()
+        setattr(a, k, v)
+    return a
+
+
+def dec_linear(args):
+    check(lib().commu_decode_fused_linear(ctypes.byref(args), stream_ptr()))
+
+
 def build_if_needed():
     """(Re)build the shared library in-tree when nvcc is available and sources are newer."""
     import importlib.util
@@ -125,6 +163,8 @@ SIGNATURES = {
     "commu_pad_heads": [P, L, I, I, I, I, P, I, L, L, L, P, P],
     "commu_decode_advance": [P, I, I, I, P],
     "commu_decode_attn": [P, P, P, P, I, P, P, I, I, I, I, I, F, P, L, P, P, P],
+    "commu_decode_fused_linear": [P, P],
+    "commu_decode_attn_split": [P, P, P, P, P, P, I, I, I, I, I, F, I, P, P, P, P, L, P, I, P],
     "commu_sample": [P, L, I, I, F, I, F, P, ctypes.c_uint64, ctypes.c_uint64, P, P, L, P, P],
     "commu_comm_unique_id": [P, P],
     "commu_comm_init": [P, P, I, I],

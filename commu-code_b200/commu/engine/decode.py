@@ -7,6 +7,7 @@ the reference (commu/midi_generator/midi_inferrer.py:199-237 over commu/model/mo
 to summation order); `precision="bf16"` halves the streamed bytes (throughput configuration).
 """
 import math
+import os
 
 import torch
 
@@ -92,9 +93,119 @@ class DecodeEngine:
         # bf16 throughput mode: the linear layers run on the tcgen05 GEMM (weights streamed once per step,
         # the 64 batch rows are one half-filled 128-row MMA tile), so activations also exist as bf16 operands
         self.tc_linear = self.bf16 and d % 8 == 0 and self.Di % 8 == 0 and (H * Dh) % 8 == 0
+        # bf16 throughput mode, fused token-step kernels (csrc/decode_fused.cu): 5 launches per layer
+        self.fused = (self.bf16 and d <= 1024 and os.environ.get("COMMU_DECODE_FUSED", "1") != "0")
+        if self.fused:
+            self._prepare_fused()
+            self.tc_linear = False
         if self.tc_linear:
             hb = lambda *s: torch.empty(*s, device=dev, dtype=torch.bfloat16)
             self.wsb = dict(x=hb(B, d), att=hb(B, H * 64), y=hb(B, d), h=hb(B, self.Di))
+
+    @torch.no_grad()
+    def _prepare_fused(self):
+        """Padded bf16 weights and the per-launch argument structs of the fused path.  Layouts: reduction
+        lengths padded to multiples of 64 (zero columns), weight rows to multiples of 16 (zero rows), the qkv
+        rows re-ordered into the padded head layout [q|k|v][H][64] so the kernel scatters without index maps."""
+        dev, m = self.dev, self.m
+        B, H, Dh, d, Di, C, V = self.B, self.H, self.Dh, self.d, self.Di, self.C, self.V
+        r64 = lambda n: (n + 63) // 64 * 64
+        r16 = lambda n: (n + 15) // 16 * 16
+        dp, dip, hd = r64(d), r64(Di), H * 64
+        self.pdl = int(os.environ.get("COMMU_DECODE_PDL", "1") != "0")
+        self.splits = int(os.environ.get("COMMU_DECODE_SPLITS", "0")) or self._pick_splits()
+        ks = None
+        for limit in (512, 1024):        # K chunk per CTA of the FF output GEMM (cluster split of d_inner)
+            for cand in (1, 2, 4, 8):
+                if ks is None and dip % (cand * 32) == 0 and dip // cand <= limit:
+                    ks = cand
+        if ks is None:
+            raise RuntimeError("commu_b200 decode: d_inner %d is beyond the fused decode kernels (<= 8192)" % Di)
+        sd = {n: p for n, p in m.named_parameters()}
+        bf = torch.bfloat16
+        zb = lambda *s: torch.zeros(*s, device=dev, dtype=bf)
+        zf = lambda *s: torch.zeros(*s, device=dev)
+        ws = self.wsf = dict(x=zf(B, d), y=zf(B, d), z1=zf(B, d), z2=zf(B, d), q=zf(B, H, 64), att=zb(B, hd),
+                             h=zb(B, dip), part=zf(B * H * self.splits * 66),
+                             cnt=torch.zeros(B * H, dtype=torch.int32, device=dev))
+        self.tok_buf = torch.zeros(B, dtype=torch.int64, device=dev)   # placeholder; step() points at its tokens
+        self.fw, self.fargs = [], []
+        mk = nv.dec_linear_args
+        for l in range(self.L):
+            pre = "layers.%d." % l
+            wq = sd[pre + "dec_attn.qkv_net.weight"].detach()
+            wqkv = zb(3 * hd, dp)
+            wqkv.view(3, H, 64, dp)[:, :, :Dh, :d].copy_(wq.view(3, H, Dh, d))
+            wo = zb(r16(d), hd)
+            wo.view(r16(d), H, 64)[:d, :, :Dh].copy_(sd[pre + "dec_attn.o_net.weight"].detach().view(d, H, Dh))
+            w1 = zb(dip, dp)
+            w1[:Di, :d].copy_(sd[pre + "pos_ff.CoreNet.0.weight"].detach())
+            b1 = zf(dip)
+            b1[:Di].copy_(sd[pre + "pos_ff.CoreNet.0.bias"].detach())
+            w2 = zb(r16(d), dip)
+            w2[:d, :Di].copy_(sd[pre + "pos_ff.CoreNet.3.weight"].detach())
+            W = self.W[l]
+            self.fw.append((wqkv, wo, w1, b1, w2))
+            prev = self.W[l - 1] if l else None
+            common = dict(B=B, pdl=self.pdl, split_k=1)
+            if l == 0:
+                a_qkv = mk(prologue=nv.PRO_EMBED, tokens=self.tok_buf, emb=self.emb32, emb_scale=math.sqrt(d), **common)
+            else:
+                a_qkv = mk(prologue=nv.PRO_LN, z=ws["z2"], ldz=d, gamma=prev["g2"], beta=prev["be2"], eps=1e-5, **common)
+            a_qkv.epilogue, a_qkv.K, a_qkv.N, a_qkv.d_true = nv.EPI_QKV, dp, 3 * hd, d
+            a_qkv.x_out, a_qkv.ldx = ws["x"].data_ptr(), d
+            a_qkv.w, a_qkv.ldw = wqkv.data_ptr(), dp
+            a_qkv.q_out, a_qkv.k_cache, a_qkv.v_cache = ws["q"].data_ptr(), self.kc[l].data_ptr(), self.vc[l].data_ptr()
+            a_qkv.H, a_qkv.C = H, C
+            a_o = mk(prologue=nv.PRO_BF16, epilogue=nv.EPI_RES, K=hd, N=d, a_bf16=ws["att"], lda=hd, w=wo, ldw=hd,
+                     res=ws["x"], ldr=d, out_f32=ws["z1"], ldo=d, **common)
+            a_f1 = mk(prologue=nv.PRO_LN, epilogue=nv.EPI_RELU, K=dp, N=dip, d_true=d, z=ws["z1"], ldz=d, gamma=W["g1"],
+                      beta=W["be1"], eps=1e-5, x_out=ws["y"], ldx=d, w=w1, ldw=dp, bias=b1, out_bf16=ws["h"], ldob=dip,
+                      **common)
+            a_f2 = mk(prologue=nv.PRO_BF16, epilogue=nv.EPI_RES, K=dip, N=d, a_bf16=ws["h"], lda=dip, w=w2, ldw=dip,
+                      bias=W["b2"], res=ws["y"], ldr=d, out_f32=ws["z2"], ldo=d, B=B, pdl=self.pdl, split_k=ks)
+            self.fargs.append((a_qkv, a_o, a_f1, a_f2))
+        wl = zb(r16(V), dp)
+        wl[:V, :d].copy_(self.emb32)
+        last = self.W[-1]
+        self.fw.append((wl,))
+        self.a_logits = mk(prologue=nv.PRO_LN, epilogue=nv.EPI_LOGITS, K=dp, N=V, d_true=d, z=ws["z2"], ldz=d,
+                           gamma=last["g2"], beta=last["be2"], eps=1e-5, w=wl, ldw=dp, bias=self.lbias,
+                           out_f32=self.ws["logits"], ldo=V, **dict(B=B, pdl=self.pdl, split_k=1))
+
+    def _pick_splits(self):
+        """Key splits of the decode attention: B*H*splits CTAs should fill the SMs' resident slots (3 CTAs of 256
+        threads per SM) a near-integer number of times, with enough CTAs to even out the tail."""
+        sms = torch.cuda.get_device_properties(self.dev).multi_processor_count if self.dev.type == "cuda" else 148
+        slots, work = 3 * sms, self.B * self.H
+        best, best_eff = 1, 0.0
+        for s in range(1, 17):
+            if self.mem_len // s < 128:
+                break
+            waves = work * s / slots
+            eff = waves / math.ceil(waves)
+            if eff > best_eff + 0.02:
+                best, best_eff = s, eff
+        return best
+
+    def _step_fused(self, tokens, slot, n_vis, dstate):
+        B, H, C = self.B, self.H, self.C
+        ws = self.wsf
+        if tokens.dtype != torch.int64 or not tokens.is_contiguous() or tokens.numel() != B:
+            raise RuntimeError("commu_b200 decode: tokens must be a contiguous int64 [B] device tensor")
+        self.fargs[0][0].tokens = tokens.data_ptr()
+        dptr = dstate.data_ptr() if dstate is not None else None
+        for l in range(self.L):
+            a_qkv, a_o, a_f1, a_f2 = self.fargs[l]
+            a_qkv.slot, a_qkv.dev_state = slot, dptr
+            nv.dec_linear(a_qkv)
+            nv.call("commu_decode_attn_split", ws["q"], self.kc[l], self.vc[l], self.rt[l], self.u, self.vb, B, H, C,
+                    n_vis, slot, self.scale, self.splits, ws["part"], ws["cnt"], ws["att"], None, H * 64, dstate,
+                    self.pdl)
+            nv.dec_linear(a_o)
+            nv.dec_linear(a_f1)
+            nv.dec_linear(a_f2)
+        nv.dec_linear(self.a_logits)
 
     def _linear(self, x, w, bias, relu, res, out, B, N, K):
         nv.call("commu_decode_linear", x, x.stride(0), w, w.stride(0), int(w.dtype == torch.bfloat16), bias,
@@ -117,6 +228,8 @@ class DecodeEngine:
     def _step_kernels(self, tokens, slot, n_vis, dstate):
         """One token for every sequence.  With `dstate` (device int32[4]) the ring slot / visible count are
         read on the device, so the identical launch sequence can be replayed from a CUDA graph."""
+        if self.fused:
+            return self._step_fused(tokens, slot, n_vis, dstate)
         B, H, Dh, d, C = self.B, self.H, self.Dh, self.d, self.C
         ws = self.ws
         cb = int(self.bf16)

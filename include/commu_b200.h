@@ -245,6 +245,62 @@ int commu_decode_advance(int* state, int C, int mem_len, int extra_visible, void
 int commu_decode_attn(const float* q, const void* kcache, const void* vcache, const void* rtab, int cache_bf16,
                       const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
                       float scale, float* out, int64_t ldo, const int* dev_state, void* out_bf16, void* stream);
+/* ---- fused token-step kernels of the bf16 decode engine (one decoder layer = 5 launches) ----
+ * commu_decode_fused_linear: out[b, n0..n0+15] per CTA = epilogue( prologue(input)[b, :K] . W[n, :K] ), B <= 64
+ * rows as the M side of warp-level bf16 MMAs, fp32 accumulation, weights streamed once per call.
+ *   prologue 0: x = emb[tokens[b]] * emb_scale          (AdaptiveEmbedding, commu/model/model.py:409-420)
+ *            1: x = LayerNorm(z[b]; gamma, beta, eps)   (post-LN of the previous block, model.py:352 / :181)
+ *            2: x = a_bf16[b, :K]                       (already a bf16 operand)
+ *            for 0 / 1 the fp32 x is also written to x_out (the residual stream) when non-NULL; d_true is the
+ *            embedding / LayerNorm width (<= K, columns d_true..K-1 are zero).
+ *   epilogue 0: N = 3*H*64 columns in the padded head layout [q|k|v][H][64]: q -> q_out fp32 [B,H,64], k / v ->
+ *               ring slot `slot` (or dev_state[0]) of the bf16 caches [B,H,C,64]   (qkv_net, model.py:283-310)
+ *            1: out_f32[b,n] = acc + bias[n] + res[b,n]                              (o_net / FF output + residual)
+ *            2: out_bf16[b,n] = bf16(relu(acc + bias[n]))                            (CoreNet.0 + ReLU, model.py:163-165)
+ *            3: out_f32[b,n] = acc + bias[n], n < N                                  (tied logits, model.py:44-51)
+ * w: bf16 [ceil16(N), K] row-major (rows beyond N zero).  K is a multiple of 64; split_k in {1,2,4,8} splits K
+ * over a thread-block cluster (prologue 2 only) with a fixed-order DSMEM reduction; K / split_k <= 1024.
+ * pdl != 0 launches with programmatic stream serialization (the kernel prefetches its weights before
+ * griddepcontrol.wait). */
+typedef struct {
+  int prologue, epilogue;
+  int B, K, N, d_true;
+  int split_k, pdl;
+  const int64_t* tokens;
+  const float* emb;
+  float emb_scale;
+  const float* z;
+  int64_t ldz;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  const void* a_bf16;
+  int64_t lda;
+  float* x_out;
+  int64_t ldx;
+  const void* w;
+  int64_t ldw;
+  const float* bias;
+  const float* res;
+  int64_t ldr;
+  float* out_f32;
+  int64_t ldo;
+  void* out_bf16;
+  int64_t ldob;
+  float* q_out;
+  void* k_cache;
+  void* v_cache;
+  int H, C, slot;
+  const int* dev_state;
+} CommuDecLinear;
+int commu_decode_fused_linear(const CommuDecLinear* args, void* stream);
+/* commu_decode_attn over a bf16 cache with the visible keys of every (sequence, head) split over `splits` CTAs
+ * (grid H x B x splits, sized for ~7 resident CTAs per SM); partial: fp32 [B*H*splits*66] scratch, counters:
+ * int32 [B*H] zero-initialised once (the last-arriving CTA merges the partials in split order and re-zeroes). */
+int commu_decode_attn_split(const float* q, const void* kcache, const void* vcache, const void* rtab,
+                            const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
+                            float scale, int splits, float* partial, int* counters, void* out_bf16, float* out_f32,
+                            int64_t ldo, const int* dev_state, int pdl, void* stream);
 /* Sampler over B rows of raw logits (token 0 is never sampled, midi_inferrer.py:206/:220): temperature
  * (0 = greedy one-hot, :211-213), top-k (:224-226), top-p (new), wrong-token mask (:227-229),
  * renormalise (:230-231), counter-based multinomial draw (:234-237).  tokens and/or probs_out. */

@@ -64,6 +64,90 @@ def test_decode_bf16_logits_close():
     assert np.array_equal(toks[ok], z["tokens"][ok])
 
 
+@pytest.mark.parametrize("env", [dict(COMMU_DECODE_FUSED="0"),
+                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_PDL="0", COMMU_DECODE_SPLITS="1"),
+                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_PDL="1", COMMU_DECODE_SPLITS="3")])
+def test_decode_bf16_paths_close_to_golden(env, monkeypatch):
+    """Every bf16 decode path (tcgen05-GEMM step, fused step with / without programmatic dependent launch and key
+    splits) stays within the bf16 tolerance of the fp32 reference logits (Dh = 16 < 64: padded head layout)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    toks, worst, z = _run_decode("bf16")
+    assert worst < 0.06 * np.abs(z["logits"]).max() + 0.02, (env, worst)
+
+
+def _bench_like_model(L=2, H=8, d=512, Di=2048, V=729, mem_len=300, seed=3):
+    class Vc:
+        def __len__(self):
+            return V
+    from commu.model.model import MemTransformerLM
+    c = NS(MODEL=NS(num_layers=L, num_heads=H, units=d, inner_size=Di, dropout=0.0, attention_dropout=0.0,
+                    same_length=True, clamp_len=-1), TRAIN=NS(tgt_length=1, mem_length=mem_len))
+    torch.manual_seed(seed)
+    m = MemTransformerLM(c, Vc())
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("layer_norm.weight"):
+                p.normal_(1.0, 0.05)
+            elif p.dim() == 1:
+                p.normal_(0.0, 0.05)
+            else:
+                p.normal_(0.0, 0.04)
+    return m.cuda().eval()
+
+
+@pytest.mark.parametrize("shape", [dict(H=8, d=512, Di=2048, B=64, mem_len=300),     # bench shape, ring wraps
+                                   dict(H=10, d=500, Di=1000, B=5, mem_len=200),     # checkpoint shape: Dh = 50, d % 64 != 0
+                                   dict(H=16, d=1024, Di=4096, B=33, mem_len=130)])   # widest supported rows
+def test_decode_fused_step_matches_unfused(shape, monkeypatch):
+    """Fused token-step kernels (csrc/decode_fused.cu) vs the kernel-per-op bf16 step on identical tokens: same
+    bf16 operands and fp32 accumulation, so the logits agree to accumulation-order noise, for mem_len + 40 steps
+    (the ring cache wraps), and vs the fp32 engine within the bf16 tolerance."""
+    from commu.engine.decode import DecodeEngine
+    B, mem_len = shape["B"], shape["mem_len"]
+    model = _bench_like_model(H=shape["H"], d=shape["d"], Di=shape["Di"], mem_len=mem_len)
+    monkeypatch.setenv("COMMU_DECODE_FUSED", "0")
+    ref = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision="bf16")
+    f32 = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision="fp32")
+    monkeypatch.setenv("COMMU_DECODE_FUSED", "1")
+    monkeypatch.setenv("COMMU_DECODE_SPLITS", "2")
+    fus = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision="bf16")
+    assert fus.fused and not ref.fused
+    g = torch.Generator().manual_seed(1)
+    toks = torch.randint(1, 729, (mem_len + 40, B), generator=g).cuda()
+    from commu.engine.decode import DecodeState
+    sa, sb, sc = DecodeState(), DecodeState(), DecodeState()
+    worst, worst32, scale = 0.0, 0.0, 0.0
+    for t in range(toks.shape[0]):
+        la, sa = ref.step(toks[t].contiguous(), sa)
+        lb, sb = fus.step(toks[t].contiguous(), sb)
+        worst = max(worst, float((la - lb).abs().max()))
+        if t % 16 == 0 or t >= mem_len:
+            lc, sc = f32.step(toks[t].contiguous(), sc)
+            worst32 = max(worst32, float((lc - lb).abs().max()))
+            scale = max(scale, float(lc.abs().max()))
+        else:
+            _, sc = f32.step(toks[t].contiguous(), sc)
+    assert worst < 0.02 * scale + 1e-3, (worst, scale)
+    assert worst32 < 0.06 * scale + 0.02, (worst32, scale)
+
+
+def test_decode_fused_graph_equals_eager(monkeypatch):
+    """bf16 fused step: CUDA-graph replay (device-resident ring state, programmatic dependent launches captured
+    into the graph) produces the same greedy tokens as eager launches; repeated runs are bit-identical."""
+    from commu.engine.decode import DecodeEngine
+    model = _bench_like_model(L=3, mem_len=150)
+    g = torch.Generator().manual_seed(2)
+    ctx = torch.randint(1, 729, (7, 16), generator=g).cuda()
+    outs = []
+    for use_graph in (False, True, True):
+        eng = DecodeEngine(model, batch=16, mem_len=150, same_length=True, precision="bf16")
+        assert eng.fused
+        outs.append(eng.generate(ctx, 170, temperature=0.0, top_k=0, top_p=0.0, use_graph=use_graph).cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    assert np.array_equal(outs[1], outs[2])
+
+
 def test_sampler_matches_reference_probs():
     from commu import _native as nv
     z = np.load(os.path.join(GOLDEN, "sampler_probs.npz"))

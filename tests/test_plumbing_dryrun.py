@@ -25,6 +25,24 @@ class _Stub:
                 assert isinstance(a, (int, float)), (name, a)
         self.calls.append(name)
 
+    def dec_linear(self, a):
+        assert isinstance(a, nv.DecLinearArgs)
+        assert a.prologue in (nv.PRO_EMBED, nv.PRO_LN, nv.PRO_BF16) and a.epilogue in range(4)
+        assert a.w and a.K % 64 == 0 and a.N > 0 and 1 <= a.B <= 64 and a.ldw == a.K
+        if a.prologue == nv.PRO_LN:
+            assert a.z and a.gamma and a.beta and a.eps > 0 and 0 < a.d_true <= a.K
+        if a.prologue == nv.PRO_EMBED:
+            assert a.tokens and a.emb and a.emb_scale > 0
+        if a.prologue == nv.PRO_BF16:
+            assert a.a_bf16 and a.lda >= a.K and a.K % (a.split_k * 32) == 0
+        if a.epilogue == nv.EPI_QKV:
+            assert a.q_out and a.k_cache and a.v_cache and a.N == 3 * a.H * 64 and 0 <= a.slot < a.C
+        if a.epilogue == nv.EPI_RES:
+            assert a.res and a.out_f32
+        if a.epilogue == nv.EPI_RELU:
+            assert a.out_bf16 and a.N % 16 == 0
+        self.calls.append("dec_linear")
+
     def gemm(self, a, b, **kw):
         assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
         for k in ("m", "n", "k"):
@@ -37,6 +55,7 @@ def stub(monkeypatch):
     s = _Stub()
     monkeypatch.setattr(nv, "call", s.call)
     monkeypatch.setattr(nv, "gemm", s.gemm)
+    monkeypatch.setattr(nv, "dec_linear", s.dec_linear)
     monkeypatch.setattr(nv, "lib", lambda: None)
     import commu.engine.native_lm as nl
     import commu.engine.decode as dec
@@ -154,3 +173,9 @@ def test_decode_plumbing(stub, monkeypatch):
         out = eng.generate(ctx, 4, temperature=0.95, top_k=0, top_p=0.9, seed=1, use_graph=False)
         assert out.shape == (4, 3)
     assert "commu_decode_attn" in stub.calls and "commu_sample" in stub.calls
+    assert "commu_decode_attn_split" in stub.calls and "dec_linear" in stub.calls      # bf16 = fused step
+    monkeypatch.setenv("COMMU_DECODE_FUSED", "0")
+    n0 = stub.calls.count("gemm")
+    eng = dec.DecodeEngine(m, 3, 24, True, "bf16")
+    eng.generate(torch.randint(1, 53, (5, 3)), 2, temperature=0.95, top_k=0, top_p=0.9, seed=1, use_graph=False)
+    assert not eng.fused
