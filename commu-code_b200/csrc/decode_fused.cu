@@ -23,6 +23,11 @@
 
 namespace cg = cooperative_groups;
 
+namespace cb_host {
+int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+                      uint32_t box_outer);   // gemm.cu
+}
+
 namespace {
 
 constexpr int DF_THREADS = 256;
@@ -53,6 +58,109 @@ struct LinP {
   float* q_out; bf16* k_cache; bf16* v_cache; int H, C, slot; const int* dstate;
 };
 
+// Embedding / LayerNorm prologue: each warp owns 8 of the 64 rows and keeps RG of them in flight (all loads
+// issued before the first reduction); a lane holds columns 4*(lane + 32*i) .. +3, i < MAXV.
+template <int PRO, int MAXV, int RG>
+__device__ __forceinline__ void prologue_rows(const LinP& p, bf16* sA, int lds, int warp, int lane) {
+  const int d = p.d_true, KC = p.KC;
+  float4 gm[MAXV], bt[MAXV];
+  if (PRO == PRO_LN) {
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      gm[i] = bt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < d) {
+        gm[i] = *reinterpret_cast<const float4*>(p.gamma + c);
+        bt[i] = *reinterpret_cast<const float4*>(p.beta + c);
+      }
+    }
+  }
+  for (int r0 = warp * 8; r0 < warp * 8 + 8; r0 += RG) {
+    float4 v[RG][MAXV];
+    float s[RG];
+#pragma unroll
+    for (int j = 0; j < RG; ++j) {
+      const int r = r0 + j;
+      const float* src = nullptr;
+      if (r < p.B) src = PRO == PRO_EMBED ? p.emb + p.tokens[r] * (long long)d : p.z + (long long)r * p.ldz;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = 4 * (lane + 32 * i);
+        v[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src && c < d) v[j][i] = *reinterpret_cast<const float4*>(src + c);
+      }
+    }
+    if (PRO == PRO_EMBED) {
+#pragma unroll
+      for (int j = 0; j < RG; ++j)
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+          v[j][i].x *= p.emb_scale; v[j][i].y *= p.emb_scale; v[j][i].z *= p.emb_scale; v[j][i].w *= p.emb_scale;
+        }
+    } else {
+#pragma unroll
+      for (int j = 0; j < RG; ++j) {
+        s[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) s[j] += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < RG; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      float mean[RG];
+#pragma unroll
+      for (int j = 0; j < RG; ++j) {
+        mean[j] = s[j] / (float)d;
+        s[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+          if (4 * (lane + 32 * i) < d) {
+            const float a0 = v[j][i].x - mean[j], a1 = v[j][i].y - mean[j], a2 = v[j][i].z - mean[j], a3 = v[j][i].w - mean[j];
+            s[j] += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int j = 0; j < RG; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = 4 * (lane + 32 * i);
+        if (c < d) {
+#pragma unroll
+          for (int j = 0; j < RG; ++j) {
+            if (r0 + j < p.B) {
+              const float rstd = rsqrtf(s[j] / (float)d + p.eps);
+              v[j][i].x = (v[j][i].x - mean[j]) * rstd * gm[i].x + bt[i].x;
+              v[j][i].y = (v[j][i].y - mean[j]) * rstd * gm[i].y + bt[i].y;
+              v[j][i].z = (v[j][i].z - mean[j]) * rstd * gm[i].z + bt[i].z;
+              v[j][i].w = (v[j][i].w - mean[j]) * rstd * gm[i].w + bt[i].w;
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < RG; ++j) {
+      const int r = r0 + j;
+      const bool writer = p.x_out && r < p.B && (r % (int)gridDim.x) == (int)blockIdx.x;
+#pragma unroll
+      for (int i = 0; i < MAXV; ++i) {
+        const int c = 4 * (lane + 32 * i);
+        if (c < KC) {
+          uint2 pk;
+          pk.x = cb::pack_bf16(v[j][i].x, v[j][i].y);
+          pk.y = cb::pack_bf16(v[j][i].z, v[j][i].w);
+          *reinterpret_cast<uint2*>(sA + r * lds + c) = pk;
+        }
+        if (writer && c < d) *reinterpret_cast<float4*>(p.x_out + (long long)r * p.ldx + c) = v[j][i];
+      }
+    }
+  }
+}
+
 // A tile [64][KC + 8] bf16, W slice [16][KC + 8] bf16, partial sums [2][64][20] fp32
 template <int PRO, int EPI, bool CLUSTER>
 __global__ void __launch_bounds__(DF_THREADS) dec_linear_kernel(const LinP p) {
@@ -67,89 +175,39 @@ __global__ void __launch_bounds__(DF_THREADS) dec_linear_kernel(const LinP p) {
 
   // ---- weight slice (independent of the previous kernel): cp.async, 16 B per request ----
   {
-    const int chunks = KC >> 3;
-    for (int c = tid; c < DF_NT * chunks; c += DF_THREADS) {
-      const int r = c / chunks, kk = (c - r * chunks) << 3;
-      cb::cp_async16(sW + r * lds + kk, p.w + (long long)(n0 + r) * p.ldw + k0 + kk, true);
-    }
+    const bf16* wsrc = p.w + (long long)n0 * p.ldw + k0;
+    for (int r = warp; r < DF_NT; r += DF_THREADS / 32)
+      for (int kk = lane * 8; kk < KC; kk += 256) cb::cp_async16(sW + r * lds + kk, wsrc + (long long)r * p.ldw + kk, true);
     cb::cp_async_commit();
+  }
+  // epilogue operands of this thread (row, 4 columns): parameters now, activations right after the wait, so
+  // that their latency hides behind the tile loads and the MMAs
+  const int row = tid >> 2, cq = (tid & 3) * 4;
+  float ebias[4] = {0.f, 0.f, 0.f, 0.f}, eres[4] = {0.f, 0.f, 0.f, 0.f};
+  if (EPI != EPI_QKV && p.bias) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n0 + cq + j < p.N) ebias[j] = p.bias[n0 + cq + j];
   }
   pdl_wait();
   pdl_launch();
+  if (EPI == EPI_RES && row < p.B && (!CLUSTER || blockIdx.y == 0)) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n0 + cq + j < p.N) eres[j] = p.res[(long long)row * p.ldr + n0 + cq + j];
+  }
 
   // ---- A tile ----
   if (PRO == PRO_BF16) {
-    const int chunks = KC >> 3;
-    for (int c = tid; c < DF_M * chunks; c += DF_THREADS) {
-      const int r = c / chunks, kk = (c - r * chunks) << 3;
+    const bf16* asrc = p.a + k0;
+    for (int r = warp; r < DF_M; r += DF_THREADS / 32) {
       const bool ok = r < p.B;
-      cb::cp_async16(sA + r * lds + kk, p.a + (long long)(ok ? r : 0) * p.lda + k0 + kk, ok);
+      for (int kk = lane * 8; kk < KC; kk += 256) cb::cp_async16(sA + r * lds + kk, asrc + (long long)(ok ? r : 0) * p.lda + kk, ok);
     }
     cb::cp_async_commit();
   } else {
-    // each warp owns 8 rows; a lane holds columns 4*(lane + 32*i) .. +3
-    constexpr int MAXV = 8;   // d <= 1024
-    const int d = p.d_true;
-    for (int rr = 0; rr < 8; ++rr) {
-      const int r = warp * 8 + rr;
-      float4 v[MAXV];
-      const float* src = nullptr;
-      float scale = 1.f;
-      if (r < p.B) {
-        if (PRO == PRO_EMBED) {
-          src = p.emb + p.tokens[r] * (long long)d;
-          scale = p.emb_scale;
-        } else {
-          src = p.z + (long long)r * p.ldz;
-        }
-      }
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int c = 4 * (lane + 32 * i);
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src && c < d) v[i] = *reinterpret_cast<const float4*>(src + c);
-        if (PRO == PRO_EMBED) { v[i].x *= scale; v[i].y *= scale; v[i].z *= scale; v[i].w *= scale; }
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-      }
-      if (PRO == PRO_LN) {
-        const float mean = cb::warp_sum(s) / (float)d;
-        float q = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-          const int c = 4 * (lane + 32 * i);
-          if (c < d) {
-            const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
-            q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-          }
-        }
-        const float rstd = rsqrtf(cb::warp_sum(q) / (float)d + p.eps);
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-          const int c = 4 * (lane + 32 * i);
-          if (src && c < d) {
-            const float4 g = *reinterpret_cast<const float4*>(p.gamma + c);
-            const float4 b = *reinterpret_cast<const float4*>(p.beta + c);
-            v[i].x = (v[i].x - mean) * rstd * g.x + b.x;
-            v[i].y = (v[i].y - mean) * rstd * g.y + b.y;
-            v[i].z = (v[i].z - mean) * rstd * g.z + b.z;
-            v[i].w = (v[i].w - mean) * rstd * g.w + b.w;
-          }
-        }
-      }
-      const bool writer = p.x_out && r < p.B && (r % (int)gridDim.x) == (int)blockIdx.x;
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int c = 4 * (lane + 32 * i);
-        if (c < KC) {
-          uint2 pk;
-          pk.x = cb::pack_bf16(v[i].x, v[i].y);
-          pk.y = cb::pack_bf16(v[i].z, v[i].w);
-          *reinterpret_cast<uint2*>(sA + r * lds + c) = pk;
-        }
-        if (writer && c < d) *reinterpret_cast<float4*>(p.x_out + (long long)r * p.ldx + c) = v[i];
-      }
-    }
+    if (p.d_true <= 512) prologue_rows<PRO, 4, 4>(p, sA, lds, warp, lane);
+    else prologue_rows<PRO, 8, 2>(p, sA, lds, warp, lane);
   }
   cb::cp_async_wait<0>();
   __syncthreads();
@@ -185,7 +243,6 @@ __global__ void __launch_bounds__(DF_THREADS) dec_linear_kernel(const LinP p) {
   __syncthreads();
 
   // ---- epilogue: thread = (row, 4 consecutive columns) ----
-  const int row = tid >> 2, cq = (tid & 3) * 4;
   float v[4];
   {
     const float4 a = *reinterpret_cast<const float4*>(sP + row * DF_PART_LD + cq);
@@ -227,10 +284,8 @@ __global__ void __launch_bounds__(DF_THREADS) dec_linear_kernel(const LinP p) {
       *reinterpret_cast<uint2*>(dst) = pk;
     }
   } else if (EPI == EPI_RELU) {
-    if (p.bias) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] += p.bias[n + j];
-    }
+    for (int j = 0; j < 4; ++j) v[j] += ebias[j];
     uint2 pk;
     pk.x = cb::pack_bf16(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f));
     pk.y = cb::pack_bf16(fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
@@ -238,12 +293,7 @@ __global__ void __launch_bounds__(DF_THREADS) dec_linear_kernel(const LinP p) {
   } else {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (n + j < p.N) {
-        float o = v[j];
-        if (p.bias) o += p.bias[n + j];
-        if (EPI == EPI_RES) o += p.res[(long long)row * p.ldr + n + j];
-        p.out_f32[(long long)row * p.ldo + n + j] = o;
-      }
+      if (n + j < p.N) p.out_f32[(long long)row * p.ldo + n + j] = v[j] + ebias[j] + eres[j];
     }
   }
 }
@@ -425,6 +475,513 @@ __global__ void __launch_bounds__(DA2_WARPS * 32, 3) dec_attn_split_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same attention on warp-level tensor cores with an asynchronous copy pipeline (the product path).
+// The SIMT kernel above spends ~500 issue slots per 16 keys on bf16 unpacking and FMAs (ncu: 45 % issue-active
+// at 64 % of HBM peak); here a 64-key tile of K, V (HBM) and R (L2) is copied by cp.async into a 4-stage
+// XOR-swizzled shared-memory ring and each warp spends ~140 issue slots per 16 keys:
+//   S^T = (q+u) K^T + (q+vb) R^T   : A = the query as row 0 of a 16-row operand, B = K / R rows via ldmatrix
+//   O  += P V                      : the score fragment is already the A fragment of the second MMA
+// rt_h is the R table laid out [H][C][64] so that a tile is contiguous per head.
+// ---------------------------------------------------------------------------------------------
+constexpr int AM_WARPS = 4;
+constexpr int AM_THREADS = AM_WARPS * 32;
+constexpr int AM_TILE = 64;
+constexpr int AM_MAT = AM_TILE * 128;          // one 64 x 64 bf16 matrix
+constexpr int AM_STAGE_BYTES = 3 * AM_MAT;     // K, R, V
+
+__device__ __forceinline__ uint32_t am_swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+template <int AM_STAGES>
+__global__ void __launch_bounds__(AM_THREADS) dec_attn_mma_kernel(
+    const float* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
+    const bf16* __restrict__ rt_h, const float* __restrict__ u, const float* __restrict__ vb, int H, int C,
+    int n_vis, int cur_slot, float scale, float* __restrict__ partial, int* __restrict__ counters,
+    bf16* __restrict__ out_bf16, float* __restrict__ out_f32, long long ldo, const int* __restrict__ dstate,
+    int cyclic, int dbg) {
+  extern __shared__ __align__(128) unsigned char am_smem[];
+  __shared__ float sh_m[AM_WARPS], sh_l[AM_WARPS], sh_o[AM_WARPS][64];
+  __shared__ int sh_last;
+  pdl_wait();
+  pdl_launch();
+  if (dstate) {
+    cur_slot = dstate[0];
+    n_vis = dstate[1];
+  }
+  // split index fastest: the CTAs of one (sequence, head) are neighbours in launch order
+  const int sp = blockIdx.x, S = gridDim.x, h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const uint32_t sbase = cb::smem_u32(am_smem);
+  const bf16* kbase = kc + ((long long)b * H + h) * C * 64;
+  const bf16* vbase = vc + ((long long)b * H + h) * C * 64;
+  const bf16* rbase = rt_h + (long long)h * C * 64;
+  // tiles of 64 ages: dealt round-robin (cyclic: the S CTAs of a (sequence, head) sweep adjacent tiles together, so
+  // the DRAM pages they touch are neighbours) or in contiguous runs
+  const int NT = (n_vis + AM_TILE - 1) / AM_TILE;
+  const int t_lo = cyclic ? sp : (int)(((long long)sp * NT) / S);
+  const int t_step = cyclic ? S : 1;
+  const int ntiles = cyclic ? (NT - sp + S - 1) / S : (int)(((long long)(sp + 1) * NT) / S) - t_lo;
+
+  auto load_tile = [&](int it) {
+    if (it < ntiles) {
+      const int a0 = (t_lo + it * t_step) * AM_TILE;
+      const uint32_t st = sbase + (it % AM_STAGES) * AM_STAGE_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = tid + AM_THREADS * i;
+        const int row = idx >> 3, ch = idx & 7;
+        const int a = a0 + row;
+        const bool ok = a < n_vis;
+        const int ac = ok ? a : 0;
+        int slot = cur_slot - ac;
+        if (slot < 0) slot += C;
+        const uint32_t dst = st + am_swz(row, ch);
+        const int sz = ok ? 16 : 0;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(kbase + (long long)slot * 64 + ch * 8), "r"(sz));
+        // dbg (timing experiments only): 1 = every R tile from the first 8 KB of the table, 2 = V from the K rows
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + AM_MAT), "l"(rbase + (long long)((dbg & 1) ? row : ac) * 64 + ch * 8), "r"(sz));
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + 2 * AM_MAT), "l"(((dbg & 2) ? kbase : vbase) + (long long)slot * 64 + ch * 8), "r"(sz));
+      }
+    }
+    cb::cp_async_commit();
+  };
+#pragma unroll
+  for (int it = 0; it < AM_STAGES - 1; ++it) load_tile(it);
+
+  // query fragments: row 0 of the 16-row A operand (lanes 0..3), everything else zero
+  uint32_t aqu[4][2], aqv[4][2];
+  {
+    const float* qp = q + ((long long)b * H + h) * 64;
+    const float* up = u + h * 64;
+    const float* vp = vb + h * 64;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        const int c = 16 * ks + 8 * hf + 2 * t;
+        const float q0 = qp[c], q1 = qp[c + 1];
+        aqu[ks][hf] = g == 0 ? cb::pack_bf16(q0 + up[c], q1 + up[c + 1]) : 0u;
+        aqv[ks][hf] = g == 0 ? cb::pack_bf16(q0 + vp[c], q1 + vp[c + 1]) : 0u;
+      }
+    }
+  }
+  float m = -INFINITY, l = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  const float sl2 = scale * 1.4426950408889634f;
+  const int row_b = 16 * warp + (lane & 7) + (lane >> 4) * 8, ch_b = (lane >> 3) & 1;       // K / R operand rows
+  const int row_v = 16 * warp + (lane & 7) + ((lane >> 3) & 1) * 8, ch_v = lane >> 4;       // V operand rows (transposed)
+
+  for (int it = 0; it < ntiles; ++it) {
+    cb::cp_async_wait<AM_STAGES - 2>();
+    __syncthreads();
+    load_tile(it + AM_STAGES - 1);
+    const uint32_t st = sbase + (it % AM_STAGES) * AM_STAGE_BYTES;
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t bk[4], br[4];
+      cb::ldmatrix_x4(bk, st + am_swz(row_b, 2 * ks + ch_b));
+      cb::ldmatrix_x4(br, st + AM_MAT + am_swz(row_b, 2 * ks + ch_b));
+      const uint32_t au[4] = {aqu[ks][0], 0u, aqu[ks][1], 0u}, av[4] = {aqv[ks][0], 0u, aqv[ks][1], 0u};
+      const uint32_t k0[2] = {bk[0], bk[1]}, k1[2] = {bk[2], bk[3]}, r0[2] = {br[0], br[1]}, r1[2] = {br[2], br[3]};
+      cb::mma_bf16_16816(acc0, au, k0);
+      cb::mma_bf16_16816(acc1, au, k1);
+      cb::mma_bf16_16816(acc0, av, r0);
+      cb::mma_bf16_16816(acc1, av, r1);
+    }
+    // row 0 of the score tile: this lane holds keys 2t, 2t+1, 8+2t, 9+2t of the warp's 16
+    const int abase = (t_lo + it * t_step) * AM_TILE + 16 * warp + 2 * t;
+    float s0 = abase < n_vis ? acc0[0] * sl2 : -INFINITY;
+    float s1 = abase + 1 < n_vis ? acc0[1] * sl2 : -INFINITY;
+    float s2 = abase + 8 < n_vis ? acc1[0] * sl2 : -INFINITY;
+    float s3 = abase + 9 < n_vis ? acc1[1] * sl2 : -INFINITY;
+    float tm = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
+    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 2));
+    const float mn = fmaxf(m, tm);
+    const float msafe = mn == -INFINITY ? 0.f : mn;
+    const float corr = exp2f(m - msafe);
+    const float p0 = exp2f(s0 - msafe), p1 = exp2f(s1 - msafe), p2 = exp2f(s2 - msafe), p3 = exp2f(s3 - msafe);
+    l = l * corr + ((p0 + p1) + (p2 + p3));
+    m = mn;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= corr;
+      o[j][1] *= corr;
+    }
+    const uint32_t ap[4] = {cb::pack_bf16(p0, p1), 0u, cb::pack_bf16(p2, p3), 0u};
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t bv[4];
+      cb::ldmatrix_x4_trans(bv, st + 2 * AM_MAT + am_swz(row_v, 2 * np + ch_v));
+      const uint32_t v0[2] = {bv[0], bv[1]}, v1[2] = {bv[2], bv[3]};
+      cb::mma_bf16_16816(o[2 * np], ap, v0);
+      cb::mma_bf16_16816(o[2 * np + 1], ap, v1);
+    }
+  }
+  cb::cp_async_wait<0>();
+  // quad-reduce the row sum; lanes 0..3 of each warp own row 0
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  if (g == 0) {
+    if (t == 0) {
+      sh_m[warp] = m;
+      sh_l[warp] = l;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sh_o[warp][8 * j + 2 * t] = o[j][0];
+      sh_o[warp][8 * j + 2 * t + 1] = o[j][1];
+    }
+  }
+  __syncthreads();
+  const int bh = b * H + h;
+  float mm = -INFINITY, ll = 0.f, oo = 0.f;
+  if (tid < 64) {
+#pragma unroll
+    for (int w = 0; w < AM_WARPS; ++w) mm = fmaxf(mm, sh_m[w]);
+#pragma unroll
+    for (int w = 0; w < AM_WARPS; ++w) {
+      const float c = sh_m[w] == -INFINITY ? 0.f : exp2f(sh_m[w] - mm);
+      ll += sh_l[w] * c;
+      oo += sh_o[w][tid] * c;
+    }
+  }
+  if (S > 1) {
+    float* mine = partial + ((long long)bh * S + sp) * 66;
+    if (tid < 64) {
+      mine[2 + tid] = oo;
+      if (tid == 0) {
+        mine[0] = mm;
+        mine[1] = ll;
+      }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) sh_last = (atomicAdd(counters + bh, 1) == S - 1);
+    __syncthreads();
+    if (!sh_last) return;
+    __threadfence();
+    if (tid < 64) {
+      const float* all = partial + (long long)bh * S * 66;
+      mm = -INFINITY;
+      for (int s2 = 0; s2 < S; ++s2) mm = fmaxf(mm, __ldcg(all + s2 * 66));
+      ll = 0.f;
+      oo = 0.f;
+      for (int s2 = 0; s2 < S; ++s2) {
+        const float ms = __ldcg(all + s2 * 66);
+        const float c = ms == -INFINITY ? 0.f : exp2f(ms - mm);
+        ll += __ldcg(all + s2 * 66 + 1) * c;
+        oo += __ldcg(all + s2 * 66 + 2 + tid) * c;
+      }
+    }
+    if (tid == 0) counters[bh] = 0;
+  }
+  if (tid < 64) {
+    const float r = oo / ll;
+    if (out_f32) out_f32[(long long)b * ldo + h * 64 + tid] = r;
+    if (out_bf16) out_bf16[(long long)b * ldo + h * 64 + tid] = __float2bfloat16_rn(r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stream-K, TMA-fed form of the tensor-core kernel (the product path).
+//   * persistent grid (2 CTAs per SM): the B*H*nt slot tiles of the launch are one flat list cut into equal contiguous
+//     runs, one per CTA, so every CTA streams the same bytes and the fixed costs are paid once per run; a
+//     (sequence, head) covered by several runs is merged by its last-arriving CTA (fixed order -> deterministic);
+//   * a producer warp issues, per 64-slot tile, three TMA tile loads (K, V from HBM; R from L2; 128-byte swizzle done
+//     by the copy engine) and one 256-byte bulk copy of the query row into a ring of STAGES stages guarded by
+//     full / empty mbarriers; the four consumer warps never compute an address and never meet at a CTA barrier
+//     inside a (sequence, head) (ncu of the cp.async version: 104 of 258 loop instructions were address arithmetic);
+//   * tiles are aligned to ring SLOTS (C is a multiple of 64), so a tile is one in-bounds box; the relative-position
+//     operand comes from the reversed, doubled table rt2[h][j] = R[h][C-1 - (j mod C)], 2C rows, where the tile
+//     of slots s0.. is rows j0.. with j0 = (C-1-cur+s0) mod C - contiguous even across the age wrap.
+// ---------------------------------------------------------------------------------------------
+constexpr int TK_THREADS = AM_THREADS + 32;     // 4 consumer warps + 1 producer warp
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(cb::smem_u32(bar))
+               : "memory");
+}
+
+template <int STAGES>
+__global__ void __launch_bounds__(TK_THREADS) dec_attn_tma_kernel(
+    const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+    const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ q, const float* __restrict__ u,
+    const float* __restrict__ vb, int BH, int H, int C, int n_vis, int cur_slot, float scale,
+    float* __restrict__ partial, int max_parts, int* __restrict__ counters, bf16* __restrict__ out_bf16,
+    float* __restrict__ out_f32, long long ldo, const int* __restrict__ dstate) {
+  extern __shared__ unsigned char tk_raw[];
+  __shared__ float sh_m[AM_WARPS], sh_l[AM_WARPS], sh_o[AM_WARPS][64];
+  __shared__ int sh_last;
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = (cb::smem_u32(tk_raw) + 1023u) & ~1023u;       // tiles need 1024-byte alignment (swizzle)
+  unsigned char* sgen = tk_raw + (sbase - cb::smem_u32(tk_raw));
+  float* s_q = reinterpret_cast<float*>(sgen + STAGES * AM_STAGE_BYTES);  // [STAGES][64]
+  float* s_uv = s_q + STAGES * 64;                                        // [2][H][64]
+  for (int i = tid; i < H * 64; i += TK_THREADS) {   // parameters: independent of the previous kernel
+    s_uv[i] = u[i];
+    s_uv[H * 64 + i] = vb[i];
+  }
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) {
+      cb::mbar_init(&full_bar[i], 1);
+      cb::mbar_init(&empty_bar[i], AM_WARPS);
+    }
+    cb::fence_barrier_init();
+    cb::tma_prefetch_desc(&tm_k);
+    cb::tma_prefetch_desc(&tm_v);
+    cb::tma_prefetch_desc(&tm_r);
+  }
+  pdl_wait();
+  pdl_launch();
+  __syncthreads();
+  if (dstate) {
+    cur_slot = dstate[0];
+    n_vis = dstate[1];
+  }
+  // slot tiles that hold visible keys: the n_vis newest slots (cur - n_vis, cur] of the ring
+  const int NTS = C >> 6;
+  int lo = cur_slot - n_vis + 1;
+  if (lo < 0) lo += C;
+  const int t_first = lo >> 6;
+  const int nt = min(NTS, ((lo & 63) + n_vis + 63) >> 6);
+  const long long T = (long long)BH * nt;
+  const int quota = (int)((T + gridDim.x - 1) / gridDim.x);
+  const long long T0 = (long long)blockIdx.x * quota;
+  const long long T1 = T0 + quota < T ? T0 + quota : T;
+  const int ntiles = T1 > T0 ? (int)(T1 - T0) : 0;
+  if (ntiles == 0) return;
+  int bh = (int)(T0 / nt), kt = (int)(T0 - (long long)bh * nt);
+
+  if (warp == AM_WARPS) {
+    // ===== producer =====
+    if (lane == 0) {
+      for (int it = 0; it < ntiles; ++it) {
+        const int st = it % STAGES;
+        if (it >= STAGES) cb::mbar_wait(&empty_bar[st], ((it / STAGES) & 1) ^ 1);
+        int tt = t_first + kt;
+        if (tt >= NTS) tt -= NTS;
+        const int s0 = tt << 6;
+        int j0 = C - 1 - cur_slot + s0;
+        if (j0 >= C) j0 -= C;
+        const uint32_t dst = sbase + st * AM_STAGE_BYTES;
+        cb::mbar_arrive_expect_tx(&full_bar[st], AM_STAGE_BYTES + 256);
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+                     "l"(reinterpret_cast<uint64_t>(&tm_k)), "r"(cb::smem_u32(&full_bar[st])), "r"(0), "r"(bh * C + s0) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst + AM_MAT),
+                     "l"(reinterpret_cast<uint64_t>(&tm_r)), "r"(cb::smem_u32(&full_bar[st])), "r"(0), "r"((bh % H) * 2 * C + j0) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst + 2 * AM_MAT),
+                     "l"(reinterpret_cast<uint64_t>(&tm_v)), "r"(cb::smem_u32(&full_bar[st])), "r"(0), "r"(bh * C + s0) : "memory");
+        bulk_load_1d(cb::smem_u32(s_q + st * 64), q + (long long)bh * 64, 256, &full_bar[st]);
+        if (++kt == nt) {
+          kt = 0;
+          ++bh;
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int g = lane >> 2, t = lane & 3;
+  bool fresh = true;
+  uint32_t aqu[4][2], aqv[4][2];
+  float m = -INFINITY, l = 0.f;
+  float o[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
+  const float sl2 = scale * 1.4426950408889634f;
+  const int row_b = 16 * warp + (lane & 7) + (lane >> 4) * 8, ch_b = (lane >> 3) & 1;
+  const int row_v = 16 * warp + (lane & 7) + ((lane >> 3) & 1) * 8, ch_v = lane >> 4;
+
+  for (int it = 0; it < ntiles; ++it) {
+    const int stg = it % STAGES;
+    cb::mbar_wait(&full_bar[stg], (it / STAGES) & 1);
+    const uint32_t st = sbase + stg * AM_STAGE_BYTES;
+    if (fresh) {   // first tile of a (sequence, head) in this run: query fragments (row 0 of the A operand)
+      const float* qp = s_q + stg * 64;
+      const float* up = s_uv + (bh % H) * 64;
+      const float* vp = up + H * 64;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int c = 16 * ks + 8 * hf + 2 * t;
+          const float q0 = qp[c], q1 = qp[c + 1];
+          aqu[ks][hf] = g == 0 ? cb::pack_bf16(q0 + up[c], q1 + up[c + 1]) : 0u;
+          aqv[ks][hf] = g == 0 ? cb::pack_bf16(q0 + vp[c], q1 + vp[c + 1]) : 0u;
+        }
+      }
+      fresh = false;
+    }
+    // 16 independent MMAs (the dependent-accumulate latency of the warp-level tensor path is what bounds a warp's
+    // tile time), summed afterwards; only elements 0 / 1 (row 0) of an accumulator are meaningful
+    float pk0[4][4], pk1[4][4], pr0[4][4], pr1[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t bk[4], br[4];
+      cb::ldmatrix_x4(bk, st + am_swz(row_b, 2 * ks + ch_b));
+      cb::ldmatrix_x4(br, st + AM_MAT + am_swz(row_b, 2 * ks + ch_b));
+      const uint32_t au[4] = {aqu[ks][0], 0u, aqu[ks][1], 0u}, av[4] = {aqv[ks][0], 0u, aqv[ks][1], 0u};
+      const uint32_t k0[2] = {bk[0], bk[1]}, k1[2] = {bk[2], bk[3]}, r0[2] = {br[0], br[1]}, r1[2] = {br[2], br[3]};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) pk0[ks][e] = pk1[ks][e] = pr0[ks][e] = pr1[ks][e] = 0.f;
+      cb::mma_bf16_16816(pk0[ks], au, k0);
+      cb::mma_bf16_16816(pk1[ks], au, k1);
+      cb::mma_bf16_16816(pr0[ks], av, r0);
+      cb::mma_bf16_16816(pr1[ks], av, r1);
+    }
+    uint32_t bvv[4][4];     // V operand fragments: independent of the softmax, fetched while the score MMAs drain
+#pragma unroll
+    for (int np = 0; np < 4; ++np) cb::ldmatrix_x4_trans(bvv[np], st + 2 * AM_MAT + am_swz(row_v, 2 * np + ch_v));
+    float acc0[2], acc1[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      acc0[e] = ((pk0[0][e] + pr0[0][e]) + (pk0[1][e] + pr0[1][e])) + ((pk0[2][e] + pr0[2][e]) + (pk0[3][e] + pr0[3][e]));
+      acc1[e] = ((pk1[0][e] + pr1[0][e]) + (pk1[1][e] + pr1[1][e])) + ((pk1[2][e] + pr1[2][e]) + (pk1[3][e] + pr1[3][e]));
+    }
+    // row 0 of the score tile: this lane holds slots s0 + 16*warp + {2t, 2t+1, 8+2t, 9+2t}; age = (cur - slot) mod C
+    int tt = t_first + kt;
+    if (tt >= NTS) tt -= NTS;
+    int age0 = cur_slot - ((tt << 6) + 16 * warp + 2 * t);    // ages of the four keys: age0, age0-1, age0-8, age0-9 (mod C)
+    auto vis = [&](int a) { return (a < 0 ? a + C : a) < n_vis; };
+    const float s0 = vis(age0) ? acc0[0] * sl2 : -INFINITY;
+    const float s1 = vis(age0 - 1) ? acc0[1] * sl2 : -INFINITY;
+    const float s2 = vis(age0 - 8) ? acc1[0] * sl2 : -INFINITY;
+    const float s3 = vis(age0 - 9) ? acc1[1] * sl2 : -INFINITY;
+    float tm = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
+    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 2));
+    const float mn = fmaxf(m, tm);
+    const float msafe = mn == -INFINITY ? 0.f : mn;
+    const float corr = exp2f(m - msafe);
+    const float p0 = exp2f(s0 - msafe), p1 = exp2f(s1 - msafe), p2 = exp2f(s2 - msafe), p3 = exp2f(s3 - msafe);
+    l = l * corr + ((p0 + p1) + (p2 + p3));
+    m = mn;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j][0] *= corr;
+      o[j][1] *= corr;
+    }
+    const uint32_t ap[4] = {cb::pack_bf16(p0, p1), 0u, cb::pack_bf16(p2, p3), 0u};
+    __syncwarp();
+    if (lane == 0) cb::mbar_arrive(&empty_bar[stg]);      // every operand of this stage is in registers
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      const uint32_t v0[2] = {bvv[np][0], bvv[np][1]}, v1[2] = {bvv[np][2], bvv[np][3]};
+      cb::mma_bf16_16816(o[2 * np], ap, v0);
+      cb::mma_bf16_16816(o[2 * np + 1], ap, v1);
+    }
+    // ---- end of this run's share of the (sequence, head): publish ----
+    if (kt == nt - 1 || it == ntiles - 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");    // the previous publication has been read
+      if (g == 0) {
+        if (t == 0) {
+          sh_m[warp] = m;
+          sh_l[warp] = l;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sh_o[warp][8 * j + 2 * t] = o[j][0];
+          sh_o[warp][8 * j + 2 * t + 1] = o[j][1];
+        }
+      }
+      asm volatile("bar.sync 1, 128;\n" ::: "memory");
+      float mm = -INFINITY, ll = 0.f, oo = 0.f;
+      if (tid < 64) {
+#pragma unroll
+        for (int w = 0; w < AM_WARPS; ++w) mm = fmaxf(mm, sh_m[w]);
+#pragma unroll
+        for (int w = 0; w < AM_WARPS; ++w) {
+          const float c = sh_m[w] == -INFINITY ? 0.f : exp2f(sh_m[w] - mm);
+          ll += sh_l[w] * c;
+          oo += sh_o[w][tid] * c;
+        }
+      }
+      // runs covering this (sequence, head): CTAs first .. last
+      const int first = (int)(((long long)bh * nt) / quota), last = (int)(((long long)(bh + 1) * nt - 1) / quota);
+      const int parts = last - first + 1;
+      bool write = true;
+      if (parts > 1) {
+        float* mine = partial + ((long long)bh * max_parts + ((int)blockIdx.x - first)) * 66;
+        if (tid < 64) {
+          mine[2 + tid] = oo;
+          if (tid == 0) {
+            mine[0] = mm;
+            mine[1] = ll;
+          }
+        }
+        __threadfence();
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        if (tid == 0) sh_last = (atomicAdd(counters + bh, 1) == parts - 1);
+        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        write = sh_last != 0;
+        if (write) {
+          __threadfence();
+          if (tid < 64) {
+            const float* all = partial + (long long)bh * max_parts * 66;
+            mm = -INFINITY;
+            for (int s2 = 0; s2 < parts; ++s2) mm = fmaxf(mm, __ldcg(all + s2 * 66));
+            ll = 0.f;
+            oo = 0.f;
+            for (int s2 = 0; s2 < parts; ++s2) {
+              const float ms = __ldcg(all + s2 * 66);
+              const float c = ms == -INFINITY ? 0.f : exp2f(ms - mm);
+              ll += __ldcg(all + s2 * 66 + 1) * c;
+              oo += __ldcg(all + s2 * 66 + 2 + tid) * c;
+            }
+          }
+          if (tid == 0) counters[bh] = 0;
+        }
+      }
+      if (write && tid < 64) {
+        const float r = oo / ll;
+        const long long off = (long long)(bh / H) * ldo + (bh % H) * 64 + tid;
+        if (out_f32) out_f32[off] = r;
+        if (out_bf16) out_bf16[off] = __float2bfloat16_rn(r);
+      }
+      m = -INFINITY;
+      l = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = 0.f;
+      fresh = true;
+    }
+    if (++kt == nt) {
+      kt = 0;
+      ++bh;
+    }
+  }
+}
+
+// tensor maps of the decode caches are encoded once per (pointer, rows) and reused
+struct TmapSlot { const void* ptr; uint64_t rows; CUtensorMap map; };
+static TmapSlot g_tmaps[256];
+static int g_ntmaps = 0;
+int cached_tmap(const void* ptr, uint64_t rows, const CUtensorMap** out) {
+  for (int i = 0; i < g_ntmaps; ++i)
+    if (g_tmaps[i].ptr == ptr && g_tmaps[i].rows == rows) {
+      *out = &g_tmaps[i].map;
+      return 0;
+    }
+  TmapSlot& s = g_tmaps[g_ntmaps < 256 ? g_ntmaps : 255];
+  const int rc = cb_host::make_tmap_bf16_2d(&s.map, ptr, 64, rows, 64, 64, 64);
+  if (rc) return rc;
+  s.ptr = ptr;
+  s.rows = rows;
+  if (g_ntmaps < 256) ++g_ntmaps;
+  *out = &s.map;
+  return 0;
+}
+
 template <int PRO, int EPI, bool CLUSTER>
 int launch_linear(const LinP& p, int grid_x, int split, size_t smem, int pdl, cudaStream_t s) {
   auto kern = dec_linear_kernel<PRO, EPI, CLUSTER>;
@@ -528,9 +1085,9 @@ int commu_decode_fused_linear(const CommuDecLinear* a, void* stream) {
 int commu_decode_attn_split(const float* q, const void* kcache, const void* vcache, const void* rtab,
                             const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
                             float scale, int splits, float* partial, int* counters, void* out_bf16, float* out_f32,
-                            int64_t ldo, const int* dev_state, int pdl, void* stream) {
+                            int64_t ldo, const int* dev_state, int pdl, int impl, void* stream) {
   CB_REQUIRE(q && kcache && vcache && rtab && (out_bf16 || out_f32), "decode_attn_split: null arg");
-  CB_REQUIRE(splits >= 1 && splits <= 16 && (splits == 1 || (partial && counters)),
+  CB_REQUIRE(splits >= 1 && splits <= 16 && ((splits == 1 && !(impl & 8)) || (partial && counters)),
              "decode_attn_split: splits=%d needs partial / counters scratch", splits);
   CB_REQUIRE(dev_state || (n_vis >= 1 && n_vis <= C && cur_slot >= 0 && cur_slot < C),
              "decode_attn_split: bad args (n_vis=%d C=%d slot=%d)", n_vis, C, cur_slot);
@@ -546,6 +1103,61 @@ int commu_decode_attn_split(const float* q, const void* kcache, const void* vcac
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = pdl ? 1 : 0;
+  if (impl & 8) {    // stream-K TMA kernel (product path): `splits` = CTAs per SM, partial = [B*H][C/64][66]
+    CB_REQUIRE(C % 64 == 0, "decode_attn_split: the TMA kernel needs a ring capacity that is a multiple of 64 (C=%d)", C);
+    static int configured_h = 0;
+    const int stages = (impl & 2) ? 3 : 4;
+    const int smem = 1024 + stages * (AM_STAGE_BYTES + 256) + 2 * H * 64 * 4;
+    if (H > configured_h) {
+      const int big = 1024 + 4 * (AM_STAGE_BYTES + 256) + 2 * H * 64 * 4;
+      CB_REQUIRE(big <= 227 * 1024, "decode_attn_split: too many heads (%d) for the shared-memory parameter block", H);
+      CB_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+      CB_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+      configured_h = H;
+    }
+    const CUtensorMap *tk, *tv, *tr;
+    int rc = cached_tmap(kcache, (uint64_t)B * H * C, &tk);
+    if (rc) return rc;
+    if ((rc = cached_tmap(vcache, (uint64_t)B * H * C, &tv))) return rc;
+    if ((rc = cached_tmap(rtab, (uint64_t)H * 2 * C, &tr))) return rc;
+    const int max_parts = C / AM_TILE;
+    cfg.gridDim = dim3(splits * cb_host::num_sms(), 1, 1);
+    cfg.blockDim = dim3(TK_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    if (stages == 3)
+      CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_attn_tma_kernel<3>, *tk, *tv, *tr, q, r_w_bias, r_r_bias, B * H, H, C, n_vis,
+                                       cur_slot, scale, partial, max_parts, counters, (bf16*)out_bf16, out_f32,
+                                       (long long)ldo, dev_state));
+    else
+      CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_attn_tma_kernel<4>, *tk, *tv, *tr, q, r_w_bias, r_r_bias, B * H, H, C, n_vis,
+                                       cur_slot, scale, partial, max_parts, counters, (bf16*)out_bf16, out_f32,
+                                       (long long)ldo, dev_state));
+    cb_host::count_launch();
+    return 0;
+  }
+  if (impl >= 1) {   // tensor-core kernel: rtab is laid out [H][C][64]; impl bits: 2 = 3-stage ring, 4 = blocked tiles
+    static bool configured = false;
+    if (!configured) {
+      CB_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * AM_STAGE_BYTES));
+      CB_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * AM_STAGE_BYTES));
+      configured = true;
+    }
+    const int stages = (impl & 2) ? 3 : 4;
+    const int cyclic = (impl & 4) ? 0 : 1;
+    cfg.gridDim = dim3(splits, H, B);
+    cfg.blockDim = dim3(AM_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = stages * AM_STAGE_BYTES;
+    if (stages == 3)
+      CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_attn_mma_kernel<3>, q, (const bf16*)kcache, (const bf16*)vcache,
+                                       (const bf16*)rtab, r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, partial,
+                                       counters, (bf16*)out_bf16, out_f32, (long long)ldo, dev_state, cyclic, (impl >> 4) & 3));
+    else
+      CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_attn_mma_kernel<4>, q, (const bf16*)kcache, (const bf16*)vcache,
+                                       (const bf16*)rtab, r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, partial,
+                                       counters, (bf16*)out_bf16, out_f32, (long long)ldo, dev_state, cyclic, (impl >> 4) & 3));
+    cb_host::count_launch();
+    return 0;
+  }
   CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_attn_split_kernel, q, (const bf16*)kcache, (const bf16*)vcache,
                                    (const bf16*)rtab, r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, partial, counters,
                                    (bf16*)out_bf16, out_f32, (long long)ldo, dev_state));

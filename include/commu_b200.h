@@ -296,11 +296,13 @@ typedef struct {
 int commu_decode_fused_linear(const CommuDecLinear* args, void* stream);
 /* commu_decode_attn over a bf16 cache with the visible keys of every (sequence, head) split over `splits` CTAs
  * (grid H x B x splits, sized for ~7 resident CTAs per SM); partial: fp32 [B*H*splits*66] scratch, counters:
- * int32 [B*H] zero-initialised once (the last-arriving CTA merges the partials in split order and re-zeroes). */
+ * int32 [B*H] zero-initialised once (the last-arriving CTA merges the partials in split order and re-zeroes).
+ * impl 0: SIMT kernel, rtab [C,H,64].  impl 1 (product path): warp-level tensor-core MMAs fed by a 4-stage
+ * cp.async ring of 64-key K / V / R tiles, rtab laid out [H,C,64]. */
 int commu_decode_attn_split(const float* q, const void* kcache, const void* vcache, const void* rtab,
                             const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
                             float scale, int splits, float* partial, int* counters, void* out_bf16, float* out_f32,
-                            int64_t ldo, const int* dev_state, int pdl, void* stream);
+                            int64_t ldo, const int* dev_state, int pdl, int impl, void* stream);
 /* Sampler over B rows of raw logits (token 0 is never sampled, midi_inferrer.py:206/:220): temperature
  * (0 = greedy one-hot, :211-213), top-k (:224-226), top-p (new), wrong-token mask (:227-229),
  * renormalise (:230-231), counter-based multinomial draw (:234-237).  tokens and/or probs_out. */

@@ -66,7 +66,10 @@ def test_decode_bf16_logits_close():
 
 @pytest.mark.parametrize("env", [dict(COMMU_DECODE_FUSED="0"),
                                  dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_PDL="0", COMMU_DECODE_SPLITS="1"),
-                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_PDL="1", COMMU_DECODE_SPLITS="3")])
+                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_PDL="1", COMMU_DECODE_SPLITS="3"),
+                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="0", COMMU_DECODE_SPLITS="2"),
+                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="1", COMMU_DECODE_SPLITS="2"),
+                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="10", COMMU_DECODE_SPLITS="1")])
 def test_decode_bf16_paths_close_to_golden(env, monkeypatch):
     """Every bf16 decode path (tcgen05-GEMM step, fused step with / without programmatic dependent launch and key
     splits) stays within the bf16 tolerance of the fp32 reference logits (Dh = 16 < 64: padded head layout)."""
@@ -110,7 +113,6 @@ def test_decode_fused_step_matches_unfused(shape, monkeypatch):
     ref = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision="bf16")
     f32 = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision="fp32")
     monkeypatch.setenv("COMMU_DECODE_FUSED", "1")
-    monkeypatch.setenv("COMMU_DECODE_SPLITS", "2")
     fus = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision="bf16")
     assert fus.fused and not ref.fused
     g = torch.Generator().manual_seed(1)
