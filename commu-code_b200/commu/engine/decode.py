@@ -55,7 +55,7 @@ class DecodeEngine:
         # 0 = SIMT kernel
         self.fused = (self.bf16 and self.d <= 1024 and os.environ.get("COMMU_DECODE_FUSED", "1") != "0")
         self.attn_impl = int(os.environ.get("COMMU_DECODE_ATTN", "8"))
-        if self.fused and self.attn_impl & 8:
+        if self.fused and self.attn_impl & 72:
             self.C = (self.mem_len + 1 + 63) // 64 * 64
         H, Dh, d, C, B = self.H, self.Dh, self.d, self.C, self.B
         sd = {n: p for n, p in m.named_parameters()}
@@ -119,8 +119,8 @@ class DecodeEngine:
         r16 = lambda n: (n + 15) // 16 * 16
         dp, dip, hd = r64(d), r64(Di), H * 64
         self.pdl = int(os.environ.get("COMMU_DECODE_PDL", "1") != "0")
-        self.splits = int(os.environ.get("COMMU_DECODE_SPLITS", "0")) or (2 if self.attn_impl & 8 else self._pick_splits())
-        if self.attn_impl & 8:
+        self.splits = int(os.environ.get("COMMU_DECODE_SPLITS", "0")) or (2 if self.attn_impl & 72 else self._pick_splits())
+        if self.attn_impl & 72:
             # reversed, doubled table per head [H, 2C, 64]: row j = R[C-1 - (j mod C)], so the 64 slots of a ring tile
             # are 64 consecutive rows even where the ages wrap (one TMA box)
             self.rt_h = [torch.cat([r.flip(0).permute(1, 0, 2)] * 2, dim=1).contiguous() for r in self.rt]
@@ -141,7 +141,7 @@ class DecodeEngine:
         zb = lambda *s: torch.zeros(*s, device=dev, dtype=bf)
         zf = lambda *s: torch.zeros(*s, device=dev)
         ws = self.wsf = dict(x=zf(B, d), y=zf(B, d), z1=zf(B, d), z2=zf(B, d), q=zf(B, H, 64), att=zb(B, hd),
-                             h=zb(B, dip), part=zf(B * H * max(self.splits, (C + 63) // 64) * 66),
+                             h=zb(B, dip), part=zf(B * H * max(self.splits, (C + 15) // 16) * 66),
                              cnt=torch.zeros(B * H, dtype=torch.int32, device=dev))
         self.tok_buf = torch.zeros(B, dtype=torch.int64, device=dev)   # placeholder; step() points at its tokens
         self.fw, self.fargs = [], []

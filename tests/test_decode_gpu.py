@@ -69,7 +69,9 @@ def test_decode_bf16_logits_close():
                                  dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_PDL="1", COMMU_DECODE_SPLITS="3"),
                                  dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="0", COMMU_DECODE_SPLITS="2"),
                                  dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="1", COMMU_DECODE_SPLITS="2"),
-                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="10", COMMU_DECODE_SPLITS="1")])
+                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="10", COMMU_DECODE_SPLITS="1"),
+                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="64", COMMU_DECODE_SPLITS="2"),
+                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="576", COMMU_DECODE_SPLITS="1")])
 def test_decode_bf16_paths_close_to_golden(env, monkeypatch):
     """Every bf16 decode path (tcgen05-GEMM step, fused step with / without programmatic dependent launch and key
     splits) stays within the bf16 tolerance of the fp32 reference logits (Dh = 16 < 64: padded head layout)."""
@@ -99,10 +101,11 @@ def _bench_like_model(L=2, H=8, d=512, Di=2048, V=729, mem_len=300, seed=3):
     return m.cuda().eval()
 
 
+@pytest.mark.parametrize("attn", ["8", "64", "320"])
 @pytest.mark.parametrize("shape", [dict(H=8, d=512, Di=2048, B=64, mem_len=300),     # bench shape, ring wraps
                                    dict(H=10, d=500, Di=1000, B=5, mem_len=200),     # checkpoint shape: Dh = 50, d % 64 != 0
                                    dict(H=16, d=1024, Di=4096, B=33, mem_len=130)])   # widest supported rows
-def test_decode_fused_step_matches_unfused(shape, monkeypatch):
+def test_decode_fused_step_matches_unfused(shape, attn, monkeypatch):
     """Fused token-step kernels (csrc/decode_fused.cu) vs the kernel-per-op bf16 step on identical tokens: same
     bf16 operands and fp32 accumulation, so the logits agree to accumulation-order noise, for mem_len + 40 steps
     (the ring cache wraps), and vs the fp32 engine within the bf16 tolerance."""
@@ -113,6 +116,7 @@ def test_decode_fused_step_matches_unfused(shape, monkeypatch):
     ref = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision="bf16")
     f32 = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision="fp32")
     monkeypatch.setenv("COMMU_DECODE_FUSED", "1")
+    monkeypatch.setenv("COMMU_DECODE_ATTN", attn)
     fus = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision="bf16")
     assert fus.fused and not ref.fused
     g = torch.Generator().manual_seed(1)
