@@ -49,6 +49,16 @@ def peaks():
     return dict(bf16=1400.0, bf16_burst=1590.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel class, from the committed `ncu --set full`
+    capture (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep); None when not captured."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel, {}).get("bytes_per_launch")
+    except (OSError, ValueError):
+        return None
+
+
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -231,7 +241,7 @@ def run_native(args):
             dur = prof[dom]["ms"] / prof[dom]["launches"] / 1e3
             ach = fl / dur / 1e12
             roof = dict(kernel=dom, bound="tensor", achieved=round(ach, 2), peak=pk["bf16"], unit="TFLOP/s",
-                        frac=round(ach / pk["bf16"], 4), traffic=None, peak_source=pk["source"],
+                        frac=round(ach / pk["bf16"], 4), traffic=ncu_traffic(dom), peak_source=pk["source"],
                         flops_per_launch=fl, avg_launch_ms=round(dur * 1e3, 4))
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": K,
@@ -316,17 +326,42 @@ def decode_bench(model, dev, pk, n_new=256, batch=64, mem_len=2048, precision="b
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    # per-kernel timing of the decode attention (events cannot live inside a graph): eager steps
-    lib.commu_prof_arm(0b1000)
-    for t in range(8):
-        one_step()
-    torch.cuda.synchronize()
-    pms, pn = ctypes.c_float(0), ctypes.c_int(0)
-    nv.check(lib.commu_prof_read(3, ctypes.byref(pms), ctypes.byref(pn)))
+    # duration of the decode-attention kernel: the 12 layers' launches captured alone in a CUDA graph (each layer streams
+    # its own 268 MB cache, far above the 126 MB L2) and replayed back to back with events around the replays, so the
+    # per-launch figure carries the same launch gaps as the real step and no host-side launch latency
     lib.commu_prof_arm(0)
+    pms, pn = ctypes.c_float(0), ctypes.c_int(0)
+    if getattr(eng, "fused", False):
+        def attn_chain():
+            for l in range(eng.L):
+                eng._attn_fused(l, 0, 1, dstate)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            attn_chain()
+        torch.cuda.current_stream().wait_stream(side)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2):
+            attn_chain()
+        for _ in range(3):
+            g2.replay()
+        torch.cuda.synchronize()
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            g2.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        pms.value, pn.value = e0.elapsed_time(e1), reps * eng.L
+    else:       # kernel-per-op engines: events around every launch of eager steps
+        lib.commu_prof_arm(0b1000)
+        for t in range(8):
+            one_step()
+        torch.cuda.synchronize()
+        nv.check(lib.commu_prof_read(3, ctypes.byref(pms), ctypes.byref(pn)))
+        lib.commu_prof_arm(0)
     esz = 2 if precision == "bf16" else 4
     L, H, d = CFG["n_layer"], CFG["n_head"], CFG["d_model"]
-    attn_bytes = batch * H * mem_len * 64 * esz * 2 + H * mem_len * 64 * esz     # K + V per sequence, R once
+    attn_bytes = batch * H * mem_len * 64 * esz * 2 + H * mem_len * 64 * esz     # K + V per sequence, R once (8d)
     step_bytes = L * attn_bytes + 41.3e6 * esz
     res = {"tokens_per_s_per_seq": round(n_new / (ms / 1e3), 1), "batch": batch, "new_tokens": n_new,
            "ms_per_token_step": round(ms / n_new, 4), "precision": precision, "sampler": "top_p=0.9 T=0.95",
@@ -336,7 +371,7 @@ def decode_bench(model, dev, pk, n_new=256, batch=64, mem_len=2048, precision="b
         dur = pms.value / pn.value / 1e3
         res["roofline"] = {"kernel": "decode_attn", "bound": "hbm", "achieved": round(attn_bytes / dur / 1e9, 1),
                            "peak": pk["hbm"], "unit": "GB/s", "frac": round(attn_bytes / dur / 1e9 / pk["hbm"], 4),
-                           "traffic": None, "avg_launch_ms": round(dur * 1e3, 4)}
+                           "traffic": ncu_traffic("decode_attn"), "avg_launch_ms": round(dur * 1e3, 4)}
     return res
 
 

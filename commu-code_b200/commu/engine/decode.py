@@ -51,11 +51,10 @@ class DecodeEngine:
         cdt = torch.bfloat16 if self.bf16 else torch.float32
         # bf16 throughput mode runs the fused token-step kernels (csrc/decode_fused.cu): 5 launches per layer.
         # attention kernel: 8 = stream-K TMA tensor-core kernel (persistent grid, `splits` CTAs per SM; ring capacity
-        # rounded up to a multiple of 64 slots), 1 = tensor-core kernel with one CTA per (sequence, head, split),
-        # 0 = SIMT kernel
+        # rounded up to a multiple of 64 slots; +2 = 3-stage ring), 0 = SIMT cross-check kernel (`splits` key splits)
         self.fused = (self.bf16 and self.d <= 1024 and os.environ.get("COMMU_DECODE_FUSED", "1") != "0")
         self.attn_impl = int(os.environ.get("COMMU_DECODE_ATTN", "8"))
-        if self.fused and self.attn_impl & 72:
+        if self.fused and self.attn_impl & 8:
             self.C = (self.mem_len + 1 + 63) // 64 * 64
         H, Dh, d, C, B = self.H, self.Dh, self.d, self.C, self.B
         sd = {n: p for n, p in m.named_parameters()}
@@ -119,14 +118,11 @@ class DecodeEngine:
         r16 = lambda n: (n + 15) // 16 * 16
         dp, dip, hd = r64(d), r64(Di), H * 64
         self.pdl = int(os.environ.get("COMMU_DECODE_PDL", "1") != "0")
-        self.splits = int(os.environ.get("COMMU_DECODE_SPLITS", "0")) or (2 if self.attn_impl & 72 else self._pick_splits())
-        if self.attn_impl & 72:
+        self.splits = int(os.environ.get("COMMU_DECODE_SPLITS", "0")) or (2 if self.attn_impl & 8 else self._pick_splits())
+        if self.attn_impl & 8:
             # reversed, doubled table per head [H, 2C, 64]: row j = R[C-1 - (j mod C)], so the 64 slots of a ring tile
             # are 64 consecutive rows even where the ages wrap (one TMA box)
             self.rt_h = [torch.cat([r.flip(0).permute(1, 0, 2)] * 2, dim=1).contiguous() for r in self.rt]
-        elif self.attn_impl >= 1:
-            # R by distance per head [H, C, 64]: a 64-distance tile of one head is contiguous for the async copies
-            self.rt_h = [r.permute(1, 0, 2).contiguous() for r in self.rt]
         else:
             self.rt_h = self.rt
         ks = None
@@ -141,7 +137,7 @@ class DecodeEngine:
         zb = lambda *s: torch.zeros(*s, device=dev, dtype=bf)
         zf = lambda *s: torch.zeros(*s, device=dev)
         ws = self.wsf = dict(x=zf(B, d), y=zf(B, d), z1=zf(B, d), z2=zf(B, d), q=zf(B, H, 64), att=zb(B, hd),
-                             h=zb(B, dip), part=zf(B * H * max(self.splits, (C + 15) // 16) * 66),
+                             h=zb(B, dip), part=zf(B * H * max(self.splits, (C + 63) // 64) * 66),
                              cnt=torch.zeros(B * H, dtype=torch.int32, device=dev))
         self.tok_buf = torch.zeros(B, dtype=torch.int64, device=dev)   # placeholder; step() points at its tokens
         self.fw, self.fargs = [], []
@@ -189,11 +185,10 @@ class DecodeEngine:
                            out_f32=self.ws["logits"], ldo=V, **dict(B=B, pdl=self.pdl, split_k=1))
 
     def _pick_splits(self):
-        """Key splits of the decode attention: B*H*splits CTAs should fill the SMs' resident slots (2 CTAs of the
-        tensor-core kernel, 3 of the SIMT kernel per SM) a near-integer number of times, with enough CTAs to even
-        out the tail."""
+        """Key splits of the SIMT decode attention: B*H*splits CTAs should fill the SMs' resident slots (3 CTAs per
+        SM) a near-integer number of times, with enough CTAs to even out the tail."""
         sms = torch.cuda.get_device_properties(self.dev).multi_processor_count if self.dev.type == "cuda" else 148
-        slots, work = (2 if self.attn_impl >= 1 else 3) * sms, self.B * self.H
+        slots, work = 3 * sms, self.B * self.H
         best, best_eff = 1, 0.0
         for s in range(1, 17):
             if self.mem_len // s < 128:
@@ -204,6 +199,13 @@ class DecodeEngine:
                 best, best_eff = s, eff
         return best
 
+    def _attn_fused(self, l, slot, n_vis, dstate):
+        """Layer l's single-query attention over its ring cache (q staged by the qkv launch) -> bf16 rows for o_net."""
+        ws = self.wsf
+        nv.call("commu_decode_attn_split", ws["q"], self.kc[l], self.vc[l], self.rt_h[l], self.u, self.vb, self.B, self.H,
+                self.C, n_vis, slot, self.scale, self.splits, ws["part"], ws["cnt"], ws["att"], None, self.H * 64, dstate,
+                self.pdl, self.attn_impl)
+
     def _step_fused(self, tokens, slot, n_vis, dstate):
         B, H, C = self.B, self.H, self.C
         ws = self.wsf
@@ -211,24 +213,11 @@ class DecodeEngine:
             raise RuntimeError("commu_b200 decode: tokens must be a contiguous int64 [B] device tensor")
         self.fargs[0][0].tokens = tokens.data_ptr()
         dptr = dstate.data_ptr() if dstate is not None else None
-        skip = os.environ.get("COMMU_DECODE_SKIP", "")     # timing experiments only (results are garbage)
         for l in range(self.L):
             a_qkv, a_o, a_f1, a_f2 = self.fargs[l]
             a_qkv.slot, a_qkv.dev_state = slot, dptr
-            if skip == "lin":
-                nv.call("commu_decode_attn_split", ws["q"], self.kc[l], self.vc[l], self.rt_h[l], self.u, self.vb, B, H, C,
-                        n_vis, slot, self.scale, self.splits, ws["part"], ws["cnt"], ws["att"], None, H * 64, dstate,
-                        self.pdl, self.attn_impl)
-                continue
             nv.dec_linear(a_qkv)
-            if skip == "attn":
-                nv.dec_linear(a_o)
-                nv.dec_linear(a_f1)
-                nv.dec_linear(a_f2)
-                continue
-            nv.call("commu_decode_attn_split", ws["q"], self.kc[l], self.vc[l], self.rt_h[l], self.u, self.vb, B, H, C,
-                    n_vis, slot, self.scale, self.splits, ws["part"], ws["cnt"], ws["att"], None, H * 64, dstate,
-                    self.pdl, self.attn_impl)
+            self._attn_fused(l, slot, n_vis, dstate)
             nv.dec_linear(a_o)
             nv.dec_linear(a_f1)
             nv.dec_linear(a_f2)

@@ -58,109 +58,6 @@ struct LinP {
   float* q_out; bf16* k_cache; bf16* v_cache; int H, C, slot; const int* dstate;
 };
 
-// Embedding / LayerNorm prologue: each warp owns 8 of the 64 rows and keeps RG of them in flight (all loads
-// issued before the first reduction); a lane holds columns 4*(lane + 32*i) .. +3, i < MAXV.
-template <int PRO, int MAXV, int RG>
-__device__ __forceinline__ void prologue_rows(const LinP& p, bf16* sA, int lds, int warp, int lane) {
-  const int d = p.d_true, KC = p.KC;
-  float4 gm[MAXV], bt[MAXV];
-  if (PRO == PRO_LN) {
-#pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      const int c = 4 * (lane + 32 * i);
-      gm[i] = bt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c < d) {
-        gm[i] = *reinterpret_cast<const float4*>(p.gamma + c);
-        bt[i] = *reinterpret_cast<const float4*>(p.beta + c);
-      }
-    }
-  }
-  for (int r0 = warp * 8; r0 < warp * 8 + 8; r0 += RG) {
-    float4 v[RG][MAXV];
-    float s[RG];
-#pragma unroll
-    for (int j = 0; j < RG; ++j) {
-      const int r = r0 + j;
-      const float* src = nullptr;
-      if (r < p.B) src = PRO == PRO_EMBED ? p.emb + p.tokens[r] * (long long)d : p.z + (long long)r * p.ldz;
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int c = 4 * (lane + 32 * i);
-        v[j][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (src && c < d) v[j][i] = *reinterpret_cast<const float4*>(src + c);
-      }
-    }
-    if (PRO == PRO_EMBED) {
-#pragma unroll
-      for (int j = 0; j < RG; ++j)
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-          v[j][i].x *= p.emb_scale; v[j][i].y *= p.emb_scale; v[j][i].z *= p.emb_scale; v[j][i].w *= p.emb_scale;
-        }
-    } else {
-#pragma unroll
-      for (int j = 0; j < RG; ++j) {
-        s[j] = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) s[j] += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int j = 0; j < RG; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-      float mean[RG];
-#pragma unroll
-      for (int j = 0; j < RG; ++j) {
-        mean[j] = s[j] / (float)d;
-        s[j] = 0.f;
-#pragma unroll
-        for (int i = 0; i < MAXV; ++i) {
-          if (4 * (lane + 32 * i) < d) {
-            const float a0 = v[j][i].x - mean[j], a1 = v[j][i].y - mean[j], a2 = v[j][i].z - mean[j], a3 = v[j][i].w - mean[j];
-            s[j] += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-        for (int j = 0; j < RG; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int c = 4 * (lane + 32 * i);
-        if (c < d) {
-#pragma unroll
-          for (int j = 0; j < RG; ++j) {
-            if (r0 + j < p.B) {
-              const float rstd = rsqrtf(s[j] / (float)d + p.eps);
-              v[j][i].x = (v[j][i].x - mean[j]) * rstd * gm[i].x + bt[i].x;
-              v[j][i].y = (v[j][i].y - mean[j]) * rstd * gm[i].y + bt[i].y;
-              v[j][i].z = (v[j][i].z - mean[j]) * rstd * gm[i].z + bt[i].z;
-              v[j][i].w = (v[j][i].w - mean[j]) * rstd * gm[i].w + bt[i].w;
-            }
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < RG; ++j) {
-      const int r = r0 + j;
-      const bool writer = p.x_out && r < p.B && (r % (int)gridDim.x) == (int)blockIdx.x;
-#pragma unroll
-      for (int i = 0; i < MAXV; ++i) {
-        const int c = 4 * (lane + 32 * i);
-        if (c < KC) {
-          uint2 pk;
-          pk.x = cb::pack_bf16(v[j][i].x, v[j][i].y);
-          pk.y = cb::pack_bf16(v[j][i].z, v[j][i].w);
-          *reinterpret_cast<uint2*>(sA + r * lds + c) = pk;
-        }
-        if (writer && c < d) *reinterpret_cast<float4*>(p.x_out + (long long)r * p.ldx + c) = v[j][i];
-      }
-    }
-  }
-}
-
 // Embedding / LayerNorm prologue shared by a cluster of PCL = 8 CTAs (8 neighbouring column slices): CTA `rank`
 // normalises rows 8*rank .. 8*rank+7 (one row per warp) and stores the bf16 row into the A tile of every CTA of the
 // cluster through distributed shared memory, so the 64 x d LayerNorm is computed once per cluster instead of once
@@ -552,222 +449,13 @@ __global__ void __launch_bounds__(DA2_WARPS * 32, 3) dec_attn_split_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------
-// The same attention on warp-level tensor cores with an asynchronous copy pipeline (the product path).
-// The SIMT kernel above spends ~500 issue slots per 16 keys on bf16 unpacking and FMAs (ncu: 45 % issue-active
-// at 64 % of HBM peak); here a 64-key tile of K, V (HBM) and R (L2) is copied by cp.async into a 4-stage
-// XOR-swizzled shared-memory ring and each warp spends ~140 issue slots per 16 keys:
-//   S^T = (q+u) K^T + (q+vb) R^T   : A = the query as row 0 of a 16-row operand, B = K / R rows via ldmatrix
-//   O  += P V                      : the score fragment is already the A fragment of the second MMA
-// rt_h is the R table laid out [H][C][64] so that a tile is contiguous per head.
-// ---------------------------------------------------------------------------------------------
-constexpr int AM_WARPS = 4;
-constexpr int AM_THREADS = AM_WARPS * 32;
-constexpr int AM_TILE = 64;
-constexpr int AM_MAT = AM_TILE * 128;          // one 64 x 64 bf16 matrix
-constexpr int AM_STAGE_BYTES = 3 * AM_MAT;     // K, R, V
-
-__device__ __forceinline__ uint32_t am_swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
-
-template <int AM_STAGES>
-__global__ void __launch_bounds__(AM_THREADS) dec_attn_mma_kernel(
-    const float* __restrict__ q, const bf16* __restrict__ kc, const bf16* __restrict__ vc,
-    const bf16* __restrict__ rt_h, const float* __restrict__ u, const float* __restrict__ vb, int H, int C,
-    int n_vis, int cur_slot, float scale, float* __restrict__ partial, int* __restrict__ counters,
-    bf16* __restrict__ out_bf16, float* __restrict__ out_f32, long long ldo, const int* __restrict__ dstate,
-    int cyclic, int dbg) {
-  extern __shared__ __align__(128) unsigned char am_smem[];
-  __shared__ float sh_m[AM_WARPS], sh_l[AM_WARPS], sh_o[AM_WARPS][64];
-  __shared__ int sh_last;
-  pdl_wait();
-  pdl_launch();
-  if (dstate) {
-    cur_slot = dstate[0];
-    n_vis = dstate[1];
-  }
-  // split index fastest: the CTAs of one (sequence, head) are neighbours in launch order
-  const int sp = blockIdx.x, S = gridDim.x, h = blockIdx.y, b = blockIdx.z;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, t = lane & 3;
-  const uint32_t sbase = cb::smem_u32(am_smem);
-  const bf16* kbase = kc + ((long long)b * H + h) * C * 64;
-  const bf16* vbase = vc + ((long long)b * H + h) * C * 64;
-  const bf16* rbase = rt_h + (long long)h * C * 64;
-  // tiles of 64 ages: dealt round-robin (cyclic: the S CTAs of a (sequence, head) sweep adjacent tiles together, so
-  // the DRAM pages they touch are neighbours) or in contiguous runs
-  const int NT = (n_vis + AM_TILE - 1) / AM_TILE;
-  const int t_lo = cyclic ? sp : (int)(((long long)sp * NT) / S);
-  const int t_step = cyclic ? S : 1;
-  const int ntiles = cyclic ? (NT - sp + S - 1) / S : (int)(((long long)(sp + 1) * NT) / S) - t_lo;
-
-  auto load_tile = [&](int it) {
-    if (it < ntiles) {
-      const int a0 = (t_lo + it * t_step) * AM_TILE;
-      const uint32_t st = sbase + (it % AM_STAGES) * AM_STAGE_BYTES;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int idx = tid + AM_THREADS * i;
-        const int row = idx >> 3, ch = idx & 7;
-        const int a = a0 + row;
-        const bool ok = a < n_vis;
-        const int ac = ok ? a : 0;
-        int slot = cur_slot - ac;
-        if (slot < 0) slot += C;
-        const uint32_t dst = st + am_swz(row, ch);
-        const int sz = ok ? 16 : 0;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(kbase + (long long)slot * 64 + ch * 8), "r"(sz));
-        // dbg (timing experiments only): 1 = every R tile from the first 8 KB of the table, 2 = V from the K rows
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + AM_MAT), "l"(rbase + (long long)((dbg & 1) ? row : ac) * 64 + ch * 8), "r"(sz));
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst + 2 * AM_MAT), "l"(((dbg & 2) ? kbase : vbase) + (long long)slot * 64 + ch * 8), "r"(sz));
-      }
-    }
-    cb::cp_async_commit();
-  };
-#pragma unroll
-  for (int it = 0; it < AM_STAGES - 1; ++it) load_tile(it);
-
-  // query fragments: row 0 of the 16-row A operand (lanes 0..3), everything else zero
-  uint32_t aqu[4][2], aqv[4][2];
-  {
-    const float* qp = q + ((long long)b * H + h) * 64;
-    const float* up = u + h * 64;
-    const float* vp = vb + h * 64;
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        const int c = 16 * ks + 8 * hf + 2 * t;
-        const float q0 = qp[c], q1 = qp[c + 1];
-        aqu[ks][hf] = g == 0 ? cb::pack_bf16(q0 + up[c], q1 + up[c + 1]) : 0u;
-        aqv[ks][hf] = g == 0 ? cb::pack_bf16(q0 + vp[c], q1 + vp[c + 1]) : 0u;
-      }
-    }
-  }
-  float m = -INFINITY, l = 0.f;
-  float o[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-  const float sl2 = scale * 1.4426950408889634f;
-  const int row_b = 16 * warp + (lane & 7) + (lane >> 4) * 8, ch_b = (lane >> 3) & 1;       // K / R operand rows
-  const int row_v = 16 * warp + (lane & 7) + ((lane >> 3) & 1) * 8, ch_v = lane >> 4;       // V operand rows (transposed)
-
-  for (int it = 0; it < ntiles; ++it) {
-    cb::cp_async_wait<AM_STAGES - 2>();
-    __syncthreads();
-    load_tile(it + AM_STAGES - 1);
-    const uint32_t st = sbase + (it % AM_STAGES) * AM_STAGE_BYTES;
-    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      uint32_t bk[4], br[4];
-      cb::ldmatrix_x4(bk, st + am_swz(row_b, 2 * ks + ch_b));
-      cb::ldmatrix_x4(br, st + AM_MAT + am_swz(row_b, 2 * ks + ch_b));
-      const uint32_t au[4] = {aqu[ks][0], 0u, aqu[ks][1], 0u}, av[4] = {aqv[ks][0], 0u, aqv[ks][1], 0u};
-      const uint32_t k0[2] = {bk[0], bk[1]}, k1[2] = {bk[2], bk[3]}, r0[2] = {br[0], br[1]}, r1[2] = {br[2], br[3]};
-      cb::mma_bf16_16816(acc0, au, k0);
-      cb::mma_bf16_16816(acc1, au, k1);
-      cb::mma_bf16_16816(acc0, av, r0);
-      cb::mma_bf16_16816(acc1, av, r1);
-    }
-    // row 0 of the score tile: this lane holds keys 2t, 2t+1, 8+2t, 9+2t of the warp's 16
-    const int abase = (t_lo + it * t_step) * AM_TILE + 16 * warp + 2 * t;
-    float s0 = abase < n_vis ? acc0[0] * sl2 : -INFINITY;
-    float s1 = abase + 1 < n_vis ? acc0[1] * sl2 : -INFINITY;
-    float s2 = abase + 8 < n_vis ? acc1[0] * sl2 : -INFINITY;
-    float s3 = abase + 9 < n_vis ? acc1[1] * sl2 : -INFINITY;
-    float tm = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
-    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
-    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 2));
-    const float mn = fmaxf(m, tm);
-    const float msafe = mn == -INFINITY ? 0.f : mn;
-    const float corr = exp2f(m - msafe);
-    const float p0 = exp2f(s0 - msafe), p1 = exp2f(s1 - msafe), p2 = exp2f(s2 - msafe), p3 = exp2f(s3 - msafe);
-    l = l * corr + ((p0 + p1) + (p2 + p3));
-    m = mn;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      o[j][0] *= corr;
-      o[j][1] *= corr;
-    }
-    const uint32_t ap[4] = {cb::pack_bf16(p0, p1), 0u, cb::pack_bf16(p2, p3), 0u};
-#pragma unroll
-    for (int np = 0; np < 4; ++np) {
-      uint32_t bv[4];
-      cb::ldmatrix_x4_trans(bv, st + 2 * AM_MAT + am_swz(row_v, 2 * np + ch_v));
-      const uint32_t v0[2] = {bv[0], bv[1]}, v1[2] = {bv[2], bv[3]};
-      cb::mma_bf16_16816(o[2 * np], ap, v0);
-      cb::mma_bf16_16816(o[2 * np + 1], ap, v1);
-    }
-  }
-  cb::cp_async_wait<0>();
-  // quad-reduce the row sum; lanes 0..3 of each warp own row 0
-  l += __shfl_xor_sync(0xffffffffu, l, 1);
-  l += __shfl_xor_sync(0xffffffffu, l, 2);
-  if (g == 0) {
-    if (t == 0) {
-      sh_m[warp] = m;
-      sh_l[warp] = l;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      sh_o[warp][8 * j + 2 * t] = o[j][0];
-      sh_o[warp][8 * j + 2 * t + 1] = o[j][1];
-    }
-  }
-  __syncthreads();
-  const int bh = b * H + h;
-  float mm = -INFINITY, ll = 0.f, oo = 0.f;
-  if (tid < 64) {
-#pragma unroll
-    for (int w = 0; w < AM_WARPS; ++w) mm = fmaxf(mm, sh_m[w]);
-#pragma unroll
-    for (int w = 0; w < AM_WARPS; ++w) {
-      const float c = sh_m[w] == -INFINITY ? 0.f : exp2f(sh_m[w] - mm);
-      ll += sh_l[w] * c;
-      oo += sh_o[w][tid] * c;
-    }
-  }
-  if (S > 1) {
-    float* mine = partial + ((long long)bh * S + sp) * 66;
-    if (tid < 64) {
-      mine[2 + tid] = oo;
-      if (tid == 0) {
-        mine[0] = mm;
-        mine[1] = ll;
-      }
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) sh_last = (atomicAdd(counters + bh, 1) == S - 1);
-    __syncthreads();
-    if (!sh_last) return;
-    __threadfence();
-    if (tid < 64) {
-      const float* all = partial + (long long)bh * S * 66;
-      mm = -INFINITY;
-      for (int s2 = 0; s2 < S; ++s2) mm = fmaxf(mm, __ldcg(all + s2 * 66));
-      ll = 0.f;
-      oo = 0.f;
-      for (int s2 = 0; s2 < S; ++s2) {
-        const float ms = __ldcg(all + s2 * 66);
-        const float c = ms == -INFINITY ? 0.f : exp2f(ms - mm);
-        ll += __ldcg(all + s2 * 66 + 1) * c;
-        oo += __ldcg(all + s2 * 66 + 2 + tid) * c;
-      }
-    }
-    if (tid == 0) counters[bh] = 0;
-  }
-  if (tid < 64) {
-    const float r = oo / ll;
-    if (out_f32) out_f32[(long long)b * ldo + h * 64 + tid] = r;
-    if (out_bf16) out_bf16[(long long)b * ldo + h * 64 + tid] = __float2bfloat16_rn(r);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // Stream-K, TMA-fed form of the tensor-core kernel (the product path).
 //   * persistent grid (2 CTAs per SM): the B*H*nt slot tiles of the launch are one flat list cut into equal contiguous
 //     runs, one per CTA, so every CTA streams the same bytes and the fixed costs are paid once per run; a
 //     (sequence, head) covered by several runs is merged by its last-arriving CTA (fixed order -> deterministic);
+//     (measured: one CTA per (sequence, head, split) reached 61 us per launch, this form 51 us in a replayed graph =
+//     5.2 TB/s = 81 % of the measured copy bandwidth; sharing the R tile between 4 sequences or splitting the MMA
+//     accumulate chains changed nothing, i.e. what is left is ramp-up / tail, not instruction issue or L2 traffic);
 //   * a producer warp issues, per 64-slot tile, three TMA tile loads (K, V from HBM; R from L2; 128-byte swizzle done
 //     by the copy engine) and one 256-byte bulk copy of the query row into a ring of STAGES stages guarded by
 //     full / empty mbarriers; the four consumer warps never compute an address and never meet at a CTA barrier
@@ -776,7 +464,15 @@ __global__ void __launch_bounds__(AM_THREADS) dec_attn_mma_kernel(
 //     operand comes from the reversed, doubled table rt2[h][j] = R[h][C-1 - (j mod C)], 2C rows, where the tile
 //     of slots s0.. is rows j0.. with j0 = (C-1-cur+s0) mod C - contiguous even across the age wrap.
 // ---------------------------------------------------------------------------------------------
+constexpr int AM_WARPS = 4;                    // consumer warps: 16 of a tile's 64 slots each
+constexpr int AM_THREADS = AM_WARPS * 32;
+constexpr int AM_TILE = 64;
+constexpr int AM_MAT = AM_TILE * 128;          // one 64 x 64 bf16 matrix
+constexpr int AM_STAGE_BYTES = 3 * AM_MAT;     // K, R, V
 constexpr int TK_THREADS = AM_THREADS + 32;     // 4 consumer warps + 1 producer warp
+
+// byte offset of 16-byte chunk `chunk` of row `row` in a 128-byte-swizzled tile (what the TMA writes)
+__device__ __forceinline__ uint32_t am_swz(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
 
 __device__ __forceinline__ void bulk_load_1d(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
@@ -897,9 +593,7 @@ __global__ void __launch_bounds__(TK_THREADS) dec_attn_tma_kernel(
       }
       fresh = false;
     }
-    // 16 independent MMAs (the dependent-accumulate latency of the warp-level tensor path is what bounds a warp's
-    // tile time), summed afterwards; only elements 0 / 1 (row 0) of an accumulator are meaningful
-    float pk0[4][4], pk1[4][4], pr0[4][4], pr1[4][4];
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t bk[4], br[4];
@@ -907,22 +601,14 @@ __global__ void __launch_bounds__(TK_THREADS) dec_attn_tma_kernel(
       cb::ldmatrix_x4(br, st + AM_MAT + am_swz(row_b, 2 * ks + ch_b));
       const uint32_t au[4] = {aqu[ks][0], 0u, aqu[ks][1], 0u}, av[4] = {aqv[ks][0], 0u, aqv[ks][1], 0u};
       const uint32_t k0[2] = {bk[0], bk[1]}, k1[2] = {bk[2], bk[3]}, r0[2] = {br[0], br[1]}, r1[2] = {br[2], br[3]};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) pk0[ks][e] = pk1[ks][e] = pr0[ks][e] = pr1[ks][e] = 0.f;
-      cb::mma_bf16_16816(pk0[ks], au, k0);
-      cb::mma_bf16_16816(pk1[ks], au, k1);
-      cb::mma_bf16_16816(pr0[ks], av, r0);
-      cb::mma_bf16_16816(pr1[ks], av, r1);
+      cb::mma_bf16_16816(acc0, au, k0);
+      cb::mma_bf16_16816(acc1, au, k1);
+      cb::mma_bf16_16816(acc0, av, r0);
+      cb::mma_bf16_16816(acc1, av, r1);
     }
     uint32_t bvv[4][4];     // V operand fragments: independent of the softmax, fetched while the score MMAs drain
 #pragma unroll
     for (int np = 0; np < 4; ++np) cb::ldmatrix_x4_trans(bvv[np], st + 2 * AM_MAT + am_swz(row_v, 2 * np + ch_v));
-    float acc0[2], acc1[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      acc0[e] = ((pk0[0][e] + pr0[0][e]) + (pk0[1][e] + pr0[1][e])) + ((pk0[2][e] + pr0[2][e]) + (pk0[3][e] + pr0[3][e]));
-      acc1[e] = ((pk1[0][e] + pr1[0][e]) + (pk1[1][e] + pr1[1][e])) + ((pk1[2][e] + pr1[2][e]) + (pk1[3][e] + pr1[3][e]));
-    }
     // row 0 of the score tile: this lane holds slots s0 + 16*warp + {2t, 2t+1, 8+2t, 9+2t}; age = (cur - slot) mod C
     int tt = t_first + kt;
     if (tt >= NTS) tt -= NTS;
@@ -1058,346 +744,6 @@ int cached_tmap(const void* ptr, uint64_t rows, const CUtensorMap** out) {
   return 0;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Grouped form of the stream-K TMA kernel: one CTA works on GRP = 4 sequences of the same head at once, one
-// consumer warp per sequence.  All sequences share the ring position, so the relative-position tile R[h] of a slot
-// tile is the same for the whole group and is fetched once per 4 sequences: shared-memory fill traffic drops from
-// 24 KB to 18 KB per (sequence, 64 keys) (the ungrouped kernel moved 402 MB through L2 per launch for 268 MB of
-// cache and stalled near the L2 -> SM ceiling), a warp owns its sequence's running softmax state outright (no
-// cross-warp merge, no CTA barrier anywhere in the loop) and issues ~2.6x fewer instructions per key.
-//   K / V tiles of the group: ONE 4-D TMA box each ({64 dims, TK slots, 1 head, 4 sequences}; sequences beyond B are
-//   zero-filled by the copy engine); stage = [K: 4 x TK x 128 B][V: same][R: TK x 128 B][q: 4 x 256 B]
-// ---------------------------------------------------------------------------------------------
-constexpr int GRP = 4;
-
-template <int STAGES, int TK>
-__global__ void __launch_bounds__(TK_THREADS) dec_attn_group_kernel(
-    const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-    const __grid_constant__ CUtensorMap tm_r, const float* __restrict__ q, const float* __restrict__ u,
-    const float* __restrict__ vb, int B, int H, int C, int n_vis, int cur_slot, float scale,
-    float* __restrict__ partial, int max_parts, int* __restrict__ counters, bf16* __restrict__ out_bf16,
-    float* __restrict__ out_f32, long long ldo, const int* __restrict__ dstate) {
-  constexpr int MAT = TK * 128;                        // one sequence's K (or V) tile, or the R tile
-  constexpr int STAGE = (2 * GRP + 1) * MAT + GRP * 256;
-  constexpr int KB = TK / 16;                          // 16-key blocks per tile
-  extern __shared__ unsigned char tk_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t sbase = (cb::smem_u32(tk_raw) + 1023u) & ~1023u;
-  unsigned char* sgen = tk_raw + (sbase - cb::smem_u32(tk_raw));
-  float* s_uv = reinterpret_cast<float*>(sgen + STAGES * STAGE);          // [2][H][64]
-  for (int i = tid; i < H * 64; i += TK_THREADS) {
-    s_uv[i] = u[i];
-    s_uv[H * 64 + i] = vb[i];
-  }
-  if (tid == 0) {
-#pragma unroll
-    for (int i = 0; i < STAGES; ++i) {
-      cb::mbar_init(&full_bar[i], 1);
-      cb::mbar_init(&empty_bar[i], AM_WARPS);
-    }
-    cb::fence_barrier_init();
-    cb::tma_prefetch_desc(&tm_k);
-    cb::tma_prefetch_desc(&tm_v);
-    cb::tma_prefetch_desc(&tm_r);
-  }
-  pdl_wait();
-  pdl_launch();
-  __syncthreads();
-  if (dstate) {
-    cur_slot = dstate[0];
-    n_vis = dstate[1];
-  }
-  // slot tiles (TK slots) that hold visible keys: the n_vis newest slots (cur - n_vis, cur] of the ring
-  const int NTS = C / TK;
-  int lo = cur_slot - n_vis + 1;
-  if (lo < 0) lo += C;
-  const int t_first = lo / TK;
-  const int nt = min(NTS, ((lo % TK) + n_vis + TK - 1) / TK);
-  const int BG = (B + GRP - 1) / GRP;
-  const long long T = (long long)BG * H * nt;
-  const int quota = (int)((T + gridDim.x - 1) / gridDim.x);
-  const long long T0 = (long long)blockIdx.x * quota;
-  const long long T1 = T0 + quota < T ? T0 + quota : T;
-  const int ntiles = T1 > T0 ? (int)(T1 - T0) : 0;
-  if (ntiles == 0) return;
-  int gh = (int)(T0 / nt), kt = (int)(T0 - (long long)gh * nt);     // gh = group * H + head
-
-  if (warp == AM_WARPS) {
-    // ===== producer =====
-    if (lane == 0) {
-      for (int it = 0; it < ntiles; ++it) {
-        const int st = it % STAGES;
-        if (it >= STAGES) cb::mbar_wait(&empty_bar[st], ((it / STAGES) & 1) ^ 1);
-        int tt = t_first + kt;
-        if (tt >= NTS) tt -= NTS;
-        const int s0 = tt * TK;
-        int j0 = C - 1 - cur_slot + s0;
-        if (j0 >= C) j0 -= C;
-        const int grp = gh / H, h = gh - grp * H;
-        const int nseq = min(GRP, B - grp * GRP);
-        const uint32_t dst = sbase + st * STAGE;
-        cb::mbar_arrive_expect_tx(&full_bar[st], (2 * GRP + 1) * MAT + nseq * 256);
-        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst),
-                     "l"(reinterpret_cast<uint64_t>(&tm_k)), "r"(cb::smem_u32(&full_bar[st])), "r"(0), "r"(s0), "r"(h), "r"(grp * GRP) : "memory");
-        asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n" ::"r"(dst + GRP * MAT),
-                     "l"(reinterpret_cast<uint64_t>(&tm_v)), "r"(cb::smem_u32(&full_bar[st])), "r"(0), "r"(s0), "r"(h), "r"(grp * GRP) : "memory");
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst + 2 * GRP * MAT),
-                     "l"(reinterpret_cast<uint64_t>(&tm_r)), "r"(cb::smem_u32(&full_bar[st])), "r"(0), "r"(h * 2 * C + j0) : "memory");
-        for (int i = 0; i < nseq; ++i)
-          bulk_load_1d(dst + (2 * GRP + 1) * MAT + i * 256, q + ((long long)(grp * GRP + i) * H + h) * 64, 256, &full_bar[st]);
-        if (++kt == nt) {
-          kt = 0;
-          ++gh;
-        }
-      }
-    }
-    return;
-  }
-
-  // ===== consumers: warp w owns sequence grp*GRP + w =====
-  const int g = lane >> 2, t = lane & 3;
-  bool fresh = true;
-  uint32_t aqu[4][2], aqv[4][2];
-  float m = -INFINITY, l = 0.f;
-  float o[8][4];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
-  const float sl2 = scale * 1.4426950408889634f;
-  const int row_b = (lane & 7) + (lane >> 4) * 8, ch_b = (lane >> 3) & 1;
-  const int row_v = (lane & 7) + ((lane >> 3) & 1) * 8, ch_v = lane >> 4;
-
-  for (int it = 0; it < ntiles; ++it) {
-    const int stg = it % STAGES;
-    cb::mbar_wait(&full_bar[stg], (it / STAGES) & 1);
-    const uint32_t st = sbase + stg * STAGE;
-    const int grp = gh / H, h = gh - grp * H;
-    const int b = grp * GRP + warp;
-    const bool live = b < B;
-    if (fresh) {
-      const float* qp = reinterpret_cast<const float*>(sgen + stg * STAGE + (2 * GRP + 1) * MAT + warp * 256);
-      const float* up = s_uv + h * 64;
-      const float* vp = up + H * 64;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int c = 16 * ks + 8 * hf + 2 * t;
-          const float q0 = live ? qp[c] : 0.f, q1 = live ? qp[c + 1] : 0.f;
-          aqu[ks][hf] = g == 0 ? cb::pack_bf16(q0 + up[c], q1 + up[c + 1]) : 0u;
-          aqv[ks][hf] = g == 0 ? cb::pack_bf16(q0 + vp[c], q1 + vp[c + 1]) : 0u;
-        }
-      }
-      fresh = false;
-    }
-    const uint32_t sk = st + warp * MAT, sv = st + (GRP + warp) * MAT, sr = st + 2 * GRP * MAT;
-    int tt = t_first + kt;
-    if (tt >= NTS) tt -= NTS;
-    float sc[KB][4];
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb) {
-      float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        uint32_t bk[4], br[4];
-        cb::ldmatrix_x4(bk, sk + am_swz(16 * kb + row_b, 2 * ks + ch_b));
-        cb::ldmatrix_x4(br, sr + am_swz(16 * kb + row_b, 2 * ks + ch_b));
-        const uint32_t au[4] = {aqu[ks][0], 0u, aqu[ks][1], 0u}, av[4] = {aqv[ks][0], 0u, aqv[ks][1], 0u};
-        const uint32_t k0[2] = {bk[0], bk[1]}, k1[2] = {bk[2], bk[3]}, r0[2] = {br[0], br[1]}, r1[2] = {br[2], br[3]};
-        cb::mma_bf16_16816(acc0, au, k0);
-        cb::mma_bf16_16816(acc1, au, k1);
-        cb::mma_bf16_16816(acc0, av, r0);
-        cb::mma_bf16_16816(acc1, av, r1);
-      }
-      // this lane: slots s0 + 16*kb + {2t, 2t+1, 8+2t, 9+2t}; age = (cur - slot) mod C
-      const int age0 = cur_slot - (tt * TK + 16 * kb + 2 * t);
-      auto vis = [&](int a) { return (a < 0 ? a + C : a) < n_vis; };
-      sc[kb][0] = vis(age0) ? acc0[0] * sl2 : -INFINITY;
-      sc[kb][1] = vis(age0 - 1) ? acc0[1] * sl2 : -INFINITY;
-      sc[kb][2] = vis(age0 - 8) ? acc1[0] * sl2 : -INFINITY;
-      sc[kb][3] = vis(age0 - 9) ? acc1[1] * sl2 : -INFINITY;
-    }
-    float tm = -INFINITY;
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb) tm = fmaxf(tm, fmaxf(fmaxf(sc[kb][0], sc[kb][1]), fmaxf(sc[kb][2], sc[kb][3])));
-    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
-    tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 2));
-    const float mn = fmaxf(m, tm);
-    const float msafe = mn == -INFINITY ? 0.f : mn;
-    const float corr = exp2f(m - msafe);
-    m = mn;
-    l *= corr;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      o[j][0] *= corr;
-      o[j][1] *= corr;
-    }
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb) {
-      const float p0 = exp2f(sc[kb][0] - msafe), p1 = exp2f(sc[kb][1] - msafe), p2 = exp2f(sc[kb][2] - msafe),
-                  p3 = exp2f(sc[kb][3] - msafe);
-      l += (p0 + p1) + (p2 + p3);
-      const uint32_t ap[4] = {cb::pack_bf16(p0, p1), 0u, cb::pack_bf16(p2, p3), 0u};
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t bv[4];
-        cb::ldmatrix_x4_trans(bv, sv + am_swz(16 * kb + row_v, 2 * np + ch_v));
-        const uint32_t v0[2] = {bv[0], bv[1]}, v1[2] = {bv[2], bv[3]};
-        cb::mma_bf16_16816(o[2 * np], ap, v0);
-        cb::mma_bf16_16816(o[2 * np + 1], ap, v1);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) cb::mbar_arrive(&empty_bar[stg]);
-    // ---- end of this run's share of the (group, head): every warp publishes its own sequence ----
-    if (kt == nt - 1 || it == ntiles - 1) {
-      float ll = l;
-      ll += __shfl_xor_sync(0xffffffffu, ll, 1);
-      ll += __shfl_xor_sync(0xffffffffu, ll, 2);
-      if (live) {
-        const int bh = b * H + h;
-        const int first = (int)(((long long)gh * nt) / quota), last = (int)(((long long)(gh + 1) * nt - 1) / quota);
-        const int parts = last - first + 1;
-        // lanes 0..3 (row 0) hold dims 8j + 2t, 8j + 2t + 1
-        if (parts == 1) {
-          if (g == 0) {
-            const float inv = 1.f / ll;
-            const long long off = (long long)b * ldo + h * 64;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int c = 8 * j + 2 * t;
-              if (out_f32) *reinterpret_cast<float2*>(out_f32 + off + c) = make_float2(o[j][0] * inv, o[j][1] * inv);
-              if (out_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + off + c) = cb::pack_bf16(o[j][0] * inv, o[j][1] * inv);
-            }
-          }
-        } else {
-          float* mine = partial + ((long long)bh * max_parts + ((int)blockIdx.x - first)) * 66;
-          if (g == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<float2*>(mine + 2 + 8 * j + 2 * t) = make_float2(o[j][0], o[j][1]);
-            if (t == 0) {
-              mine[0] = m;
-              mine[1] = ll;
-            }
-          }
-          __threadfence();
-          __syncwarp();
-          int is_last = 0;
-          if (lane == 0) is_last = (atomicAdd(counters + bh, 1) == parts - 1);
-          is_last = __shfl_sync(0xffffffffu, is_last, 0);
-          if (is_last) {
-            __threadfence();
-            const float* all = partial + (long long)bh * max_parts * 66;
-            float mm = -INFINITY;
-            for (int s2 = 0; s2 < parts; ++s2) mm = fmaxf(mm, __ldcg(all + s2 * 66));
-            float lsum = 0.f, o0 = 0.f, o1 = 0.f;
-            for (int s2 = 0; s2 < parts; ++s2) {
-              const float ms = __ldcg(all + s2 * 66);
-              const float c = ms == -INFINITY ? 0.f : exp2f(ms - mm);
-              lsum += __ldcg(all + s2 * 66 + 1) * c;
-              o0 += __ldcg(all + s2 * 66 + 2 + 2 * lane) * c;
-              o1 += __ldcg(all + s2 * 66 + 3 + 2 * lane) * c;
-            }
-            const float inv = 1.f / lsum;
-            const long long off = (long long)b * ldo + h * 64 + 2 * lane;
-            if (out_f32) *reinterpret_cast<float2*>(out_f32 + off) = make_float2(o0 * inv, o1 * inv);
-            if (out_bf16) *reinterpret_cast<uint32_t*>(out_bf16 + off) = cb::pack_bf16(o0 * inv, o1 * inv);
-            if (lane == 0) counters[bh] = 0;
-          }
-        }
-      }
-      m = -INFINITY;
-      l = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j][0] = o[j][1] = 0.f;
-      fresh = true;
-    }
-    if (++kt == nt) {
-      kt = 0;
-      ++gh;
-    }
-  }
-}
-
-typedef CUresult (*EncodeTiledFnD)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-// 4-D map over a bf16 cache [B][H][C][64]: dims {64, C, H, B}, box {64, tk, 1, GRP}, 128-byte swizzle
-int cached_tmap4(const void* ptr, int B, int H, int C, int tk, const CUtensorMap** out) {
-  const uint64_t key = ((uint64_t)B << 40) ^ ((uint64_t)H << 32) ^ ((uint64_t)C << 8) ^ (uint64_t)tk ^ (1ull << 63);
-  for (int i = 0; i < g_ntmaps; ++i)
-    if (g_tmaps[i].ptr == ptr && g_tmaps[i].rows == key) {
-      *out = &g_tmaps[i].map;
-      return 0;
-    }
-  static EncodeTiledFnD fn = nullptr;
-  if (!fn) {
-    void* pf = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &pf, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return cb_host::fail(COMMU_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-    fn = reinterpret_cast<EncodeTiledFnD>(pf);
-  }
-  TmapSlot& s = g_tmaps[g_ntmaps < 256 ? g_ntmaps : 255];
-  cuuint64_t dims[4] = {64, (cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {128, (cuuint64_t)C * 128, (cuuint64_t)H * C * 128};
-  cuuint32_t box[4] = {64, (cuuint32_t)tk, 1, GRP};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = fn(&s.map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return cb_host::fail(COMMU_ERR_CUDA, "cuTensorMapEncodeTiled(4d) failed (%d)", (int)r);
-  s.ptr = ptr;
-  s.rows = key;
-  if (g_ntmaps < 256) ++g_ntmaps;
-  *out = &s.map;
-  return 0;
-}
-// 2-D map with a box of `tk` rows
-int cached_tmap2(const void* ptr, uint64_t rows, int tk, const CUtensorMap** out) {
-  const uint64_t key = rows ^ ((uint64_t)tk << 48) ^ (1ull << 62);
-  for (int i = 0; i < g_ntmaps; ++i)
-    if (g_tmaps[i].ptr == ptr && g_tmaps[i].rows == key) {
-      *out = &g_tmaps[i].map;
-      return 0;
-    }
-  TmapSlot& s = g_tmaps[g_ntmaps < 256 ? g_ntmaps : 255];
-  const int rc = cb_host::make_tmap_bf16_2d(&s.map, ptr, 64, rows, 64, 64, tk);
-  if (rc) return rc;
-  s.ptr = ptr;
-  s.rows = key;
-  if (g_ntmaps < 256) ++g_ntmaps;
-  *out = &s.map;
-  return 0;
-}
-
-template <int STAGES, int TK>
-int launch_group(const void* kcache, const void* vcache, const void* rtab, const float* q, const float* u, const float* vb,
-                 int B, int H, int C, int n_vis, int cur_slot, float scale, float* partial, int* counters, void* out_bf16,
-                 float* out_f32, long long ldo, const int* dev_state, int ctas_per_sm, cudaLaunchConfig_t cfg) {
-  auto kern = dec_attn_group_kernel<STAGES, TK>;
-  const int smem = 1024 + STAGES * ((2 * GRP + 1) * TK * 128 + GRP * 256) + 2 * H * 64 * 4;
-  CB_REQUIRE(smem <= 227 * 1024, "decode_attn_split: shared memory %d exceeds the limit", smem);
-  static int configured = 0;
-  if (smem > configured) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = smem;
-  }
-  const CUtensorMap *tk, *tv, *tr;
-  int rc;
-  if ((rc = cached_tmap4(kcache, B, H, C, TK, &tk))) return rc;
-  if ((rc = cached_tmap4(vcache, B, H, C, TK, &tv))) return rc;
-  if ((rc = cached_tmap2(rtab, (uint64_t)H * 2 * C, TK, &tr))) return rc;
-  cfg.gridDim = dim3(ctas_per_sm * cb_host::num_sms(), 1, 1);
-  cfg.blockDim = dim3(TK_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, *tk, *tv, *tr, q, u, vb, B, H, C, n_vis, cur_slot, scale, partial, C / 16, counters,
-                                   (bf16*)out_bf16, out_f32, ldo, dev_state));
-  cb_host::count_launch();
-  return 0;
-}
-
 template <int PRO, int EPI, bool CLUSTER>
 int launch_linear(const LinP& p, int grid_x, int split, size_t smem, int pdl, cudaStream_t s) {
   auto kern = dec_linear_kernel<PRO, EPI, CLUSTER>;
@@ -1522,18 +868,6 @@ int commu_decode_attn_split(const float* q, const void* kcache, const void* vcac
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = pdl ? 1 : 0;
-  if (impl & 64) {   // grouped stream-K TMA kernel: 4 sequences per CTA share the R tile; partial = [B*H][C/16][66]
-    CB_REQUIRE(C % 64 == 0, "decode_attn_split: the TMA kernels need a ring capacity that is a multiple of 64 (C=%d)", C);
-#define COMMU_LG(ST, TKK) launch_group<ST, TKK>(kcache, vcache, rtab, q, r_w_bias, r_r_bias, B, H, C, n_vis, cur_slot, scale, \
-                                               partial, counters, out_bf16, out_f32, (long long)ldo, dev_state, splits, cfg)
-    switch ((impl >> 8) & 3) {   // (stages, slots per tile): shared memory per CTA 78 / 117 / 226 / 116 KB
-      case 0: return COMMU_LG(4, 16);
-      case 1: return COMMU_LG(3, 32);
-      case 2: return COMMU_LG(3, 64);
-      default: return COMMU_LG(6, 16);
-    }
-#undef COMMU_LG
-  }
   if (impl & 8) {    // stream-K TMA kernel (product path): `splits` = CTAs per SM, partial = [B*H][C/64][66]
     CB_REQUIRE(C % 64 == 0, "decode_attn_split: the TMA kernel needs a ring capacity that is a multiple of 64 (C=%d)", C);
     static int configured_h = 0;
@@ -1563,29 +897,6 @@ int commu_decode_attn_split(const float* q, const void* kcache, const void* vcac
       CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_attn_tma_kernel<4>, *tk, *tv, *tr, q, r_w_bias, r_r_bias, B * H, H, C, n_vis,
                                        cur_slot, scale, partial, max_parts, counters, (bf16*)out_bf16, out_f32,
                                        (long long)ldo, dev_state));
-    cb_host::count_launch();
-    return 0;
-  }
-  if (impl >= 1) {   // tensor-core kernel: rtab is laid out [H][C][64]; impl bits: 2 = 3-stage ring, 4 = blocked tiles
-    static bool configured = false;
-    if (!configured) {
-      CB_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_mma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * AM_STAGE_BYTES));
-      CB_CHECK_CUDA(cudaFuncSetAttribute(dec_attn_mma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * AM_STAGE_BYTES));
-      configured = true;
-    }
-    const int stages = (impl & 2) ? 3 : 4;
-    const int cyclic = (impl & 4) ? 0 : 1;
-    cfg.gridDim = dim3(splits, H, B);
-    cfg.blockDim = dim3(AM_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = stages * AM_STAGE_BYTES;
-    if (stages == 3)
-      CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_attn_mma_kernel<3>, q, (const bf16*)kcache, (const bf16*)vcache,
-                                       (const bf16*)rtab, r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, partial,
-                                       counters, (bf16*)out_bf16, out_f32, (long long)ldo, dev_state, cyclic, (impl >> 4) & 3));
-    else
-      CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, dec_attn_mma_kernel<4>, q, (const bf16*)kcache, (const bf16*)vcache,
-                                       (const bf16*)rtab, r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, partial,
-                                       counters, (bf16*)out_bf16, out_f32, (long long)ldo, dev_state, cyclic, (impl >> 4) & 3));
     cb_host::count_launch();
     return 0;
   }

@@ -294,11 +294,14 @@ typedef struct {
   const int* dev_state;
 } CommuDecLinear;
 int commu_decode_fused_linear(const CommuDecLinear* args, void* stream);
-/* commu_decode_attn over a bf16 cache with the visible keys of every (sequence, head) split over `splits` CTAs
- * (grid H x B x splits, sized for ~7 resident CTAs per SM); partial: fp32 [B*H*splits*66] scratch, counters:
- * int32 [B*H] zero-initialised once (the last-arriving CTA merges the partials in split order and re-zeroes).
- * impl 0: SIMT kernel, rtab [C,H,64].  impl 1 (product path): warp-level tensor-core MMAs fed by a 4-stage
- * cp.async ring of 64-key K / V / R tiles, rtab laid out [H,C,64]. */
+/* commu_decode_attn over a bf16 cache [B,H,C,64], two implementations:
+ *  impl & 8 (product path): stream-K tensor-core kernel.  C must be a multiple of 64; rtab is the reversed, doubled
+ *    table [H, 2C, 64] with row j = R[C-1 - (j mod C)].  A persistent grid of `splits` CTAs per SM cuts the flat list
+ *    of B*H*(visible 64-slot tiles) into equal contiguous runs; a producer warp feeds K / V / R tiles by TMA (128-byte
+ *    swizzle) into an mbarrier ring (4 stages, 3 with impl & 2), four consumer warps run warp-level bf16 MMAs.
+ *    partial: fp32 [B*H][C/64][66] scratch, counters: int32 [B*H] zero-initialised once (the CTA that arrives last at
+ *    a (sequence, head) merges its runs in run order and re-zeroes the counter: deterministic).
+ *  impl == 0 (cross-check): SIMT kernel, rtab [C,H,64], grid H x B x splits, partial fp32 [B*H*splits*66]. */
 int commu_decode_attn_split(const float* q, const void* kcache, const void* vcache, const void* rtab,
                             const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
                             float scale, int splits, float* partial, int* counters, void* out_bf16, float* out_f32,

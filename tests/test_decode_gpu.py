@@ -54,6 +54,42 @@ def test_decode_fp32_free_running_greedy_identical():
         assert np.array_equal(cur.cpu().numpy(), z["tokens"][t]), t
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_decode_fp32_greedy_512_tokens(seed):
+    """SURVEY.md 8(d) parity gate: greedy decode of >= 512 tokens for 4 seeds of weights.  The oracle re-runs the
+    reference's forward_generate (model.py:606-628) over [memory ; token] per step on the CPU; the fp32 decode
+    engine must pick the identical token at every step (the ring cache wraps: 520 steps > mem_len = 48).  Both sides
+    follow the oracle's tokens, so a single disagreement cannot hide later ones."""
+    from commu.engine.decode import DecodeEngine, DecodeState
+    cfg = orc.make_cfg(n_layer=2, n_head=2, d_model=64, d_inner=128, tgt_len=1, mem_len=48, same_length=True,
+                       clamp_len=-1, n_token=97)
+    P = orc.init_params(cfg, seed=100 + seed, std=0.3)           # large weights: peaked, well-separated logits
+    model = build_model(cfg, P)
+    model.eval()
+    eng = DecodeEngine(model, batch=2, mem_len=cfg.mem_len, same_length=True, precision="fp32")
+    g = torch.Generator().manual_seed(seed)
+    cur = torch.randint(1, 97, (1, 2), generator=g)
+    mems, st = None, DecodeState()
+    thin = 0
+    with torch.no_grad():
+        for t in range(520):
+            lo, mems = orc.forward_generate(cfg, P, cur, mems)
+            lg, st = eng.step(cur[0].cuda().contiguous(), st)
+            ref = lo[-1]                                           # [B, V]
+            tok_o = 1 + ref[:, 1:].argmax(-1)                      # token 0 is never sampled (midi_inferrer.py:206)
+            tok_n, _ = eng.sample(lg, 0.0)
+            top2 = ref[:, 1:].topk(2, -1).values
+            margin = top2[:, 0] - top2[:, 1]
+            for b in range(2):
+                if margin[b] > 1e-4:
+                    assert int(tok_n[b]) == int(tok_o[b]), (seed, t, b, float(margin[b]))
+                else:
+                    thin += 1
+            assert (lg.cpu() - ref).abs().max() < 2e-3 * max(1.0, float(ref.abs().max())), (seed, t)
+            cur = tok_o[None]
+    assert thin <= 4, thin
+
+
 def test_decode_bf16_logits_close():
     toks, worst, z = _run_decode("bf16")
     assert worst < 0.06 * np.abs(z["logits"]).max() + 0.02, worst
@@ -68,10 +104,7 @@ def test_decode_bf16_logits_close():
                                  dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_PDL="0", COMMU_DECODE_SPLITS="1"),
                                  dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_PDL="1", COMMU_DECODE_SPLITS="3"),
                                  dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="0", COMMU_DECODE_SPLITS="2"),
-                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="1", COMMU_DECODE_SPLITS="2"),
-                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="10", COMMU_DECODE_SPLITS="1"),
-                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="64", COMMU_DECODE_SPLITS="2"),
-                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="576", COMMU_DECODE_SPLITS="1")])
+                                 dict(COMMU_DECODE_FUSED="1", COMMU_DECODE_ATTN="10", COMMU_DECODE_SPLITS="1")])
 def test_decode_bf16_paths_close_to_golden(env, monkeypatch):
     """Every bf16 decode path (tcgen05-GEMM step, fused step with / without programmatic dependent launch and key
     splits) stays within the bf16 tolerance of the fp32 reference logits (Dh = 16 < 64: padded head layout)."""
@@ -101,7 +134,7 @@ def _bench_like_model(L=2, H=8, d=512, Di=2048, V=729, mem_len=300, seed=3):
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("attn", ["8", "64", "320"])
+@pytest.mark.parametrize("attn", ["8", "10", "0"])
 @pytest.mark.parametrize("shape", [dict(H=8, d=512, Di=2048, B=64, mem_len=300),     # bench shape, ring wraps
                                    dict(H=10, d=500, Di=1000, B=5, mem_len=200),     # checkpoint shape: Dh = 50, d % 64 != 0
                                    dict(H=16, d=1024, Di=4096, B=33, mem_len=130)])   # widest supported rows

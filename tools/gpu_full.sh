@@ -1,9 +1,8 @@
 #!/bin/bash
 set +e
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -q -m gpu --deselect tests/test_gemm_gpu.py::test_gemm_perf 2>&1 | tail -30 > gpurun_out/tests_full.log; tail -6 gpurun_out/tests_full.log
+timeout 1500 python -m pytest tests -q -m gpu --deselect tests/test_gemm_gpu.py::test_gemm_perf 2>&1 | tail -30 > gpurun_out/tests_full.log; tail -6 gpurun_out/tests_full.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json | cut -c1-700; tail -2 gpurun_out/bench_ref.err
 timeout 1200 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 python - <<'PY'
 import json
@@ -12,5 +11,3 @@ try:
 except Exception as e: print("bench parse failed", e)
 PY
 tail -3 gpurun_out/bench_default.err
-timeout 600 python bench.py --dropout 0 --no-decode --no-cpu-baseline > gpurun_out/bench_drop0.json 2> gpurun_out/bench_drop0.err; cut -c1-400 gpurun_out/bench_drop0.json; python -c "
-import json; j=json.load(open('gpurun_out/bench_drop0.json')); print(j['value'], j['ms_per_step'], j['kernel_time_ms_per_step'])"
