@@ -6,12 +6,15 @@
 //   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier tx)
 //   warp 1   : MMA issuer     (one elected lane issues tcgen05.mma, tcgen05.commit frees slots)
 //   warp 2   : TMEM allocator (2 accumulator buffers so the epilogue overlaps the next tile)
-//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 4-11: epilogue      (tcgen05.ld 32x32b -> registers -> fused epilogue -> global; two warps per TMEM lane
+//                              quadrant, the load of the next 32-column chunk in flight while one is stored: with
+//                              four warps and a wait after every load the K = 512 shapes were epilogue-bound)
 //
 // Both operand majors are supported so forward (K-major x K-major), dgrad (K-major x K-major on a
 // transposed weight shadow) and wgrad (MN-major x MN-major: reduction over tokens) all run here.
 // Replaces the nn.Linear calls of the reference (commu/model/model.py:285-286, 348, 163-169, 46)
 // and their autograd backward.
+#include <stdlib.h>
 #include "api_common.h"
 #include "common.cuh"
 
@@ -20,7 +23,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle span
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;   // warps 0-3: producer / MMA / TMEM alloc / idle, warps 4-11: epilogue
+constexpr int EPI_WARPS = 8;       // two warps per TMEM lane quadrant, each half of the tile's columns
 constexpr int SMEM_BUDGET = 200 * 1024;
 
 struct GemmKernelParams {
@@ -178,7 +182,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int b = 0; b < 2; ++b) {
       cb::mbar_init(&tmem_full[b], 1);
-      cb::mbar_init(&tmem_empty[b], 128);
+      cb::mbar_init(&tmem_empty[b], EPI_WARPS * 32);
     }
     cb::fence_barrier_init();
   }
@@ -277,7 +281,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int q = warp - 4;
+    const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
+    constexpr int CH = BLOCK_N / 64;       // 32-column chunks per epilogue warp
     int buf = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
@@ -290,15 +295,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       cb::mbar_wait(&tmem_full[buf], acc_phase);
       cb::tc_fence_after();
       const int row = m_blk * BLOCK_M + q * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int n0 = n_blk * BLOCK_N + c * 32;
-        if (n0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        cb::tmem_ld_32x32b_x32(taddr + c * 32, r);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + half * (CH * 32);
+      const int nbase = n_blk * BLOCK_N + half * (CH * 32);
+      uint32_t r[2][32];
+      cb::tmem_ld_32x32b_x32(taddr, r[0]);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
         cb::tmem_ld_wait();
-        epilogue_store(p, r, row, n0);
+        if (c + 1 < CH) cb::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+        const int n0 = nbase + c * 32;
+        if (n0 < p.N) epilogue_store(p, r[c & 1], row, n0);
       }
       cb::tc_fence_before();
       cb::mbar_arrive(&tmem_empty[buf]);
@@ -312,6 +318,242 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp == 2) {
     cb::tc_fence_after();
     cb::tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs on the two SMs of a TPC owns a 256 x 256 output
+// tile.  Each CTA stages its own 128 rows of A and only HALF of the B tile (128 of the 256 n-rows); the pair's MMA
+// (M = 256) reads the other half from the peer's shared memory, so the shared-memory fill per CTA and k-block drops
+// from 48 KB to 32 KB (at 128 x 256 x 64 per 0.37 us a single CTA needs ~130 GB/s of L2 -> SM bandwidth, which is what
+// caps the one-CTA kernel on the model's K = 512 shapes).  Protocol:
+//   * both producers issue their TMA loads with .cta_group::2 so that the bytes land on the LEADER's full barrier;
+//   * only the leader (cluster rank 0) issues tcgen05.mma.cta_group::2; its commits are multicast to the empty /
+//     tmem_full barriers of both CTAs;
+//   * the epilogue warps of both CTAs arrive on the leader's tmem_empty barrier (512 arrivals).
+// ---------------------------------------------------------------------------------------------
+struct Cfg2 {
+  static constexpr int BLOCK_N = 256;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // this CTA's 128 rows
+  static constexpr int B_BYTES = (BLOCK_N / 2) * BLOCK_K * 2;    // this CTA's half of the n-rows
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];\n" ::"r"(cb::smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on `bar` of both CTAs of the pair
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+          cb::smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmKernelParams p) {
+  using C = Cfg2;
+  constexpr int BLOCK_N = C::BLOCK_N;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full = empty_bar + C::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  const int m_pairs = (p.M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int kb_per = (kb_total + p.split_k - 1) / p.split_k;
+  const int num_items = m_pairs * n_tiles * p.split_k;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    cb::tma_prefetch_desc(&tmap_a);
+    cb::tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) {
+      cb::mbar_init(&full_bar[s], 1);
+      cb::mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      cb::mbar_init(&tmem_full[b], 1);
+      cb::mbar_init(&tmem_empty[b], 2 * EPI_WARPS * 32);     // the epilogue threads of both CTAs (leader's copy is the one used)
+    }
+    cb::fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(cb::smem_u32(tmem_ptr)),
+                 "r"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+  }
+  cb::tc_fence_before();
+  cluster_sync_all();
+  cb::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (cb::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const int n_blk = item % n_tiles;
+        const int m_blk = (item / n_tiles) % m_pairs;
+        const int ks = item / (n_tiles * m_pairs);
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(kb_total, kb0 + kb_per);
+        const int m0 = m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M;
+        const int n0 = n_blk * BLOCK_N + (int)rank * (BLOCK_N / 2);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          cb::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          const uint32_t lbar = mapa_rank(cb::smem_u32(&full_bar[stage]), 0);
+          if (rank == 0) cb::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          if (!p.a_mn) {
+            tma_load_2d_2sm(sa, &tmap_a, lbar, kb * BLOCK_K, m0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_M / 64; ++a)
+              tma_load_2d_2sm(sa + a * (64 * BLOCK_K * 2), &tmap_a, lbar, m0 + a * 64, kb * BLOCK_K);
+          }
+          if (!p.b_mn) {
+            tma_load_2d_2sm(sb, &tmap_b, lbar, kb * BLOCK_K, n0);
+          } else {
+#pragma unroll
+            for (int a = 0; a < BLOCK_N / 128; ++a)
+              tma_load_2d_2sm(sb + a * (64 * BLOCK_K * 2), &tmap_b, lbar, n0 + a * 64, kb * BLOCK_K);
+          }
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0 && cb::elect_one()) {
+      const uint32_t idesc = cb::umma_idesc_bf16(2 * BLOCK_M, BLOCK_N, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? (BLOCK_K * 128) : 16;
+      const uint32_t b_lbo = p.b_mn ? (BLOCK_K * 128) : 16;
+      const uint32_t a_kstep = p.a_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      const uint32_t b_kstep = p.b_mn ? (UMMA_K * 128) >> 4 : (UMMA_K * 2) >> 4;
+      int stage = 0;
+      uint32_t phase = 0;
+      int buf = 0;
+      uint32_t acc_phase = 0;
+      for (int item = cluster_id; item < num_items; item += num_clusters) {
+        const int ks = item / (n_tiles * m_pairs);
+        const int kb0 = ks * kb_per;
+        const int kb1 = min(kb_total, kb0 + kb_per);
+        if (kb0 >= kb1) continue;
+        cb::mbar_wait(&tmem_empty[buf], acc_phase ^ 1);
+        cb::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          cb::mbar_wait(&full_bar[stage], phase);
+          cb::tc_fence_after();
+          const uint32_t sa = cb::smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+          const uint64_t adesc = cb::umma_smem_desc(sa, a_lbo, 1024);
+          const uint64_t bdesc = cb::umma_smem_desc(sb, b_lbo, 1024);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16_ss_2sm(tmem_d, adesc + (uint64_t)(k * a_kstep), bdesc + (uint64_t)(k * b_kstep), idesc,
+                             (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&tmem_full[buf]);
+        buf ^= 1;
+        if (buf == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs: their own 128 rows) =====================
+    const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
+    constexpr int CH = BLOCK_N / 64;
+    int buf = 0;
+    uint32_t acc_phase = 0;
+    for (int item = cluster_id; item < num_items; item += num_clusters) {
+      const int n_blk = item % n_tiles;
+      const int m_blk = (item / n_tiles) % m_pairs;
+      const int ks = item / (n_tiles * m_pairs);
+      const int kb0 = ks * kb_per;
+      const int kb1 = min(kb_total, kb0 + kb_per);
+      if (kb0 >= kb1) continue;
+      cb::mbar_wait(&tmem_full[buf], acc_phase);
+      cb::tc_fence_after();
+      const int row = m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M + q * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + half * (CH * 32);
+      const int nbase = n_blk * BLOCK_N + half * (CH * 32);
+      uint32_t r[2][32];
+      cb::tmem_ld_32x32b_x32(taddr, r[0]);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        cb::tmem_ld_wait();
+        if (c + 1 < CH) cb::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+        const int n0 = nbase + c * 32;
+        if (n0 < p.N) epilogue_store(p, r[c & 1], row, n0);
+      }
+      cb::tc_fence_before();
+      mbar_arrive_cluster(mapa_rank(cb::smem_u32(&tmem_empty[buf]), 0));
+      buf ^= 1;
+      if (buf == 0) acc_phase ^= 1;
+    }
+  }
+
+  cb::tc_fence_before();
+  cluster_sync_all();      // nobody leaves while the peer may still read this CTA's tiles or signal its barriers
+  if (warp == 2) {
+    cb::tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
   }
 }
 
@@ -421,6 +663,47 @@ static int launch_tc(const commu_gemm_args* a, const GemmKernelParams& p, cudaSt
   return 0;
 }
 
+static int launch_tc_2cta(const commu_gemm_args* a, const GemmKernelParams& p, cudaStream_t stream) {
+  using C = Cfg2;
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a->a_mn_major)
+    rc = cb_host::make_tmap_bf16_2d(&ta, a->a, a->k, a->m, a->lda, 64, BLOCK_M);
+  else
+    rc = cb_host::make_tmap_bf16_2d(&ta, a->a, a->m, a->k, a->lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!a->b_mn_major)
+    rc = cb_host::make_tmap_bf16_2d(&tb, a->b, a->k, a->n, a->ldb, 64, C::BLOCK_N / 2);
+  else
+    rc = cb_host::make_tmap_bf16_2d(&tb, a->b, a->n, a->k, a->ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int m_pairs = cb_host::ceil_div(a->m, 2 * BLOCK_M), n_tiles = cb_host::ceil_div(a->n, C::BLOCK_N);
+  const int items = m_pairs * n_tiles * p.split_k;
+  const int max_clusters = cb_host::num_sms() / 2;
+  const int clusters = items < max_clusters ? items : max_clusters;
+  cb_host::ProfScope prof(cb_host::PROF_GEMM, stream);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters, 1, 1);
+  cfg.blockDim = dim3(NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel, ta, tb, p));
+  cb_host::count_launch();
+  return 0;
+}
+
 extern "C" int commu_gemm_bf16(const commu_gemm_args* a, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CB_REQUIRE(a && a->a && a->b, "gemm: null operand");
@@ -472,6 +755,16 @@ extern "C" int commu_gemm_bf16(const commu_gemm_args* a, void* stream_) {
   CB_REQUIRE(al16(a->a) && al16(a->b) && (a->lda % 8 == 0) && (a->ldb % 8 == 0),
              "gemm: TMA needs 16-byte aligned operands and leading dims that are multiples of 8 "
              "(lda=%lld ldb=%lld)", (long long)a->lda, (long long)a->ldb);
+  // impl 2 forces the CTA-pair kernel, impl 3 the one-CTA kernel; impl 0 picks the pair kernel for wide outputs
+  // with at least two row tiles and a long reduction (COMMU_GEMM_2CTA=0 disables it)
+  static const int use_2cta = []() {
+    const char* e = getenv("COMMU_GEMM_2CTA");
+    return (e && e[0] == '0') ? 0 : 1;
+  }();
+  // (measured: +10-12 % where a split's reduction length is >= 1024, no gain on the epilogue-paced K = 512 shapes)
+  const int k_per_split = a->k / split;
+  if (a->impl == 2 || (a->impl == 0 && use_2cta && a->n > 128 && a->m > BLOCK_M && k_per_split >= 1024))
+    return launch_tc_2cta(a, p, stream);
   if (a->n > 128) return launch_tc<256>(a, p, stream);
   return launch_tc<128>(a, p, stream);
 }

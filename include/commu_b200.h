@@ -46,7 +46,9 @@ int commu_device_info(int* sm_major, int* sm_minor, int* num_sms);
  *   v = alpha*acc ; v += bias[n] ; v = relu(v) ; v *= (relu_mask[m,n] > 0) ; v += add_f32[m,n]
  *   out_bf16[m,n] = bf16(v) ; out_f32[m,n] = v (f32_atomic=0) or atomically += v (f32_atomic=1)
  * split_k > 1 partitions the k range over CTAs and requires f32_atomic = 1 and no bf16 output.
- * impl: 0 = tcgen05 kernel (product path), 1 = naive SIMT kernel (test cross-check only).
+ * impl: 0 = tcgen05 kernels (product path: the CTA-pair kernel, tcgen05 cta_group::2 on 256 x 256 tiles with the B tile
+ *       split across the two SMs of a TPC, for n > 128 and m > 128; else the one-CTA kernel), 1 = naive SIMT kernel
+ *       (test cross-check only), 2 / 3 = force the CTA-pair / the one-CTA tcgen05 kernel.
  * ------------------------------------------------------------------------------------------ */
 typedef struct {
   const void* a;

@@ -29,7 +29,7 @@ CASES = [
 
 
 @pytest.mark.parametrize("m,n,k,a_mn,b_mn,split", CASES)
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 def test_gemm_plain(m, n, k, a_mn, b_mn, split, impl):
     from commu import _native as nv
     torch.manual_seed(m * 7 + n * 3 + k)
@@ -53,7 +53,7 @@ def test_gemm_plain(m, n, k, a_mn, b_mn, split, impl):
         assert out[:, n:].abs().max().item() == 0.0
 
 
-@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("impl", [0, 1, 2, 3])
 def test_gemm_epilogue(impl):
     from commu import _native as nv
     torch.manual_seed(5)
