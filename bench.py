@@ -466,8 +466,8 @@ def main():
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--decode-only", action="store_true")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "native":
-        args.warmup = 3
+    if args.warmup < 3 and args.impl == "native" and os.environ.get("COMMU_BENCH_PROFILE") != "1":
+        args.warmup = 3          # (COMMU_BENCH_PROFILE=1: launch-list runs under ncu, whose numbers are never reported)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -17,6 +17,8 @@ dout = torch.randn(T, B, H * Dh, device=dev).bfloat16()
 delta = torch.empty(B, H, T, device=dev); dq = torch.empty_like(q); dkv = torch.empty_like(kv)
 dr = torch.zeros(K, H * Dh, device=dev); du = torch.zeros(H, Dh, device=dev); dvb = torch.zeros(H, Dh, device=dev)
 sc = 1 / math.sqrt(Dh)
+PD = float(os.environ.get("DROPATT", "0.1"))     # the bench default (reference attention_dropout 0.1)
+nv.call("commu_relattn_set_dropout", PD, 0x1234567)
 for it in range(2):
     nv.call("commu_relattn_fwd_tc", q, H * Dh, kv, kv[:, :, H * Dh:], 2 * H * Dh, r, H * Dh, K, u, vb, None,
             T, M, B, H, 0, T, sc, out, H * Dh, lse, qu, qv)
