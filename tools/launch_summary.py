@@ -1,5 +1,5 @@
 """Condenses an ncu launch list (gpu__time_duration.sum per launch) into per-kernel totals and shares.
-usage: python tools/launch_summary.py launches.csv [out.md] [first_id]   (launches with ID < first_id are ignored)"""
+usage: python tools/launch_summary.py launches.csv [out.md] [first_id [last_id]]   (only launches with first_id <= ID < last_id)"""
 import csv, sys
 from collections import defaultdict
 rows = list(csv.reader(open(sys.argv[1])))
@@ -8,8 +8,9 @@ hdr, data = rows[hi], rows[hi + 1:]
 ki, vi, gi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Metric Unit")
 agg = defaultdict(list)
 first_id = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+last_id = int(sys.argv[4]) if len(sys.argv) > 4 else 1 << 60
 for r in data:
-    if len(r) <= vi or int(r[0]) < first_id:
+    if len(r) <= vi or not (first_id <= int(r[0]) < last_id):
         continue
     v = float(r[vi].replace(",", ""))
     v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[ui], 1e-3)
