@@ -31,6 +31,7 @@ class GemmArgs(ctypes.Structure):
         ("out_bf16", c_void_p), ("ld_out_bf16", c_int64),
         ("out_f32", c_void_p), ("ld_out_f32", c_int64),
         ("f32_atomic", c_int), ("impl", c_int),
+        ("drop_p", c_float), ("drop_seed", ctypes.c_uint64),
     ]
 
 
@@ -120,7 +121,8 @@ def stream_ptr():
 
 def gemm(a, b, *, m, n, k, lda=None, ldb=None, a_mn=False, b_mn=False, split_k=1, alpha=1.0,
          bias=None, relu=False, relu_mask=None, ld_mask=0, add_f32=None, ld_add=0,
-         out_bf16=None, ld_out_bf16=0, out_f32=None, ld_out_f32=0, f32_atomic=False, impl=0):
+         out_bf16=None, ld_out_bf16=0, out_f32=None, ld_out_f32=0, f32_atomic=False, impl=0,
+         drop_p=0.0, drop_seed=0):
     """C[m,n] = alpha * sum_k A[m,k] B[n,k] with the fused epilogue of commu_gemm_bf16."""
     args = GemmArgs()
     args.a = a.data_ptr(); args.lda = lda if lda is not None else a.stride(0); args.a_mn_major = int(a_mn)
@@ -140,6 +142,8 @@ def gemm(a, b, *, m, n, k, lda=None, ldb=None, a_mn=False, b_mn=False, split_k=1
     args.ld_out_f32 = ld_out_f32 or (out_f32.stride(0) if out_f32 is not None else 0)
     args.f32_atomic = int(f32_atomic)
     args.impl = impl
+    args.drop_p = drop_p
+    args.drop_seed = drop_seed & 0xFFFFFFFFFFFFFFFF
     check(lib().commu_gemm_bf16(ctypes.byref(args), stream_ptr()))
 
 

@@ -249,11 +249,10 @@ class NativeLM:
                     S["u"], S["vb"], reset_u8, T, M, B, self.H, int(bool(same_length)), shift, scale,
                     av, self.hd, lse, qu, qv)
             z1 = torch.empty(rows, self.dp, device=dev)
-            if pd > 0:   # attn_out = self.drop(self.o_net(attn_vec)); w + attn_out  (model.py:348-352)
-                nv.gemm(av, s["wo"], m=rows, n=self.dp, k=self.hd, out_f32=z1)
-                self._drop(z1, rows, self.dp, pd, site_seed(dbase, l, SITE_ATTN_OUT), res=x, out_f32=z1)
-            else:
-                nv.gemm(av, s["wo"], m=rows, n=self.dp, k=self.hd, add_f32=x, out_f32=z1)
+            # attn_out = self.drop(self.o_net(attn_vec)); w + attn_out  (model.py:348-352): dropout and residual are the
+            # GEMM epilogue
+            nv.gemm(av, s["wo"], m=rows, n=self.dp, k=self.hd, add_f32=x, out_f32=z1, drop_p=pd,
+                    drop_seed=site_seed(dbase, l, SITE_ATTN_OUT) if pd > 0 else 0)
             pre = "layers.%d." % l
             y1 = torch.empty(rows, self.dp, device=dev)
             y1b = torch.empty(rows, self.dp, device=dev, dtype=bf)
@@ -263,14 +262,12 @@ class NativeLM:
                     self.P[pre + "dec_attn.layer_norm.bias"], self.d, self.dp, 1e-5, rows, y1, self.dp,
                     y1b, self.dp, mean1, rstd1)
             hdn = torch.empty(rows, self.dip, device=dev, dtype=bf)
-            nv.gemm(y1b, s["w1"], m=rows, n=self.dip, k=self.dp, bias=s["b1"], relu=True, out_bf16=hdn)
+            # Linear, ReLU, Dropout, Linear, Dropout; inp + core_out  (model.py:163-179): both dropouts in the epilogues
+            nv.gemm(y1b, s["w1"], m=rows, n=self.dip, k=self.dp, bias=s["b1"], relu=True, out_bf16=hdn, drop_p=pd,
+                    drop_seed=site_seed(dbase, l, SITE_FF_HID) if pd > 0 else 0)
             z2 = torch.empty(rows, self.dp, device=dev)
-            if pd > 0:   # Linear, ReLU, Dropout, Linear, Dropout; inp + core_out  (model.py:163-179)
-                self._drop(hdn, rows, self.dip, pd, site_seed(dbase, l, SITE_FF_HID), out_bf16=hdn)
-                nv.gemm(hdn, s["w2"], m=rows, n=self.dp, k=self.dip, bias=s["b2"], out_f32=z2)
-                self._drop(z2, rows, self.dp, pd, site_seed(dbase, l, SITE_FF_OUT), res=y1, out_f32=z2)
-            else:
-                nv.gemm(hdn, s["w2"], m=rows, n=self.dp, k=self.dip, bias=s["b2"], add_f32=y1, out_f32=z2)
+            nv.gemm(hdn, s["w2"], m=rows, n=self.dp, k=self.dip, bias=s["b2"], add_f32=y1, out_f32=z2, drop_p=pd,
+                    drop_seed=site_seed(dbase, l, SITE_FF_OUT) if pd > 0 else 0)
             nxt = new_cat(l + 1) if l + 1 < self.L else torch.empty(krows, self.dp, device=dev, dtype=bf)
             if l + 1 == self.L and M > 0:
                 nxt[: M * B].copy_(mems.bufs[self.L])

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include "api_common.h"
 #include "common.cuh"
+#include "dropout.cuh"
 
 namespace {
 
@@ -44,6 +45,8 @@ struct GemmKernelParams {
   long long ld_out_f32;
   int f32_atomic;
   int vec_ok;  // all leading dims / bases allow 16-byte vector stores
+  uint32_t drop_thr2, drop_ka, drop_kb;   // drop_thr2 != 0: inverted dropout of the result (counter-based mask)
+  float drop_inv;
 };
 
 template <int BLOCK_N>
@@ -56,6 +59,7 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+template <bool DROP>
 __device__ __forceinline__ void epilogue_store(const GemmKernelParams& p, const uint32_t (&r)[32],
                                                int row, int n0) {
   if (row >= p.M) return;
@@ -88,6 +92,18 @@ __device__ __forceinline__ void epilogue_store(const GemmKernelParams& p, const 
     } else {
       for (int i = 0; i < 32; ++i)
         if (n0 + i < p.N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
+    }
+  }
+  if (DROP) {   // same (seed, row, column) -> keep function as dropout.cu
+    const drop::Keys dk = drop::row_keys(p.drop_ka, p.drop_kb, (uint32_t)row);
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+      const uint2 rnd = drop::rand64((uint32_t)((n0 >> 2) + c4), dk);
+      const uint32_t f0 = drop::keep_flags(rnd.x, p.drop_thr2), f1 = drop::keep_flags(rnd.y, p.drop_thr2);
+      v[c4 * 4 + 0] = (f0 & 0x8000u) ? v[c4 * 4 + 0] * p.drop_inv : 0.f;
+      v[c4 * 4 + 1] = (f0 & 0x80000000u) ? v[c4 * 4 + 1] * p.drop_inv : 0.f;
+      v[c4 * 4 + 2] = (f1 & 0x8000u) ? v[c4 * 4 + 2] * p.drop_inv : 0.f;
+      v[c4 * 4 + 3] = (f1 & 0x80000000u) ? v[c4 * 4 + 3] * p.drop_inv : 0.f;
     }
   }
   if (p.add_f32) {
@@ -148,7 +164,7 @@ __device__ __forceinline__ void epilogue_store(const GemmKernelParams& p, const 
   }
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool DROP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmKernelParams p) {
@@ -304,7 +320,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         cb::tmem_ld_wait();
         if (c + 1 < CH) cb::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
         const int n0 = nbase + c * 32;
-        if (n0 < p.N) epilogue_store(p, r[c & 1], row, n0);
+        if (n0 < p.N) epilogue_store<DROP>(p, r[c & 1], row, n0);
       }
       cb::tc_fence_before();
       cb::mbar_arrive(&tmem_empty[buf]);
@@ -383,6 +399,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmKernelParams p) {
@@ -540,7 +557,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         cb::tmem_ld_wait();
         if (c + 1 < CH) cb::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
         const int n0 = nbase + c * 32;
-        if (n0 < p.N) epilogue_store(p, r[c & 1], row, n0);
+        if (n0 < p.N) epilogue_store<DROP>(p, r[c & 1], row, n0);
       }
       cb::tc_fence_before();
       mbar_arrive_cluster(mapa_rank(cb::smem_u32(&tmem_empty[buf]), 0));
@@ -632,7 +649,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
 }
 }  // namespace cb_host
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool DROP>
 static int launch_tc(const commu_gemm_args* a, const GemmKernelParams& p, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
   CUtensorMap ta, tb;
@@ -649,7 +666,7 @@ static int launch_tc(const commu_gemm_args* a, const GemmKernelParams& p, cudaSt
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N>,
+    CB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, DROP>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
@@ -657,12 +674,13 @@ static int launch_tc(const commu_gemm_args* a, const GemmKernelParams& p, cudaSt
   const int items = m_tiles * n_tiles * p.split_k;
   const int grid = items < cb_host::num_sms() ? items : cb_host::num_sms();
   cb_host::ProfScope prof(cb_host::PROF_GEMM, stream);
-  gemm_tcgen05_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_tcgen05_kernel<BLOCK_N, DROP><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
+template <bool DROP>
 static int launch_tc_2cta(const commu_gemm_args* a, const GemmKernelParams& p, cudaStream_t stream) {
   using C = Cfg2;
   CUtensorMap ta, tb;
@@ -679,7 +697,7 @@ static int launch_tc_2cta(const commu_gemm_args* a, const GemmKernelParams& p, c
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int m_pairs = cb_host::ceil_div(a->m, 2 * BLOCK_M), n_tiles = cb_host::ceil_div(a->n, C::BLOCK_N);
@@ -699,7 +717,7 @@ static int launch_tc_2cta(const commu_gemm_args* a, const GemmKernelParams& p, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel, ta, tb, p));
+  CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<DROP>, ta, tb, p));
   cb_host::count_launch();
   return 0;
 }
@@ -737,6 +755,15 @@ extern "C" int commu_gemm_bf16(const commu_gemm_args* a, void* stream_) {
   p.out_f32 = a->out_f32;
   p.ld_out_f32 = a->ld_out_f32;
   p.f32_atomic = a->f32_atomic;
+  p.drop_thr2 = 0; p.drop_ka = p.drop_kb = 0; p.drop_inv = 1.f;
+  if (a->drop_p > 0.f) {
+    CB_REQUIRE(a->drop_p < 1.f && split == 1 && a->impl != 1, "gemm: fused dropout needs 0 < p < 1, no split-k, a tcgen05 kernel");
+    const uint32_t thr = drop::thr15_of(a->drop_p);
+    p.drop_thr2 = thr * 0x00010001u;
+    p.drop_inv = 1.f / (1.f - (float)thr / 32768.f);
+    p.drop_ka = (uint32_t)a->drop_seed;
+    p.drop_kb = (uint32_t)(a->drop_seed >> 32);
+  }
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = 1;
   if (p.out_bf16 && (!al16(p.out_bf16) || (p.ld_out_bf16 % 8))) p.vec_ok = 0;
@@ -764,7 +791,7 @@ extern "C" int commu_gemm_bf16(const commu_gemm_args* a, void* stream_) {
   // (measured: +10-12 % where a split's reduction length is >= 1024, no gain on the epilogue-paced K = 512 shapes)
   const int k_per_split = a->k / split;
   if (a->impl == 2 || (a->impl == 0 && use_2cta && a->n > 128 && a->m > BLOCK_M && k_per_split >= 1024))
-    return launch_tc_2cta(a, p, stream);
-  if (a->n > 128) return launch_tc<256>(a, p, stream);
-  return launch_tc<128>(a, p, stream);
+    return p.drop_thr2 ? launch_tc_2cta<true>(a, p, stream) : launch_tc_2cta<false>(a, p, stream);
+  if (a->n > 128) return p.drop_thr2 ? launch_tc<256, true>(a, p, stream) : launch_tc<256, false>(a, p, stream);
+  return p.drop_thr2 ? launch_tc<128, true>(a, p, stream) : launch_tc<128, false>(a, p, stream);
 }

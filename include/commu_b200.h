@@ -43,7 +43,7 @@ int commu_device_info(int* sm_major, int* sm_minor, int* num_sms);
  *   a_mn_major = 1: A stored [k, m] row-major (m contiguous), lda = row stride. (wgrad operands)
  *   same for B with n.
  * Epilogue (all optional, applied in this order):
- *   v = alpha*acc ; v += bias[n] ; v = relu(v) ; v *= (relu_mask[m,n] > 0) ; v += add_f32[m,n]
+ *   v = alpha*acc ; v += bias[n] ; v = relu(v) ; v *= (relu_mask[m,n] > 0) ; v = dropout(v) ; v += add_f32[m,n]
  *   out_bf16[m,n] = bf16(v) ; out_f32[m,n] = v (f32_atomic=0) or atomically += v (f32_atomic=1)
  * split_k > 1 partitions the k range over CTAs and requires f32_atomic = 1 and no bf16 output.
  * impl: 0 = tcgen05 kernels (product path: the CTA-pair kernel, tcgen05 cta_group::2 on 256 x 256 tiles with the B tile
@@ -72,6 +72,11 @@ typedef struct {
   int64_t ld_out_f32;
   int f32_atomic;
   int impl;
+  /* inverted dropout of the GEMM result (nn.Dropout after o_net / CoreNet.1 / CoreNet.3, model.py:349, 166-168):
+   * with drop_p > 0, after bias / relu and before add_f32:  v = keep(drop_seed, m, n) ? v / keep_prob : 0, the same
+   * counter-based mask as commu_dropout (element (row m, column n) of the [m, n] result). */
+  float drop_p;
+  uint64_t drop_seed;
 } commu_gemm_args;
 
 int commu_gemm_bf16(const commu_gemm_args* args, void* stream);

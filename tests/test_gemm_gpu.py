@@ -118,3 +118,32 @@ def test_gemm_perf(out_dir):
     with open(os.path.join(out_dir, "gemm_perf.json"), "w") as f:
         json.dump(res, f, indent=1)
     print(json.dumps(res))
+
+
+@pytest.mark.parametrize("impl", [2, 3])
+def test_gemm_dropout_epilogue(impl):
+    """Fused inverted dropout of the GEMM result (bias -> relu -> dropout -> residual): the mask is the counter-based
+    keep function of commu_dropout, restated in numpy in tests/helpers.py."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import drop_keep_mask, drop_keep_prob
+    from commu import _native as nv
+    torch.manual_seed(3)
+    dev = "cuda"
+    m, n, k, p_drop, seed = 300, 320, 256, 0.1, 0x1234_5678_9ABC_DEF1
+    a = torch.randn(m, k, device=dev).bfloat16()
+    b = torch.randn(n, k, device=dev).bfloat16()
+    bias = torch.randn(n, device=dev)
+    add = torch.randn(m, n, device=dev)
+    keep = drop_keep_mask(seed, m, n, p_drop).to(dev)
+    ref = torch.relu(a.float() @ b.float().t() + bias) * keep / drop_keep_prob(p_drop) + add
+    out = torch.empty(m, n, device=dev)
+    outb = torch.empty(m, n, device=dev, dtype=torch.bfloat16)
+    nv.gemm(a, b, m=m, n=n, k=k, bias=bias, relu=True, add_f32=add, out_f32=out, out_bf16=outb, impl=impl,
+            drop_p=p_drop, drop_seed=seed)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    assert (out - ref).abs().max().item() <= 2e-3 * scale + 1e-3
+    assert (outb.float() - ref).abs().max().item() <= 1e-2 * scale
+    frac = 1.0 - keep.float().mean().item()
+    assert abs(frac - p_drop) < 0.01
