@@ -56,43 +56,82 @@ struct Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + EPI_WARPS * 3072 /*epilogue staging + bias*/;
 };
 
+// One warp's 32 rows x 32 columns of the accumulator (lane = row).  The fused element-wise part runs with a row per
+// lane; the result is then transposed through a 2.5 KB per-warp staging tile so that the global accesses of a warp
+// cover whole 64-byte row segments (a row per lane made every 16-byte store instruction touch 32 different lines:
+// the epilogue was bound by the LSU, not by its warps).
+constexpr int EPI_PITCH = 80;                          // bytes per staged row: 64 data + 16 pad (conflict-free 16 B accesses)
+constexpr int EPI_STAGE_BYTES = 32 * EPI_PITCH;        // per epilogue warp
+constexpr int EPI_BIAS_BYTES = 512;                    // the warp's 128 bias values of the current tile
+constexpr int EPI_WARP_BYTES = EPI_STAGE_BYTES + EPI_BIAS_BYTES;
+
+// Stages the bias of the 128 columns this epilogue warp owns in the current tile (one guarded load per lane and
+// value, issued while the warp still waits for the accumulator; the chunks then read it back as shared-memory
+// broadcasts: 32 scalar __ldg per chunk went to L2 every time, the 28 KB of L1 left beside the smem ring being
+// thrashed by the output stream - 35 % of the executed instructions and 32 % of the stall samples of the FF1 GEMM).
+__device__ __forceinline__ void epilogue_stage_bias(const GemmKernelParams& p, int nbase, int lane, unsigned char* ws) {
+  if (!p.bias) return;
+  float4 bv;
+  const int c = nbase + lane * 4;
+  bv.x = c + 0 < p.N ? __ldg(p.bias + c + 0) : 0.f;
+  bv.y = c + 1 < p.N ? __ldg(p.bias + c + 1) : 0.f;
+  bv.z = c + 2 < p.N ? __ldg(p.bias + c + 2) : 0.f;
+  bv.w = c + 3 < p.N ? __ldg(p.bias + c + 3) : 0.f;
+  __syncwarp();
+  *reinterpret_cast<float4*>(ws + EPI_STAGE_BYTES + lane * 16) = bv;
+  __syncwarp();
+}
+
+// chunk: index of the 32-column chunk inside the warp's 128 columns (selects the staged bias values)
 template <bool DROP>
 __device__ __forceinline__ void epilogue_store(const GemmKernelParams& p, const uint32_t (&r)[32],
-                                               int row, int n0) {
-  if (row >= p.M) return;
-  const bool full = (n0 + 32 <= p.N) && p.vec_ok;
+                                               int row0, int lane, int n0, int chunk, unsigned char* stage) {
+  const int row = row0 + lane;
+  const bool rowok = row < p.M;
+  const bool full = (n0 + 32 <= p.N) && p.vec_ok;      // warp-uniform
+  const int tr = lane >> 2, tc = lane & 3;             // transposed role: rows tr + 8 i, 16-byte chunk tc of a staged row
+  const bool path_a = p.out_bf16 && !p.add_f32 && !p.out_f32;
+  // operands of the transposed (coalesced) phase do not depend on the accumulator: fetch them first
+  uint4 mk_a[4];
+  float4 ad[2][4];
+  uint2 mk_b[2][4];
+  if (full) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long rr = row0 + tr + 8 * i;
+      const bool ok = rr < p.M;
+      if (path_a) {
+        mk_a[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+        if (p.relu_mask && ok) mk_a[i] = __ldg(reinterpret_cast<const uint4*>(p.relu_mask + rr * p.ld_mask + n0 + tc * 8));
+      } else {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int col = n0 + hf * 16 + tc * 4;
+          ad[hf][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          mk_b[hf][i] = make_uint2(0x3f803f80u, 0x3f803f80u);
+          if (p.add_f32 && ok) ad[hf][i] = __ldg(reinterpret_cast<const float4*>(p.add_f32 + rr * p.ld_add + col));
+          if (p.relu_mask && ok) mk_b[hf][i] = __ldg(reinterpret_cast<const uint2*>(p.relu_mask + rr * p.ld_mask + col));
+        }
+      }
+    }
+  }
   float v[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
   if (p.bias) {
+    const float4* bs = reinterpret_cast<const float4*>(stage + EPI_STAGE_BYTES + chunk * 128);
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (n0 + i < p.N) v[i] += __ldg(p.bias + n0 + i);
+    for (int i = 0; i < 8; ++i) {
+      const float4 bq = bs[i];
+      v[i * 4 + 0] += bq.x; v[i * 4 + 1] += bq.y; v[i * 4 + 2] += bq.z; v[i * 4 + 3] += bq.w;
+    }
   }
   if (p.relu) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
-  }
-  if (p.relu_mask) {
-    const bf16* mrow = p.relu_mask + (long long)row * p.ld_mask + n0;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 q = __ldg(reinterpret_cast<const uint4*>(mrow) + i);
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (!(cb::bf16_lo(w[j]) > 0.f)) v[i * 8 + j * 2] = 0.f;
-          if (!(cb::bf16_hi(w[j]) > 0.f)) v[i * 8 + j * 2 + 1] = 0.f;
-        }
-      }
-    } else {
-      for (int i = 0; i < 32; ++i)
-        if (n0 + i < p.N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
-    }
   }
   if (DROP) {   // same (seed, row, column) -> keep function as dropout.cu
     const drop::Keys dk = drop::row_keys(p.drop_ka, p.drop_kb, (uint32_t)row);
@@ -106,59 +145,90 @@ __device__ __forceinline__ void epilogue_store(const GemmKernelParams& p, const 
       v[c4 * 4 + 3] = (f1 & 0x80000000u) ? v[c4 * 4 + 3] * p.drop_inv : 0.f;
     }
   }
-  if (p.add_f32) {
-    const float* arow = p.add_f32 + (long long)row * p.ld_add + n0;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float4 q = __ldg(reinterpret_cast<const float4*>(arow) + i);
-        v[i * 4 + 0] += q.x;
-        v[i * 4 + 1] += q.y;
-        v[i * 4 + 2] += q.z;
-        v[i * 4 + 3] += q.w;
-      }
-    } else {
+  if (!full) {       // ragged tile edge / unaligned buffers: a row per lane, scalar accesses
+    if (!rowok) return;
+    if (p.relu_mask) {
+      const bf16* mrow = p.relu_mask + (long long)row * p.ld_mask + n0;
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N && !(__bfloat162float(mrow[i]) > 0.f)) v[i] = 0.f;
+    }
+    if (p.add_f32) {
+      const float* arow = p.add_f32 + (long long)row * p.ld_add + n0;
       for (int i = 0; i < 32; ++i)
         if (n0 + i < p.N) v[i] += arow[i];
     }
-  }
-  if (p.out_bf16) {
-    bf16* orow = p.out_bf16 + (long long)row * p.ld_out_bf16 + n0;
-    if (full) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        uint4 q;
-        q.x = cb::pack_bf16(v[i * 8 + 0], v[i * 8 + 1]);
-        q.y = cb::pack_bf16(v[i * 8 + 2], v[i * 8 + 3]);
-        q.z = cb::pack_bf16(v[i * 8 + 4], v[i * 8 + 5]);
-        q.w = cb::pack_bf16(v[i * 8 + 6], v[i * 8 + 7]);
-        reinterpret_cast<uint4*>(orow)[i] = q;
-      }
-    } else {
+    if (p.out_bf16) {
+      bf16* orow = p.out_bf16 + (long long)row * p.ld_out_bf16 + n0;
       for (int i = 0; i < 32; ++i)
         if (n0 + i < p.N) orow[i] = __float2bfloat16_rn(v[i]);
     }
+    if (p.out_f32) {
+      float* orow = p.out_f32 + (long long)row * p.ld_out_f32 + n0;
+      for (int i = 0; i < 32; ++i)
+        if (n0 + i < p.N) {
+          if (p.f32_atomic) atomicAdd(orow + i, v[i]);
+          else orow[i] = v[i];
+        }
+    }
+    return;
   }
-  if (p.out_f32) {
-    float* orow = p.out_f32 + (long long)row * p.ld_out_f32 + n0;
-    if (p.f32_atomic) {
-      if (full) {
+  unsigned char* mine = stage + lane * EPI_PITCH;
+  if (path_a) {
+    // bf16 only: stage 32 columns (64 B per row), every store instruction writes 8 rows x 64 contiguous bytes
+    __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          cb::red_add_v4(orow + i * 4, v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-      } else {
-        for (int i = 0; i < 32; ++i)
-          if (n0 + i < p.N) atomicAdd(orow + i, v[i]);
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<uint4*>(mine + c * 16) =
+          make_uint4(cb::pack_bf16(v[c * 8 + 0], v[c * 8 + 1]), cb::pack_bf16(v[c * 8 + 2], v[c * 8 + 3]),
+                     cb::pack_bf16(v[c * 8 + 4], v[c * 8 + 5]), cb::pack_bf16(v[c * 8 + 6], v[c * 8 + 7]));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = tr + 8 * i;
+      uint4 q = *reinterpret_cast<const uint4*>(stage + rr * EPI_PITCH + tc * 16);
+      if (p.relu_mask) {   // keep where the saved activation is > 0 (positive bf16: sign clear and not zero)
+        const uint32_t w[4] = {mk_a[i].x, mk_a[i].y, mk_a[i].z, mk_a[i].w};
+        uint32_t* qq = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (!(cb::bf16_lo(w[j]) > 0.f)) qq[j] &= 0xFFFF0000u;
+          if (!(cb::bf16_hi(w[j]) > 0.f)) qq[j] &= 0x0000FFFFu;
+        }
       }
-    } else {
-      if (full) {
+      if (row0 + rr < p.M)
+        *reinterpret_cast<uint4*>(p.out_bf16 + (long long)(row0 + rr) * p.ld_out_bf16 + n0 + tc * 8) = q;
+    }
+    return;
+  }
+  // fp32 result (+ residual, + optional bf16 copy): two halves of 16 columns (64 B per row) through the staging tile
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          reinterpret_cast<float4*>(orow)[i] =
-              make_float4(v[i * 4], v[i * 4 + 1], v[i * 4 + 2], v[i * 4 + 3]);
-      } else {
-        for (int i = 0; i < 32; ++i)
-          if (n0 + i < p.N) orow[i] = v[i];
+  for (int hf = 0; hf < 2; ++hf) {
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      *reinterpret_cast<float4*>(mine + c * 16) =
+          make_float4(v[hf * 16 + c * 4], v[hf * 16 + c * 4 + 1], v[hf * 16 + c * 4 + 2], v[hf * 16 + c * 4 + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rr = tr + 8 * i;
+      if (row0 + rr >= p.M) continue;
+      float4 q = *reinterpret_cast<const float4*>(stage + rr * EPI_PITCH + tc * 16);
+      const long long col = n0 + hf * 16 + tc * 4;
+      if (p.relu_mask) {
+        if (!(cb::bf16_lo(mk_b[hf][i].x) > 0.f)) q.x = 0.f;
+        if (!(cb::bf16_hi(mk_b[hf][i].x) > 0.f)) q.y = 0.f;
+        if (!(cb::bf16_lo(mk_b[hf][i].y) > 0.f)) q.z = 0.f;
+        if (!(cb::bf16_hi(mk_b[hf][i].y) > 0.f)) q.w = 0.f;
+      }
+      q.x += ad[hf][i].x; q.y += ad[hf][i].y; q.z += ad[hf][i].z; q.w += ad[hf][i].w;
+      if (p.out_bf16)
+        *reinterpret_cast<uint2*>(p.out_bf16 + (long long)(row0 + rr) * p.ld_out_bf16 + col) =
+            make_uint2(cb::pack_bf16(q.x, q.y), cb::pack_bf16(q.z, q.w));
+      if (p.out_f32) {
+        float* o = p.out_f32 + (long long)(row0 + rr) * p.ld_out_f32 + col;
+        if (p.f32_atomic) cb::red_add_v4(o, q.x, q.y, q.z, q.w);
+        else *reinterpret_cast<float4*>(o) = q;
       }
     }
   }
@@ -298,6 +368,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
+    unsigned char* epi_stage = smem + C::STAGES * C::STAGE_BYTES + 256 + (warp - 4) * EPI_WARP_BYTES;
     constexpr int CH = BLOCK_N / 64;       // 32-column chunks per epilogue warp
     int buf = 0;
     uint32_t acc_phase = 0;
@@ -308,6 +379,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int kb0 = ks * kb_per;
       const int kb1 = min(kb_total, kb0 + kb_per);
       if (kb0 >= kb1) continue;
+      epilogue_stage_bias(p, n_blk * BLOCK_N + half * (CH * 32), lane, epi_stage);
       cb::mbar_wait(&tmem_full[buf], acc_phase);
       cb::tc_fence_after();
       const int row = m_blk * BLOCK_M + q * 32 + lane;
@@ -320,7 +392,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         cb::tmem_ld_wait();
         if (c + 1 < CH) cb::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
         const int n0 = nbase + c * 32;
-        if (n0 < p.N) epilogue_store<DROP>(p, r[c & 1], row, n0);
+        if (n0 < p.N) epilogue_store<DROP>(p, r[c & 1], row - lane, lane, n0, c, epi_stage);
       }
       cb::tc_fence_before();
       cb::mbar_arrive(&tmem_empty[buf]);
@@ -355,7 +427,7 @@ struct Cfg2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + EPI_WARPS * 3072;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -535,6 +607,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   } else if (warp >= 4) {
     // ===================== epilogue (both CTAs: their own 128 rows) =====================
     const int q = (warp - 4) & 3, half = (warp - 4) >> 2;
+    unsigned char* epi_stage = smem + C::STAGES * C::STAGE_BYTES + 256 + (warp - 4) * EPI_WARP_BYTES;
     constexpr int CH = BLOCK_N / 64;
     int buf = 0;
     uint32_t acc_phase = 0;
@@ -545,6 +618,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int kb0 = ks * kb_per;
       const int kb1 = min(kb_total, kb0 + kb_per);
       if (kb0 >= kb1) continue;
+      epilogue_stage_bias(p, n_blk * BLOCK_N + half * (CH * 32), lane, epi_stage);
       cb::mbar_wait(&tmem_full[buf], acc_phase);
       cb::tc_fence_after();
       const int row = m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M + q * 32 + lane;
@@ -557,7 +631,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         cb::tmem_ld_wait();
         if (c + 1 < CH) cb::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
         const int n0 = nbase + c * 32;
-        if (n0 < p.N) epilogue_store<DROP>(p, r[c & 1], row, n0);
+        if (n0 < p.N) epilogue_store<DROP>(p, r[c & 1], row - lane, lane, n0, c, epi_stage);
       }
       cb::tc_fence_before();
       mbar_arrive_cluster(mapa_rank(cb::smem_u32(&tmem_empty[buf]), 0));
