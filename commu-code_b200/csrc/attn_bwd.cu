@@ -231,19 +231,26 @@ __device__ __forceinline__ uint8_t* xpose_row_base(BwdSmem& sm, int which) {
 // ------------------------------------------------------------------------------------------------
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, long long ldo, const bf16* __restrict__ dout,
                                   long long lddo, int T, int B, int H, float* __restrict__ delta) {
-  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  // 8 lanes per (i, b, h) row of 64 values (16 bytes each), four rows per warp
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int part = threadIdx.x & 7;
   const long long total = (long long)T * B * H;
-  if (w >= total) return;
-  const int h = w % H;
-  const long long ib = w / H;  // i*B + b
+  const bool ok = w < total;
+  const long long wc = ok ? w : 0;
+  const int h = wc % H;
+  const long long ib = wc / H;  // i*B + b
   const int b = ib % B;
   const int i = ib / B;
-  const uint32_t a = *reinterpret_cast<const uint32_t*>(o + ib * ldo + h * DH + lane * 2);
-  const uint32_t d = *reinterpret_cast<const uint32_t*>(dout + ib * lddo + h * DH + lane * 2);
-  float s = cb::bf16_lo(a) * cb::bf16_lo(d) + cb::bf16_hi(a) * cb::bf16_hi(d);
-  s = cb::warp_sum(s);
-  if (lane == 0) delta[((long long)b * H + h) * T + i] = s;
+  const uint4 a = *reinterpret_cast<const uint4*>(o + ib * ldo + h * DH + part * 8);
+  const uint4 d = *reinterpret_cast<const uint4*>(dout + ib * lddo + h * DH + part * 8);
+  float s = cb::bf16_lo(a.x) * cb::bf16_lo(d.x) + cb::bf16_hi(a.x) * cb::bf16_hi(d.x);
+  s += cb::bf16_lo(a.y) * cb::bf16_lo(d.y) + cb::bf16_hi(a.y) * cb::bf16_hi(d.y);
+  s += cb::bf16_lo(a.z) * cb::bf16_lo(d.z) + cb::bf16_hi(a.z) * cb::bf16_hi(d.z);
+  s += cb::bf16_lo(a.w) * cb::bf16_lo(d.w) + cb::bf16_hi(a.w) * cb::bf16_hi(d.w);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (ok && part == 0) delta[((long long)b * H + h) * T + i] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -596,8 +603,10 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
   }
   cb_host::ProfScope prof(cb_host::PROF_ATTN_BWD, stream);
   {
-    const long long warps = (long long)T * B * H;
-    attn_delta_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(
+    const long long rows8 = (long long)T * B * H * 8;      // 8 lanes per row
+    CB_REQUIRE(ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (reinterpret_cast<uintptr_t>(dout) & 15) == 0,
+               "relattn_bwd: out / dout must be 16-byte aligned with leading dims that are multiples of 8");
+    attn_delta_kernel<<<(unsigned)((rows8 + 255) / 256), 256, 0, stream>>>(
         (const bf16*)out, ldo, (const bf16*)dout, lddo, T, B, H, delta_ws);
   }
   const int Ktot = T + M;

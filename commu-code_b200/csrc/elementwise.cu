@@ -214,6 +214,47 @@ __global__ void colsum_bf16_kernel(const bf16* __restrict__ x, long long ld, int
   atomicAdd(out + c, s);
 }
 
+// The same with 8 columns (16 bytes) per thread: a CTA is 32 column groups x 8 row lanes, four rows in flight per
+// thread, the row lanes are reduced through shared memory so that a CTA issues one atomic per column (the scalar
+// version read 2 bytes per thread and row: 67 us for the 134 MB FF hidden gradient = 2 TB/s).
+__global__ void __launch_bounds__(256) colsum_bf16_v8_kernel(const bf16* __restrict__ x, long long ld, int ncols, long long rows,
+                                                             long long rows_per_block, float* __restrict__ out) {
+  __shared__ float red[8][32][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 8;
+  const bool live = c < ncols;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  auto acc = [&](const uint4 a) {
+    s[0] += cb::bf16_lo(a.x); s[1] += cb::bf16_hi(a.x); s[2] += cb::bf16_lo(a.y); s[3] += cb::bf16_hi(a.y);
+    s[4] += cb::bf16_lo(a.z); s[5] += cb::bf16_hi(a.z); s[6] += cb::bf16_lo(a.w); s[7] += cb::bf16_hi(a.w);
+  };
+  if (live) {
+    long long r = r0 + ty;
+    const bf16* px = x + r * ld + c;
+    for (; r + 24 < r1; r += 32, px += 32 * ld) {
+      const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(px));
+      const uint4 a1 = __ldg(reinterpret_cast<const uint4*>(px + 8 * ld));
+      const uint4 a2 = __ldg(reinterpret_cast<const uint4*>(px + 16 * ld));
+      const uint4 a3 = __ldg(reinterpret_cast<const uint4*>(px + 24 * ld));
+      acc(a0); acc(a1); acc(a2); acc(a3);
+    }
+    for (; r < r1; r += 8, px += 8 * ld) acc(__ldg(reinterpret_cast<const uint4*>(px)));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx][j] = s[j];
+  __syncthreads();
+  // 256 threads -> 256 columns of the CTA
+  const int col = threadIdx.x;             // column inside the CTA's 256
+  const int gx = col >> 3, gj = col & 7;
+  float t = 0.f;
+#pragma unroll
+  for (int y = 0; y < 8; ++y) t += red[y][gx][gj];
+  const int cc = blockIdx.x * 256 + col;
+  if (cc < ncols) atomicAdd(out + cc, t);
+}
+
 // ---------------------------------------------------------------------------------------------
 // fp32 master weight [R, C] -> bf16 shadow with segment padding on rows / cols, optional transpose.
 //   dst_r = (r / rseg) * rseg_pad + r % rseg,  dst_c likewise.  Padding is never written (the
@@ -406,6 +447,17 @@ int commu_nll_bwd(const float* logits, int64_t ld, int V, int Vp, const float* l
 
 int commu_colsum_bf16(const void* x, int64_t ld, int ncols, int64_t rows, float* out, void* stream) {
   CB_REQUIRE(x && out && rows > 0 && ncols > 0, "colsum: bad args");
+  if (ncols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int bxv = cb_host::ceil_div(ncols, 256);
+    int byv = (cb_host::num_sms() * 4) / bxv;
+    if (byv < 1) byv = 1;
+    if ((long long)byv * 32 > rows) byv = (int)((rows + 31) / 32);
+    const long long rpbv = (rows + byv - 1) / byv;
+    colsum_bf16_v8_kernel<<<dim3(bxv, byv), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, ld, ncols, rows, rpbv, out);
+    cb_host::count_launch();
+    CB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int bx = cb_host::ceil_div(ncols, 128);
   int by = (cb_host::num_sms() * 4) / bx;
   if (by < 1) by = 1;

@@ -261,6 +261,10 @@ def test_cast_colsum_adam():
     out = torch.zeros(130, device=dev)
     nv.call("commu_colsum_bf16", x, 136, 130, 1000, out)
     assert (out - x.float()[:, :130].sum(0)).abs().max() < 1e-2
+    x8 = torch.randn(1003, 520, device=dev).bfloat16()          # vector path: 8 columns per thread, row tail
+    out8 = torch.ones(512, device=dev)
+    nv.call("commu_colsum_bf16", x8, 520, 512, 1003, out8)
+    assert (out8 - 1 - x8.float()[:, :512].sum(0)).abs().max() < 2e-2
     # clip + adam vs torch
     n = 100003
     n_al = (n + 3) // 4 * 4
