@@ -179,7 +179,7 @@ SIGNATURES = {
     "commu_embed_bwd": [P, P, L, I, F, L, P, P],
     "commu_pos_table": [P, I, I, I, I, P, P, P],
     "commu_layernorm_fwd": [P, L, P, P, I, I, F, L, P, L, P, L, P, P, P],
-    "commu_layernorm_bwd": [P, L, P, L, P, P, P, I, I, L, P, L, P, L, P, P, P],
+    "commu_layernorm_bwd": [P, L, P, L, P, P, P, I, I, L, P, L, P, L, P, P, F, ctypes.c_uint64, P],
     "commu_nll_fwd": [P, L, I, P, L, P, P, P],
     "commu_nll_bwd": [P, L, I, I, P, P, P, L, P, L, P],
     "commu_colsum_bf16": [P, L, I, L, P, P],

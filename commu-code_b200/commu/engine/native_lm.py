@@ -391,9 +391,9 @@ class NativeLM:
             dz2b = torch.empty(rows, self.dp, device=dev, dtype=bf)
             nv.call("commu_layernorm_bwd", dx, self.dp, a["z2"], self.dp, a["mean2"], a["rstd2"],
                     self.P[pre + "pos_ff.layer_norm.weight"], d, self.dp, rows, dz2, self.dp, dz2b, self.dp,
-                    grads[pre + "pos_ff.layer_norm.weight"], grads[pre + "pos_ff.layer_norm.bias"])
-            if pd > 0:   # gradient through the FF output dropout (the residual branch keeps dz2)
-                self._drop(dz2, rows, self.dp, pd, site_seed(dbase, l, SITE_FF_OUT), out_bf16=dz2b)
+                    grads[pre + "pos_ff.layer_norm.weight"], grads[pre + "pos_ff.layer_norm.bias"],
+                    # the bf16 copy carries the gradient through the FF output dropout; the residual branch keeps dz2
+                    float(pd), site_seed(dbase, l, SITE_FF_OUT) if pd > 0 else 0)
             nv.call("commu_colsum_bf16", dz2b, self.dp, d, rows, grads[pre + "pos_ff.CoreNet.3.bias"])
             self._wgrad(dz2b, a["hdn"], self.dp, self.dip, rows, grads[pre + "pos_ff.CoreNet.3.weight"])
             dpre = torch.empty(rows, self.dip, device=dev, dtype=bf)
@@ -409,9 +409,9 @@ class NativeLM:
             dz1b = dz2b
             nv.call("commu_layernorm_bwd", dy1, self.dp, a["z1"], self.dp, a["mean1"], a["rstd1"],
                     self.P[pre + "dec_attn.layer_norm.weight"], d, self.dp, rows, dz1, self.dp, dz1b, self.dp,
-                    grads[pre + "dec_attn.layer_norm.weight"], grads[pre + "dec_attn.layer_norm.bias"])
-            if pd > 0:   # gradient through the attention output dropout (the residual branch keeps dz1)
-                self._drop(dz1, rows, self.dp, pd, site_seed(dbase, l, SITE_ATTN_OUT), out_bf16=dz1b)
+                    grads[pre + "dec_attn.layer_norm.weight"], grads[pre + "dec_attn.layer_norm.bias"],
+                    # the bf16 copy carries the gradient through the attention output dropout
+                    float(pd), site_seed(dbase, l, SITE_ATTN_OUT) if pd > 0 else 0)
             self._wgrad(dz1b, a["av"], self.dp, self.hd, rows, grads[pre + "dec_attn.o_net.weight"],
                         cseg=Dh, cseg_pad=64)
             dav = torch.empty(rows, self.hd, device=dev, dtype=bf)

@@ -4,6 +4,7 @@
 // the fused clip+Adam update.  All are vectorised, coalesced, grid sized from the SM count.
 #include "api_common.h"
 #include "common.cuh"
+#include "dropout.cuh"
 #include <math.h>
 
 namespace {
@@ -149,6 +150,157 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, long long lddy, cons
   for (int i = 0; i < MAXC; ++i) {
     atomicAdd(&sh_g[lane + 32 * i], acc_g[i]);
     atomicAdd(&sh_b[lane + 32 * i], acc_b[i]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    atomicAdd(dgamma + c, sh_g[c]);
+    atomicAdd(dbeta + c, sh_b[c]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vectorised LayerNorm (d, dp, leading dims multiples of 4, 16-byte aligned rows): one warp per row, the row lives in
+// registers as float4 (a lane owns columns 4*(lane + 32 i) .. +3), so z / dy are read once with 16-byte accesses
+// (the scalar kernels above read z three times with 4-byte loads: 41 / 51 us per launch = 63-70 % of HBM peak).
+// The backward can apply the inverted dropout of the sub-block output to its bf16 copy (the GEMM operand of the
+// sub-block's weight / input gradients); the fp32 copy (residual branch) stays undropped.
+// ---------------------------------------------------------------------------------------------
+template <int MAXV>
+__global__ void ln_fwd_v4_kernel(const float* __restrict__ z, long long ldz, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, int d, int dp, float eps, long long rows,
+                                 float* __restrict__ y_f32, long long ldy, bf16* __restrict__ y_bf16, long long ldyb,
+                                 float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float4 gm[MAXV], bt[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = 4 * (lane + 32 * i);
+    gm[i] = bt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < d) {
+      gm[i] = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      bt[i] = __ldg(reinterpret_cast<const float4*>(beta + c));
+    }
+  }
+  for (long long r = warp; r < rows; r += nwarps) {
+    float4 v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < d) v[i] = *reinterpret_cast<const float4*>(z + r * ldz + c);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = cb::warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (4 * (lane + 32 * i) < d) {
+        const float a0 = v[i].x - mean, a1 = v[i].y - mean, a2 = v[i].z - mean, a3 = v[i].w - mean;
+        q += (a0 * a0 + a1 * a1) + (a2 * a2 + a3 * a3);
+      }
+    }
+    const float rstd = rsqrtf(cb::warp_sum(q) / d + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (c < dp) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < d) {
+          o.x = (v[i].x - mean) * rstd * gm[i].x + bt[i].x;
+          o.y = (v[i].y - mean) * rstd * gm[i].y + bt[i].y;
+          o.z = (v[i].z - mean) * rstd * gm[i].z + bt[i].z;
+          o.w = (v[i].w - mean) * rstd * gm[i].w + bt[i].w;
+        }
+        if (y_f32) *reinterpret_cast<float4*>(y_f32 + r * ldy + c) = o;
+        if (y_bf16) *reinterpret_cast<uint2*>(y_bf16 + r * ldyb + c) = make_uint2(cb::pack_bf16(o.x, o.y), cb::pack_bf16(o.z, o.w));
+      }
+    }
+  }
+}
+
+template <int MAXV>
+__global__ void ln_bwd_v4_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ z,
+                                 long long ldz, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                 const float* __restrict__ gamma, int d, int dp, long long rows,
+                                 float* __restrict__ dz_f32, long long lddz, bf16* __restrict__ dz_bf16,
+                                 long long lddzb, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                 uint32_t drop_thr2, uint32_t drop_ka, uint32_t drop_kb, float drop_inv) {
+  __shared__ float sh_g[128 * MAXV];
+  __shared__ float sh_b[128 * MAXV];
+  for (int c = threadIdx.x; c < 128 * MAXV; c += blockDim.x) sh_g[c] = sh_b[c] = 0.f;
+  __syncthreads();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  float4 gm[MAXV], acc_g[MAXV], acc_b[MAXV];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = 4 * (lane + 32 * i);
+    gm[i] = c < d ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc_g[i] = acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long long r = warp; r < rows; r += nwarps) {
+    const float mu = mean[r], rs = rstd[r];
+    float4 xh[MAXV], g[MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      xh[i] = g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < d) {
+        const float4 dyv = *reinterpret_cast<const float4*>(dy + r * lddy + c);
+        const float4 zv = *reinterpret_cast<const float4*>(z + r * ldz + c);
+        xh[i] = make_float4((zv.x - mu) * rs, (zv.y - mu) * rs, (zv.z - mu) * rs, (zv.w - mu) * rs);
+        g[i] = make_float4(dyv.x * gm[i].x, dyv.y * gm[i].y, dyv.z * gm[i].z, dyv.w * gm[i].w);
+        acc_g[i].x += dyv.x * xh[i].x; acc_g[i].y += dyv.y * xh[i].y; acc_g[i].z += dyv.z * xh[i].z; acc_g[i].w += dyv.w * xh[i].w;
+        acc_b[i].x += dyv.x; acc_b[i].y += dyv.y; acc_b[i].z += dyv.z; acc_b[i].w += dyv.w;
+        s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+        s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
+      }
+    }
+    s1 = cb::warp_sum(s1) / d;
+    s2 = cb::warp_sum(s2) / d;
+    const drop::Keys dk = drop::row_keys(drop_ka, drop_kb, (uint32_t)r);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (c < dp) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < d) {
+          o.x = rs * (g[i].x - s1 - xh[i].x * s2);
+          o.y = rs * (g[i].y - s1 - xh[i].y * s2);
+          o.z = rs * (g[i].z - s1 - xh[i].z * s2);
+          o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+        }
+        if (dz_f32) *reinterpret_cast<float4*>(dz_f32 + r * lddz + c) = o;
+        if (dz_bf16) {
+          if (drop_thr2) {
+            const uint2 rnd = drop::rand64((uint32_t)(c >> 2), dk);
+            const uint32_t f0 = drop::keep_flags(rnd.x, drop_thr2), f1 = drop::keep_flags(rnd.y, drop_thr2);
+            o.x = (f0 & 0x8000u) ? o.x * drop_inv : 0.f;
+            o.y = (f0 & 0x80000000u) ? o.y * drop_inv : 0.f;
+            o.z = (f1 & 0x8000u) ? o.z * drop_inv : 0.f;
+            o.w = (f1 & 0x80000000u) ? o.w * drop_inv : 0.f;
+          }
+          *reinterpret_cast<uint2*>(dz_bf16 + r * lddzb + c) = make_uint2(cb::pack_bf16(o.x, o.y), cb::pack_bf16(o.z, o.w));
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int c = 4 * (lane + 32 * i);
+    atomicAdd(&sh_g[c + 0], acc_g[i].x); atomicAdd(&sh_g[c + 1], acc_g[i].y);
+    atomicAdd(&sh_g[c + 2], acc_g[i].z); atomicAdd(&sh_g[c + 3], acc_g[i].w);
+    atomicAdd(&sh_b[c + 0], acc_b[i].x); atomicAdd(&sh_b[c + 1], acc_b[i].y);
+    atomicAdd(&sh_b[c + 2], acc_b[i].z); atomicAdd(&sh_b[c + 3], acc_b[i].w);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -399,6 +551,19 @@ int commu_layernorm_fwd(const float* z, int64_t ldz, const float* gamma, const f
                         float eps, int64_t rows, float* y_f32, int64_t ldy, void* y_bf16, int64_t ldyb,
                         float* mean, float* rstd, void* stream) {
   CB_REQUIRE(z && gamma && beta && rows > 0, "layernorm_fwd: bad args");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (d % 4 == 0 && dp % 4 == 0 && dp <= 1024 && ldz % 4 == 0 && al16(z) && al16(gamma) && al16(beta) &&
+      (!y_f32 || (ldy % 4 == 0 && al16(y_f32))) && (!y_bf16 || (ldyb % 4 == 0 && al16(y_bf16)))) {
+    if (dp <= 512)
+      ln_fwd_v4_kernel<4><<<grid_for_rows(rows), THREADS, 0, (cudaStream_t)stream>>>(
+          z, ldz, gamma, beta, d, dp, eps, rows, y_f32, ldy, (bf16*)y_bf16, ldyb, mean, rstd);
+    else
+      ln_fwd_v4_kernel<8><<<grid_for_rows(rows), THREADS, 0, (cudaStream_t)stream>>>(
+          z, ldz, gamma, beta, d, dp, eps, rows, y_f32, ldy, (bf16*)y_bf16, ldyb, mean, rstd);
+    cb_host::count_launch();
+    CB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   ln_fwd_kernel<<<grid_for_rows(rows), THREADS, 0, (cudaStream_t)stream>>>(
       z, ldz, gamma, beta, d, dp, eps, rows, y_f32, ldy, (bf16*)y_bf16, ldyb, mean, rstd);
   cb_host::count_launch();
@@ -409,11 +574,31 @@ int commu_layernorm_fwd(const float* z, int64_t ldz, const float* gamma, const f
 int commu_layernorm_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* mean,
                         const float* rstd, const float* gamma, int d, int dp, int64_t rows, float* dz_f32,
                         int64_t lddz, void* dz_bf16, int64_t lddzb, float* dgamma, float* dbeta,
-                        void* stream) {
+                        float drop_p, uint64_t drop_seed, void* stream) {
   CB_REQUIRE(dy && z && mean && rstd && gamma && dgamma && dbeta && rows > 0, "layernorm_bwd: bad args");
   CB_REQUIRE(dp <= 1024, "layernorm_bwd: d_model (padded) %d > 1024 unsupported", dp);
+  CB_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "layernorm_bwd: drop_p must be in [0, 1)");
   const int grid = cb_host::num_sms() * 2;
   cudaStream_t s = (cudaStream_t)stream;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec = d % 4 == 0 && dp % 4 == 0 && lddy % 4 == 0 && ldz % 4 == 0 && al16(dy) && al16(z) && al16(gamma) &&
+                   (!dz_f32 || (lddz % 4 == 0 && al16(dz_f32))) && (!dz_bf16 || (lddzb % 4 == 0 && al16(dz_bf16)));
+  CB_REQUIRE(vec || drop_p == 0.f, "layernorm_bwd: the fused dropout needs 16-byte aligned rows and d, dp multiples of 4");
+  if (vec) {
+    const uint32_t thr = drop_p > 0.f ? drop::thr15_of(drop_p) : 0u;
+    const uint32_t thr2 = thr * 0x00010001u;
+    const float inv = 1.f / (1.f - (float)thr / 32768.f);
+    const uint32_t ka = (uint32_t)drop_seed, kb = (uint32_t)(drop_seed >> 32);
+    if (dp <= 512)
+      ln_bwd_v4_kernel<4><<<grid, THREADS, 0, s>>>(dy, lddy, z, ldz, mean, rstd, gamma, d, dp, rows, dz_f32, lddz,
+                                                   (bf16*)dz_bf16, lddzb, dgamma, dbeta, thr2, ka, kb, inv);
+    else
+      ln_bwd_v4_kernel<8><<<grid, THREADS, 0, s>>>(dy, lddy, z, ldz, mean, rstd, gamma, d, dp, rows, dz_f32, lddz,
+                                                   (bf16*)dz_bf16, lddzb, dgamma, dbeta, thr2, ka, kb, inv);
+    cb_host::count_launch();
+    CB_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (dp <= 512)
     ln_bwd_kernel<16><<<grid, THREADS, 0, s>>>(dy, lddy, z, ldz, mean, rstd, gamma, d, dp, rows, dz_f32,
                                                lddz, (bf16*)dz_bf16, lddzb, dgamma, dbeta);

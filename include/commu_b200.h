@@ -111,7 +111,9 @@ int commu_layernorm_fwd(const float* z, int64_t ldz, const float* gamma, const f
 int commu_layernorm_bwd(const float* dy, int64_t lddy, const float* z, int64_t ldz, const float* mean,
                         const float* rstd, const float* gamma, int d, int dp, int64_t rows, float* dz_f32,
                         int64_t lddz, void* dz_bf16, int64_t lddzb, float* dgamma, float* dbeta,
-                        void* stream);
+                        float drop_p, uint64_t drop_seed, void* stream);
+/* (drop_p > 0: the bf16 copy dz_bf16 additionally carries the inverted dropout of the sub-block output, i.e. the
+ * gradient that enters o_net / CoreNet.3 (model.py:349, 168); the fp32 copy is the undropped residual-branch gradient.) */
 
 /* Per-token NLL = -log_softmax(logits)[target] (ProjectedAdaptiveLogSoftmax.forward, n_clusters == 0
  * branch, model.py:64-73) and its backward dlogits = (softmax - onehot) * dloss (bf16, Vp columns). */

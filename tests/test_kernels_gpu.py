@@ -216,9 +216,21 @@ def test_embed_pos_ln_nll():
     dzb = torch.empty(n, dp, device=dev, dtype=torch.bfloat16)
     dg = torch.zeros(d, device=dev)
     db = torch.zeros(d, device=dev)
-    nv.call("commu_layernorm_bwd", dy, dp, z, dp, mean, rstd, gam, d, dp, n, dzf, dp, dzb, dp, dg, db)
+    nv.call("commu_layernorm_bwd", dy, dp, z, dp, mean, rstd, gam, d, dp, n, dzf, dp, dzb, dp, dg, db, 0.0, 0)
     assert (dzf[:, :d] - zz.grad).abs().max() < 1e-4
     assert (dg - g2.grad).abs().max() < 1e-3 and (db - b2.grad).abs().max() < 1e-3
+    assert (dzb[:, :d].float() - zz.grad).abs().max() < 0.02 * zz.grad.abs().max() + 1e-3
+    # fused dropout of the bf16 gradient copy (the fp32 copy stays undropped)
+    from helpers import drop_keep_mask, drop_keep_prob
+    dzf2 = torch.empty(n, dp, device=dev)
+    dzb2 = torch.empty(n, dp, device=dev, dtype=torch.bfloat16)
+    dg2 = torch.zeros(d, device=dev)
+    db2 = torch.zeros(d, device=dev)
+    nv.call("commu_layernorm_bwd", dy, dp, z, dp, mean, rstd, gam, d, dp, n, dzf2, dp, dzb2, dp, dg2, db2, 0.25, 987654321)
+    keep = drop_keep_mask(987654321, n, dp, 0.25).to(dev)[:, :d]
+    assert torch.equal(dzf2, dzf)
+    refd = zz.grad * keep / drop_keep_prob(0.25)
+    assert (dzb2[:, :d].float() - refd).abs().max() < 0.02 * refd.abs().max() + 1e-3
     # nll
     Vp = 64
     lg = torch.randn(n, Vp, device=dev) * 3
