@@ -14,6 +14,34 @@ import torch
 from commu import _native as nv
 
 
+# ------------------------------------------------------------------------------------------------
+# Index arithmetic of the TMA decode-attention kernel (csrc/decode_fused.cu, dec_attn_tma_kernel), restated on the host:
+# documentation of the ring / table layout and the subject of tests/test_decode_index_cpu.py.  The kernel itself never
+# calls these.
+# ------------------------------------------------------------------------------------------------
+def visible_slot_tiles(C, cur_slot, n_vis, tile=64):
+    """Ring-slot tiles (index t covers slots t*tile .. t*tile+tile-1) that hold at least one of the n_vis newest
+    entries (ages 0..n_vis-1, age 0 at cur_slot), in the order the kernel walks them.  C is a multiple of `tile`."""
+    nts = C // tile
+    lo = cur_slot - n_vis + 1
+    if lo < 0:
+        lo += C
+    t_first = lo // tile
+    nt = min(nts, ((lo % tile) + n_vis + tile - 1) // tile)
+    return [(t_first + k) % nts for k in range(nt)]
+
+
+def slot_age(C, cur_slot, slot):
+    """Age of a ring slot (0 = newest); a slot is attended iff its age < n_vis."""
+    return (cur_slot - slot) % C
+
+
+def rtab2_row(C, cur_slot, slot):
+    """Row of the reversed, doubled table rt2[h] (2C rows, rt2[j] = R[C-1 - (j mod C)]) that pairs with `slot`:
+    consecutive slots of a tile map to consecutive rows starting at this value for the tile's first slot."""
+    return (C - 1 - cur_slot + slot) % C
+
+
 class DecodeState:
     """Immutable handle playing the role of the reference's `mems` in the decode loop: how many
     tokens are cached and where the newest sits in the ring.  Passing an older handle back rewinds."""

@@ -101,3 +101,38 @@ def test_no_cpu_fallback():
         m(x, x, None, None)
     with pytest.raises(RuntimeError):
         m.forward_generate(x, None)
+
+
+def test_c_structs_match_ctypes_layout(tmp_path):
+    """The argument structs of the C-ABI (include/commu_b200.h) and their ctypes mirrors (commu/_native.py) must agree
+    field by field: a C program built from the header prints sizeof / offsetof, compared with ctypes."""
+    import shutil
+    import subprocess
+    from commu import _native as nv
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    pairs = {"commu_gemm_args": nv.GemmArgs, "CommuDecLinear": nv.DecLinearArgs}
+    lines = []
+    for cname, cls in pairs.items():
+        lines.append('printf("%s sizeof %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "commu_b200.h"\nint main(void) {\n%s\nreturn 0; }\n'
+                   % "\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        cname, fname, val = ln.split()
+        cls = pairs[cname]
+        if fname == "sizeof":
+            assert ctypes.sizeof(cls) == int(val), (cname, ctypes.sizeof(cls), val)
+        else:
+            assert getattr(cls, fname).offset == int(val), (cname, fname, getattr(cls, fname).offset, val)
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in pairs.values())
