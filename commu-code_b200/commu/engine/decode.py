@@ -150,7 +150,7 @@ class DecodeEngine:
         if self.attn_impl & 8:
             # reversed, doubled table per head [H, 2C, 64]: row j = R[C-1 - (j mod C)], so the 64 slots of a ring tile
             # are 64 consecutive rows even where the ages wrap (one TMA box)
-            self.rt_h = [torch.cat([r.flip(0).permute(1, 0, 2)] * 2, dim=1).contiguous() for r in self.rt]
+            self.rt_h = [self._reverse_double(r) for r in self.rt]
         else:
             self.rt_h = self.rt
         ks = None
@@ -211,6 +211,11 @@ class DecodeEngine:
         self.a_logits = mk(prologue=nv.PRO_LN, epilogue=nv.EPI_LOGITS, K=dp, N=V, d_true=d, z=ws["z2"], ldz=d,
                            gamma=last["g2"], beta=last["be2"], eps=1e-5, w=wl, ldw=dp, bias=self.lbias,
                            out_f32=self.ws["logits"], ldo=V, **dict(B=B, pdl=self.pdl, split_k=1))
+
+    @staticmethod
+    def _reverse_double(r):
+        """R by distance [C, H, 64] -> per head reversed and doubled [H, 2C, 64]: row j = R[C-1 - (j mod C)]."""
+        return torch.cat([r.flip(0).permute(1, 0, 2)] * 2, dim=1).contiguous()
 
     def _pick_splits(self):
         """Key splits of the SIMT decode attention: B*H*splits CTAs should fill the SMs' resident slots (3 CTAs per

@@ -179,3 +179,63 @@ def test_decode_plumbing(stub, monkeypatch):
     eng = dec.DecodeEngine(m, 3, 24, True, "bf16")
     eng.generate(torch.randint(1, 53, (5, 3)), 2, temperature=0.95, top_k=0, top_p=0.9, seed=1, use_graph=False)
     assert not eng.fused
+
+
+def test_fused_decode_weight_layouts(stub, monkeypatch):
+    """The padded bf16 weights of the fused decode step (DecodeEngine._prepare_fused) reproduce the unpadded linear
+    layers: q / k / v in the padded head layout [q|k|v][H][64], o_net over the padded head columns, FF matrices with
+    zero padding, tied logits - checked with plain CPU matmuls (d = 60, Dh = 10, d_inner = 100: every padding bites)."""
+    import commu.engine.decode as dec
+    torch.manual_seed(0)
+    m = _model()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.normal_(0.0, 0.5)
+
+    def init(self, model, batch, mem_len, same_length=True, precision="fp32"):
+        real_dev = model.r_w_bias.device
+        monkeypatch.setattr(dec.torch.Tensor, "device", property(lambda s: real_dev), raising=False)
+        self.m = model
+        self.B, self.mem_len, self.same_length = batch, mem_len, bool(same_length)
+        self.bf16 = precision == "bf16"
+        self.L, self.H, self.d, self.Dh = model.n_layer, model.n_head, model.d_model, model.d_head
+        self.Di, self.V = model.d_inner, model.n_token
+        self.C = mem_len + 1
+        self.dev = real_dev
+        self.scale = 1.0
+        self._prepare()
+    monkeypatch.setattr(dec.DecodeEngine, "__init__", init)
+    eng = dec.DecodeEngine(m, 3, 24, True, "bf16")
+    assert eng.fused and eng.C % 64 == 0 and eng.C >= 25
+    H, Dh, d, Di, V = eng.H, eng.Dh, eng.d, eng.Di, eng.V
+    sd = dict(m.named_parameters())
+    x = torch.randn(3, d)
+    xp = torch.zeros(3, 64)
+    xp[:, :d] = x
+    tol = dict(rtol=2e-2, atol=2e-2)            # the padded copies are bf16
+    for l in range(eng.L):
+        wqkv, wo, w1, b1, w2 = [t.float() for t in eng.fw[l]]
+        pre = "layers.%d." % l
+        ref = (x @ sd[pre + "dec_attn.qkv_net.weight"].t()).view(3, 3, H, Dh)
+        got = (xp @ wqkv.t()).view(3, 3, H, 64)
+        assert torch.allclose(got[..., :Dh], ref, **tol) and float(got[..., Dh:].abs().max()) == 0.0
+        att = torch.randn(3, H, Dh)
+        attp = torch.zeros(3, H, 64)
+        attp[..., :Dh] = att
+        ref_o = att.reshape(3, H * Dh) @ sd[pre + "dec_attn.o_net.weight"].t()
+        assert torch.allclose((attp.reshape(3, H * 64) @ wo.t())[:, :d], ref_o, **tol)
+        ref_h = x @ sd[pre + "pos_ff.CoreNet.0.weight"].t() + sd[pre + "pos_ff.CoreNet.0.bias"]
+        got_h = xp @ w1.t() + b1
+        assert torch.allclose(got_h[:, :Di], ref_h, **tol) and float(got_h[:, Di:].abs().max()) == 0.0
+        hh = torch.zeros(3, w2.shape[1])
+        hh[:, :Di] = torch.randn(3, Di)
+        assert torch.allclose((hh @ w2.t())[:, :d], hh[:, :Di] @ sd[pre + "pos_ff.CoreNet.3.weight"].t(), **tol)
+    wl = eng.fw[-1][0].float()
+    assert torch.allclose((xp @ wl.t())[:, :V], x @ sd["word_emb.emb_layers.0.weight"].t(), **tol)
+    # reversed, doubled relative-position table of the TMA kernel: rt2[h, j] = rt[C-1 - (j mod C), h]
+    C = eng.C
+    rt = torch.randn(C, H, 64)
+    rt2 = dec.DecodeEngine._reverse_double(rt)
+    assert rt2.shape == (H, 2 * C, 64) and eng.rt_h[0].shape == (H, 2 * C, 64)
+    j = torch.arange(2 * C)
+    assert torch.equal(rt2, rt[C - 1 - (j % C)].permute(1, 0, 2))
