@@ -242,7 +242,9 @@ def run_native(args):
             ach = fl / dur / 1e12
             roof = dict(kernel=dom, bound="tensor", achieved=round(ach, 2), peak=pk["bf16"], unit="TFLOP/s",
                         frac=round(ach / pk["bf16"], 4), traffic=ncu_traffic(dom), peak_source=pk["source"],
-                        flops_per_launch=fl, avg_launch_ms=round(dur * 1e3, 4))
+                        flops_per_launch=fl, avg_launch_ms=round(dur * 1e3, 4),
+                        launch_unit={"attn_bwd": "one layer's attention backward = dq + dk/dv + dR passes + delta",
+                                     "attn_fwd": "one layer's attention forward"}.get(dom, dom))
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": round(ms_dev / K, 3), "higher_is_better": True, "scaling": "weak",
