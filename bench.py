@@ -152,8 +152,8 @@ def run_native(args):
         print(json.dumps({"decode": decode_bench(model, dev, peaks())}), flush=True)
         return
     model.train()
-    tr = Trainer(model, lr=0.004 / world, warmup_step=100, lr_min=1e-4, clip=1.0, batch_chunk=1, world=world,
-                 comm=comm)
+    tr = Trainer(model, lr=0.004 / world, warmup_step=100, lr_min=1e-4, clip=1.0, batch_chunk=args.batch_chunk,
+                 world=world, comm=comm, global_lr=0.004)
     T, B = CFG["tgt_len"], B_PER_GPU
     K, W = args.steps, args.warmup
     gen = torch.Generator().manual_seed(1111 + 1000 * rank)
@@ -251,7 +251,7 @@ def run_native(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1]: 12L d512 H8 Di2048 T=2048 M=2048 V=729 train step "
                                    "(fwd+bwd+clip+Adam), dropout %g / attention_dropout %g (reference default 0.1), "
-                                   "batch_chunk 1" % (args.dropout, args.dropout),
+                                   "batch_chunk %d" % (args.dropout, args.dropout, args.batch_chunk),
                        "global_batch": B * world, "per_gpu_batch": B, "seq_len": T, "mem_len": CFG["mem_len"],
                        "parallelism": "dp%d" % world,
                        "l2": "per-step working set (activations ~%d MB/GPU) >> 126 MB L2" % int(0.64 * 12 * B / 16 * 1000)},
@@ -273,6 +273,20 @@ def run_native(args):
                 out["decode"] = {"error": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(1, 1, args.dropout)
+        if world == 1 and not args.no_reference_gpu:
+            del tr, model
+            torch.cuda.empty_cache()
+            try:
+                rg = reference_gpu_leg(dev, args.dropout)
+                out["reference_gpu"] = rg
+                out["vs_reference_gpu"] = {
+                    "fp32": round(value / rg["best_fp32_tokens_per_s"], 2) if rg.get("best_fp32_tokens_per_s") else None,
+                    "autocast_bf16": round(value / rg["best_autocast_bf16_tokens_per_s"], 2)
+                    if rg.get("best_autocast_bf16_tokens_per_s") else None,
+                    "e2e_fp32": round(e2e / rg["best_fp32_tokens_per_s"], 2) if rg.get("best_fp32_tokens_per_s") else None,
+                    "target": ">= 10x the reference PyTorch-GPU (fp32 eager) tokens/s (BASELINE.json north_star)"}
+            except Exception as e:
+                out["reference_gpu"] = {"error": repr(e)[:300]}
         print(json.dumps(out), flush=True)
     if comm is not None:
         comm.close()
@@ -436,6 +450,71 @@ def cpu_baseline(steps, warmup, p_drop=0.1):
                                       (len(times), p_drop, tot)}
 
 
+def reference_gpu_leg(dev, p_drop, steps=3, warmup=2):
+    """The number the north-star ratio is about (SURVEY.md 8(d) "Reference GPU baseline"): the reference algorithm
+    (oracle port of commu/model/model.py:540-693, plain eager PyTorch) with the restated train loop of
+    train.py:133-169 (pad-masked mean loss, backward, clip_grad_norm_(1.0), torch.optim.Adam) on THIS B200, same
+    model / T / M / dropout, synthetic tokens: eager fp32 (what the reference runs: it never enables autocast or
+    TF32) and, labelled, under torch.autocast(bf16) as a stronger baseline.  B = 4 (like-for-like micro-batch of
+    SURVEY 8d) and the largest of 8 / 16 that fits the 180 GB.  The oracle is only the thing timed here, never part
+    of the product path."""
+    from oracle import transfoxl_oracle as orc
+    cfg = orc.make_cfg(CFG["n_layer"], CFG["n_head"], CFG["d_model"], CFG["d_inner"], CFG["tgt_len"],
+                       CFG["mem_len"], False, -1, CFG["n_token"])
+    T = CFG["tgt_len"]
+    res = {}
+
+    def drop(site, layer, t):
+        return torch.nn.functional.dropout(t, p_drop, True)
+
+    def one(B, autocast):
+        P0 = orc.init_params(cfg, seed=1111, std=0.01)
+        P = {k: torch.nn.Parameter(v.to(dev)) for k, v in P0.items()}
+        opt = torch.optim.Adam(list(P.values()), lr=1e-4)
+        gen = torch.Generator(device=dev).manual_seed(7)
+        mems = None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for s in range(warmup + steps):
+            if s == warmup:
+                torch.cuda.synchronize()
+                e0.record()
+            tok = torch.randint(2, 560, (T + 1, B), generator=gen, device=dev)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                nll, mems = orc.forward_loss(cfg, P, tok[:-1], tok[1:], None, mems, drop=drop if p_drop > 0 else None)
+                loss = nll[tok[1:] != 0].float().mean()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(list(P.values()), 1.0)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            loss.item()                               # the reference logs the loss every step (train.py:157)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"tokens_per_s": round(T * B / (ms / 1e3), 1), "ms_per_step": round(ms, 2), "batch": B,
+                "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)}
+
+    for B in (4, 16, 8):
+        if B == 8 and "fp32_B16" in res and "error" not in res["fp32_B16"]:
+            continue
+        for autocast in (False, True):
+            key = ("autocast_bf16" if autocast else "fp32") + "_B%d" % B
+            torch.cuda.empty_cache()
+            torch.cuda.reset_peak_memory_stats(dev)
+            try:
+                res[key] = one(B, autocast)
+            except torch.cuda.OutOfMemoryError:
+                res[key] = {"error": "out of memory at B=%d" % B}
+            except Exception as e:                     # never hide the training metric behind the baseline
+                res[key] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+    ok = lambda pre: [v["tokens_per_s"] for k, v in res.items() if k.startswith(pre) and "tokens_per_s" in v]
+    res["best_fp32_tokens_per_s"] = max(ok("fp32"), default=None)
+    res["best_autocast_bf16_tokens_per_s"] = max(ok("autocast"), default=None)
+    res["what"] = ("oracle port of the reference model + restated train.py loop, eager PyTorch %s on this GPU, "
+                   "dropout %g, %d timed steps after %d warm-up" % (torch.__version__, p_drop, steps, warmup))
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -464,8 +543,11 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--dropout", type=float, default=0.1,
                     help="MODEL.dropout = MODEL.attention_dropout (reference default 0.1, config_helper.py:11-12)")
+    ap.add_argument("--batch-chunk", type=int, default=1,
+                    help="TRAIN.batch_chunk micro-batches per optimizer step (reference default 4, train.py:123,136-155)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-decode", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--decode-only", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native" and os.environ.get("COMMU_BENCH_PROFILE") != "1":

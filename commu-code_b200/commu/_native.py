@@ -186,7 +186,7 @@ SIGNATURES = {
     "commu_cast_pad": [P, L, I, I, I, I, I, I, P, L, I, P],
     "commu_unpad_accum": [P, L, I, I, I, I, I, I, P, L, F, P],
     "commu_sumsq": [P, L, P, P],
-    "commu_clip_adam": [P, P, P, P, L, F, F, F, F, I, P, F, F, P, P],
+    "commu_clip_adam": [P, P, P, P, L, F, F, F, F, I, P, F, F, F, P, P],
     "commu_relattn_fwd": [P, L, P, P, L, P, L, I, P, P, P, I, I, I, I, I, I, F, P, L, P, P, P, P],
     "commu_relattn_fwd_tc": [P, L, P, P, L, P, L, I, P, P, P, I, I, I, I, I, I, F, P, L, P, P, P, P],
     "commu_relattn_bwd": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, L, P, P, L, P, P, L,

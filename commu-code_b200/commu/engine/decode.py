@@ -352,7 +352,7 @@ class DecodeEngine:
         if not use_graph:
             for t in range(n_new):
                 logits, state = self.step(cur, state)
-                cur, _ = self.sample(logits, temperature, top_k, top_p, None, seed, t)
+                cur, _ = self.sample(logits, temperature, top_k, top_p, None, seed, t + 1)   # counter t+1: same draws as the graph path
                 out[t] = cur
             return out
         dstate = torch.tensor([state.slot, 0, state.count, 0], dtype=torch.int32, device=self.dev)

@@ -61,9 +61,15 @@ class GradComm:
 
 class Trainer:
     def __init__(self, model, lr, warmup_step=0, lr_min=0.0, clip=1.0, betas=(0.9, 0.999), eps=1e-8,
-                 batch_chunk=1, pad_id=0, world=1, comm=None):
+                 batch_chunk=1, pad_id=0, world=1, comm=None, global_lr=None, weight_decay=0.0):
+        """lr is the per-rank learning rate (reference: cfg.TRAIN.lr / num_gpus, train.py:441); the floor of the
+        schedule is the ratio lr_min / global_lr with the UNDIVIDED cfg.TRAIN.lr (train.py:456), so callers that divide
+        lr by the world size pass global_lr = cfg.TRAIN.lr (default: lr, i.e. one rank).  weight_decay is Adam's L2
+        term (g += wd * p before the moment updates, torch.optim.Adam; train.py:442-443)."""
         self.model = model
         self.base_lr, self.warmup_step, self.lr_min = lr, warmup_step, lr_min
+        self.global_lr = lr if global_lr is None else global_lr
+        self.weight_decay = float(weight_decay)
         self.clip, self.betas, self.eps = clip, betas, eps
         self.batch_chunk, self.pad_id = batch_chunk, pad_id
         self.world, self.comm = world, comm
@@ -101,7 +107,7 @@ class Trainer:
         self.engine.refresh_shadow()
 
     def current_lr(self):
-        return self.base_lr * lr_multiplier(self.step, self.warmup_step, self.base_lr, self.lr_min)
+        return self.base_lr * lr_multiplier(self.step, self.warmup_step, self.global_lr, self.lr_min)
 
     @torch.no_grad()
     def train_step(self, data, target, reset):
@@ -133,7 +139,7 @@ class Trainer:
         nv.call("commu_sumsq", self.flat_g, self.flat_g.numel(), self.gnorm_sq)
         nv.call("commu_clip_adam", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_p.numel(),
                 lr, self.betas[0], self.betas[1], self.eps, self.step, self.gnorm_sq, self.clip,
-                1.0 / self.world, self.gnorm)
+                1.0 / self.world, self.weight_decay, self.gnorm)
         eng.refresh_shadow()
         return total, self.gnorm[0].clone()
 
@@ -146,7 +152,7 @@ class Trainer:
                           "exp_avg": self.flat_m[o:o + p.numel()].view_as(p).clone(),
                           "exp_avg_sq": self.flat_v[o:o + p.numel()].view_as(p).clone()}
             idx += 1
-        group = {"lr": self.current_lr(), "betas": self.betas, "eps": self.eps, "weight_decay": 0.0,
+        group = {"lr": self.current_lr(), "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
                  "amsgrad": False, "params": list(range(idx))}
         return {"state": state, "param_groups": [group]}
 

@@ -55,7 +55,7 @@ extern "C" {
 
 const char* commu_last_error(void) { return cb_host::error_buffer(); }
 
-int commu_abi_version(void) { return 2; }   // 2: commu_gemm_args drop fields, commu_layernorm_bwd dropout args, fused decode entry points
+int commu_abi_version(void) { return 3; }   // 3: commu_clip_adam weight_decay, commu_relattn_bwd workspace (materialised dS), stored probabilities
 
 int commu_device_info(int* sm_major, int* sm_minor, int* num_sms) {
   int dev = 0;

@@ -488,7 +488,7 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                             float bc1, float bc2, const float* __restrict__ gnorm_sq, float clip,
-                            float grad_scale, float* __restrict__ gnorm_out) {
+                            float grad_scale, float weight_decay, float* __restrict__ gnorm_out) {
   float coef = grad_scale;
   const float norm = sqrtf(*gnorm_sq) * grad_scale;
   if (clip > 0.f) coef *= fminf(1.f, clip / (norm + 1e-6f));
@@ -497,7 +497,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   const float rsq_bc2 = rsqrtf(bc2);
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float gi = g[i] * coef;
+    const float gi = fmaf(weight_decay, p[i], g[i] * coef);   // torch.optim.Adam: grad += weight_decay * param (after the clip)
     const float mi = b1 * m[i] + (1.f - b1) * gi;
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
@@ -687,12 +687,12 @@ int commu_sumsq(const float* g, int64_t n, float* out_accum, void* stream) {
 
 int commu_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                     float beta2, float eps, int step, const float* gnorm_sq, float clip, float grad_scale,
-                    float* gnorm_out, void* stream) {
+                    float weight_decay, float* gnorm_out, void* stream) {
   CB_REQUIRE(p && g && m && v && gnorm_sq && n > 0 && step >= 1, "clip_adam: bad args");
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
   adam_kernel<<<cb_host::num_sms() * 8, THREADS, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, gnorm_sq, clip, grad_scale, gnorm_out);
+      p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, gnorm_sq, clip, grad_scale, weight_decay, gnorm_out);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

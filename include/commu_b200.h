@@ -135,11 +135,12 @@ int commu_unpad_accum(const float* src, int64_t ld_src, int R, int C, int rseg, 
 
 /* Optimizer tail (train.py:159-169): out_accum += sum(g^2); then
  * g' = g * grad_scale * min(1, clip / (||g * grad_scale|| + 1e-6)) (clip_grad_norm_) followed by Adam
- * (torch.optim.Adam: no amsgrad, weight_decay 0) on flat fp32 arenas.  step >= 1. */
+ * (torch.optim.Adam, no amsgrad; weight_decay is its L2 term g' += weight_decay * p, train.py:442-443) on flat
+ * fp32 arenas.  step >= 1. */
 int commu_sumsq(const float* g, int64_t n, float* out_accum, void* stream);
 int commu_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                     float beta2, float eps, int step, const float* gnorm_sq, float clip, float grad_scale,
-                    float* gnorm_out, void* stream);
+                    float weight_decay, float* gnorm_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused relative-position attention (RelPartialLearnableMultiHeadAttn.forward, model.py:312-345,

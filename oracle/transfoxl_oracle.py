@@ -86,13 +86,13 @@ def inv_freq(d_model, dtype=torch.float32):
     return 1.0 / (10000 ** (torch.arange(0.0, d_model, 2.0) / d_model)).to(dtype)
 
 
-def sinusoid_by_distance(klen, d_model, clamp_len, dtype):
+def sinusoid_by_distance(klen, d_model, clamp_len, dtype, device=None):
     """Row delta holds [sin(delta*f) | cos(delta*f)] (model.py:145-147), delta clamped like
     model.py:581-582."""
-    dist = torch.arange(klen, dtype=dtype)
+    dist = torch.arange(klen, dtype=dtype, device=device)
     if clamp_len > 0:
         dist = dist.clamp(max=clamp_len)
-    ang = torch.outer(dist, inv_freq(d_model, dtype))
+    ang = torch.outer(dist, inv_freq(d_model, dtype).to(device))
     return torch.cat([ang.sin(), ang.cos()], dim=-1)
 
 
@@ -129,8 +129,8 @@ def _layer(cfg, P, pre, x, mem, pos, valid, drop=None, l=0):
     u, vb = P["r_w_bias"], P["r_r_bias"]
     AC = torch.einsum("ibhd,jbhd->bhij", q + u, k)
     QR = torch.einsum("ibhd,thd->bhit", q + vb, R)                        # [B,H,T,K] by distance
-    ii = torch.arange(T)[:, None]
-    jj = torch.arange(K)[None, :]
+    ii = torch.arange(T, device=x.device)[:, None]
+    jj = torch.arange(K, device=x.device)[None, :]
     dist = (ii + M - jj).clamp(min=0)                                      # masked where < 0
     BD = QR.gather(3, dist[None, None].expand(B, H, T, K))
     score = (AC + BD) * (1.0 / math.sqrt(Dh))
@@ -156,10 +156,12 @@ def hidden_forward(cfg, P, data, reset=None, mems=None, drop=None):
     E = P["word_emb.emb_layers.0.weight"]
     x = E[data] * math.sqrt(cfg.d_model)
     M = 0 if (mems is None or mems.numel() == 0) else mems.shape[1]
+    dev = E.device                      # the arrays live wherever the parameters do (CPU for parity tests and the
+                                        # CPU baseline; bench.py's reference-GPU leg puts them on the B200)
     if reset is None:
-        reset = torch.zeros(B, dtype=torch.bool)
-    valid = visible_mask(T, M, cfg.mem_len, cfg.same_length, reset)
-    pos = sinusoid_by_distance(T + M, cfg.d_model, cfg.clamp_len, dtype)
+        reset = torch.zeros(B, dtype=torch.bool, device=dev)
+    valid = visible_mask(T, M, cfg.mem_len, cfg.same_length, reset, device=dev)
+    pos = sinusoid_by_distance(T + M, cfg.d_model, cfg.clamp_len, dtype, device=dev)
     if drop is not None:                                                   # model.py:585-586
         x = drop("emb", 0, x)
         pos = drop("pos", 0, pos)

@@ -265,3 +265,56 @@ def test_inference_task_surface():
     probs = task.apply_sampling(task.calc_probs(logits), [])
     tok = task.infer_token(probs)
     assert tok == 1 + int(logits.argmax())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_decode_greedy_512_tokens_at_bench_shape(precision):
+    """BASELINE configs[3] model shape (12 layers, d_model 512, 8 heads, d_inner 2048, mem_len 2048), B = 2, a full
+    2048-token memory prefilled, then 512 greedy tokens.  The oracle (reference forward_generate restated,
+    model.py:606-628; fp32 torch on the same GPU, TF32 off) recomputes [memory ; token] per step; both sides follow the
+    oracle's tokens so a disagreement cannot hide later ones.
+      fp32 engine: the identical token at every step whose oracle top-2 margin exceeds fp32 summation-order noise (1e-4).
+      bf16 engine (throughput mode; bf16 K/V cache and weights): logits within the bf16 tolerance, identical tokens
+      wherever the margin exceeds 4x the measured logit error - it is NOT bit-exact by construction, which is why
+      bench.py's headline decode number is the fp32 engine."""
+    from commu.engine.decode import DecodeEngine
+    assert not torch.backends.cuda.matmul.allow_tf32
+    L, H, d, Di, V, mem_len, B = 12, 8, 512, 2048, 729, 2048, 2
+    cfg = orc.make_cfg(n_layer=L, n_head=H, d_model=d, d_inner=Di, tgt_len=1, mem_len=mem_len, same_length=True,
+                       clamp_len=-1, n_token=V)
+    P = orc.init_params(cfg, seed=77, std=0.06)           # peaked, well-separated logits
+    model = build_model(cfg, P)
+    model.eval()
+    Pg = {k: v.cuda() for k, v in P.items()}
+    eng = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision=precision)
+    g = torch.Generator().manual_seed(5)
+    ctx = torch.randint(1, V, (mem_len + 1, B), generator=g).cuda()
+    worst, scale, thin, wrong = 0.0, 0.0, 0, 0
+    with torch.no_grad():
+        _, mems = orc.forward_generate(cfg, Pg, ctx[:-1], None)
+        _, st = eng.prefill(ctx[:-1])
+        cur = ctx[-1:].contiguous()
+        for t in range(512):
+            lo, mems = orc.forward_generate(cfg, Pg, cur, mems)
+            lg, st = eng.step(cur[0].contiguous(), st)
+            ref = lo[-1]
+            tok_o = 1 + ref[:, 1:].argmax(-1)
+            tok_n, _ = eng.sample(lg, 0.0)
+            top2 = ref[:, 1:].topk(2, -1).values
+            margin = (top2[:, 0] - top2[:, 1])
+            err = float((lg - ref).abs().max())
+            worst, scale = max(worst, err), max(scale, float(ref.abs().max()))
+            bound = 1e-4 if precision == "fp32" else 4 * max(err, 1e-3)
+            for b in range(B):
+                if float(margin[b]) > bound:
+                    wrong += int(tok_n[b]) != int(tok_o[b])
+                else:
+                    thin += 1
+            cur = tok_o[None].contiguous()
+    assert wrong == 0, (precision, wrong, thin, worst)
+    if precision == "fp32":
+        assert worst < 2e-3 * max(1.0, scale), (worst, scale)
+        assert thin <= 4, thin
+    else:
+        assert worst < 0.06 * scale + 0.02, (worst, scale)
+        assert thin <= 0.2 * 512 * B, thin

@@ -83,7 +83,7 @@ def test_library_exports_every_declared_symbol():
     # and every bound signature refers to a declared symbol
     for sym in nv.SIGNATURES:
         assert sym in declared, sym
-    assert lib.commu_abi_version() == 2
+    assert lib.commu_abi_version() == 3
 
 
 def test_no_cpu_fallback():

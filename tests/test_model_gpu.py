@@ -218,3 +218,41 @@ def test_forward_backward_at_config5_width():
             continue
         tol = 0.08 if "pos_ff.CoreNet.0" in k else 0.05       # ReLU-mask flips behind FF1 (see test_dropout_gpu)
         assert fro_err(p.grad.cpu(), Pl[k].grad) < tol, (k, fro_err(p.grad.cpu(), Pl[k].grad))
+
+
+def test_forward_backward_at_bench_shape():
+    """BASELINE configs[1] attention geometry (d_model 512, 8 heads of 64, d_inner 2048, T = M = 2048: the 16 x 32
+    tile walk with distances up to 4095 that bench.py times) on a 2-layer stack, B = 2, three segments with memory
+    (the third with a memory reset on one column): per-segment loss within 1e-3 relative of the oracle and the
+    gradients within the bf16 tolerance.  The oracle runs in fp32 on the same GPU (plain torch, TF32 off) - at
+    this size it needs ~5 GB of score tensors; it is the checker, not the thing tested."""
+    assert not torch.backends.cuda.matmul.allow_tf32
+    T = M = 2048
+    cfg = orc.make_cfg(n_layer=2, n_head=8, d_model=512, d_inner=2048, tgt_len=T, mem_len=M, n_token=729)
+    P = orc.init_params(cfg, seed=21, std=0.02)
+    model = build_model(cfg, P)
+    model.train()
+    Pl = {k: v.clone().cuda().requires_grad_(True) for k, v in P.items()}
+    g = torch.Generator().manual_seed(4)
+    mems_o = mems_n = None
+    for s in range(3):
+        data = torch.randint(1, 729, (T, 2), generator=g).cuda()
+        target = torch.randint(1, 729, (T, 2), generator=g).cuda()
+        reset = torch.tensor([False, s == 2]).cuda()
+        lo, mems_o = orc.forward_loss(cfg, Pl, data, target, reset, mems_o)
+        lo.mean().backward()
+        ln, mems_n = model(data, target, reset, mems_n)
+        ln.mean().backward()
+        rel = abs(float(ln.mean()) - float(lo.mean())) / float(lo.mean())
+        assert rel < 1e-3, (s, rel)
+        assert (ln.detach() - lo.detach()).abs().max() < 0.05, s
+        assert (mems_n.float() - mems_o).abs().max() < 0.05 * mems_o.abs().max() + 0.02, s
+        del lo, ln
+    errs = {}
+    for k, p in model.named_parameters():
+        if k == "crit.out_layers.0.weight":
+            continue
+        errs[k] = (fro_err(p.grad.cpu(), Pl[k].grad.cpu()), rel_err(p.grad.cpu(), Pl[k].grad.cpu()))
+    _dump("bench_shape", errs)
+    bad = {k: v for k, v in errs.items() if v[0] >= (0.08 if "pos_ff.CoreNet.0" in k else 0.05)}
+    assert not bad, bad

@@ -146,6 +146,27 @@ def test_trainer_plumbing(stub, monkeypatch):
     assert "commu_clip_adam" in stub.calls and "commu_sumsq" in stub.calls
 
 
+def test_lr_schedule_floor_is_world_independent(stub, monkeypatch):
+    """train.py:441-461 of the reference: the optimizer runs at cfg.TRAIN.lr / num_gpus, but the floor of the
+    inverse-sqrt schedule is the ratio lr_min / cfg.TRAIN.lr with the UNDIVIDED lr.  At 8 ranks the floor multiplier
+    must stay 1e-4 / 0.004 = 0.025 (not 0.2), i.e. lr keeps decaying past step 2500 down to lr_min / 8."""
+    import commu.engine.native_lm as nl
+    from commu.engine.trainer import Trainer, lr_multiplier
+    monkeypatch.setattr(nl.NativeLM, "__init__", _cpu_init(nl.NativeLM))
+    lr, lr_min, warm = 0.004, 1e-4, 100
+    for world in (1, 2, 8):
+        m = _model(d=64, H=1, Di=128, same=False)
+        tr = Trainer(m, lr=lr / world, warmup_step=warm, lr_min=lr_min, world=world, global_lr=lr)
+        for step in (0, 1, 50, 100, 101, 2500, 20000, 10 ** 6):
+            tr.step = step
+            ref = (lr / world) * lr_multiplier(step, warm, lr, lr_min)        # LambdaLR(lr_lambda) * local_lr
+            assert abs(tr.current_lr() - ref) < 1e-15, (world, step)
+        tr.step = 20000
+        assert abs(tr.current_lr() - (lr / world) * (warm ** 0.5) / (20000 ** 0.5)) < 1e-12   # still decaying
+        tr.step = 10 ** 7
+        assert abs(tr.current_lr() - lr_min / world) < 1e-15                                   # the floor
+
+
 def test_decode_plumbing(stub, monkeypatch):
     import commu.engine.decode as dec
     m = _model()

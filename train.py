@@ -164,7 +164,7 @@ def main(argv=None):
     comm = GradComm(rank, world, device) if distributed else None
     trainer = Trainer(model, lr=cfg.TRAIN.lr / world, warmup_step=cfg.TRAIN.warmup_step, lr_min=cfg.TRAIN.lr_min,
                       clip=cfg.TRAIN.clip, batch_chunk=cfg.TRAIN.batch_chunk, pad_id=vocab.pad_id, world=world,
-                      comm=comm)
+                      comm=comm, global_lr=cfg.TRAIN.lr, weight_decay=cfg.TRAIN.weight_decay)
     logger.info("=" * 100)
     logger.info(args)
     logger.info("=" * 100)
