@@ -147,6 +147,36 @@ def gemm(a, b, *, m, n, k, lda=None, ldb=None, a_mn=False, b_mn=False, split_k=1
     check(lib().commu_gemm_bf16(ctypes.byref(args), stream_ptr()))
 
 
+def attn_sizes(T, M, B, H):
+    """Byte sizes of the buffers of the materialised attention backward for one call of shape (T, M, B, H):
+    (p_save, mt_save, workspace, leading part of the workspace that must be zero on first use)."""
+    out = [c_int64(0) for _ in range(4)]
+    fn = lib().commu_relattn_bwd_sizes
+    fn.argtypes = [c_int, c_int, c_int, c_int] + [ctypes.POINTER(c_int64)] * 4
+    fn.restype = c_int
+    check(fn(T, M, B, H, *[ctypes.byref(o) for o in out]))
+    return tuple(int(o.value) for o in out)
+
+
+_attn_ws = {}
+
+
+def attn_bwd_workspace(T, M, B, H, device):
+    """The backward workspace of a shape, allocated (and zeroed) once and then shared by every layer and step of
+    that shape - the kernels keep its zero regions valid (include/commu_b200.h, commu_relattn_bwd).  At most two
+    shapes stay resident (a training run alternates between at most the warm-up and the steady-state memory length)."""
+    import torch
+    key = (T, M, B, H, str(device))
+    ws = _attn_ws.get(key)
+    if ws is None:
+        _, _, ws_bytes, _ = attn_sizes(T, M, B, H)
+        while len(_attn_ws) >= 2:
+            _attn_ws.pop(next(iter(_attn_ws)))
+        ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=device)
+        _attn_ws[key] = ws
+    return ws
+
+
 # ------------------------------------------------------------------------------------------------
 # Typed signatures of the remaining entry points (kept in one table so a CPU test can verify that
 # every symbol declared in include/commu_b200.h is exported and bound).
@@ -188,9 +218,12 @@ SIGNATURES = {
     "commu_sumsq": [P, L, P, P],
     "commu_clip_adam": [P, P, P, P, L, F, F, F, F, I, P, F, F, F, P, P],
     "commu_relattn_fwd": [P, L, P, P, L, P, L, I, P, P, P, I, I, I, I, I, I, F, P, L, P, P, P, P],
-    "commu_relattn_fwd_tc": [P, L, P, P, L, P, L, I, P, P, P, I, I, I, I, I, I, F, P, L, P, P, P, P],
+    "commu_relattn_fwd_tc": [P, L, P, P, L, P, L, I, P, P, P, I, I, I, I, I, I, F, P, L, P, P, P, P, P, P],
     "commu_relattn_bwd": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, L, P, P, L, P, P, L,
-                          P, P, L, P, P, P, P],
+                          P, P, L, P, P, P, P, P, P, L, P],
+    "commu_relattn_bwd_sizes": [I, I, I, I, P, P, P, P],
+    "commu_relattn_bwd_mat": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, P, P, L, P, L,
+                              P, P, L, P, P, P, P],
 }
 _bound = set()
 

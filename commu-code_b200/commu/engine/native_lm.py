@@ -110,6 +110,10 @@ class NativeLM:
         # attention forward implementation: "tc" = tcgen05 / TMEM kernel, "v1" = warp-MMA kernel
         self.attn_fwd_impl = {"tc": "commu_relattn_fwd_tc", "v1": "commu_relattn_fwd"}[
             os.environ.get("COMMU_ATTN_FWD", "tc")]
+        # attention backward: "mat" = probabilities stored by the forward, dS materialised once, band GEMMs
+        # (attn_bwd_mat.cu); "recompute" = the three recompute passes (no extra memory)
+        self.bwd_materialise = (os.environ.get("COMMU_ATTN_BWD", "mat") == "mat"
+                                and self.attn_fwd_impl == "commu_relattn_fwd_tc")
         self.saved = None
 
     # ------------------------------------------------------------------ weight shadows ------------
@@ -230,6 +234,8 @@ class NativeLM:
         if pd > 0:   # core_out = self.drop(word_emb)  (model.py:585); the dropped embedding is what enters the memory
             self._drop(x, rows, self.dp, pd, site_seed(dbase, 0, SITE_EMB), out_f32=x, out_bf16=cats[0][M * B:])
         layers_ctx = []
+        if save and self.bwd_materialise:
+            p_bytes, mt_bytes, _, _ = nv.attn_sizes(T, M, B, self.H)
         for l in range(self.L):
             s = S["layers"][l]
             cat = cats[l]
@@ -245,9 +251,19 @@ class NativeLM:
             qu = torch.empty(rows, self.hd, device=dev, dtype=bf) if save else None
             qv = torch.empty(rows, self.hd, device=dev, dtype=bf) if save else None
             nv.call("commu_relattn_set_dropout", float(patt), site_seed(dbase, l, SITE_ATT))
+            psv = mtv = None
+            if self.attn_fwd_impl == "commu_relattn_fwd_tc":
+                if save and self.bwd_materialise:
+                    # probabilities kept for the backward (2 bytes per score element; attn_bwd_mat.cu); never
+                    # initialised: the backward only reads the tiles the forward wrote
+                    psv = torch.empty(p_bytes, dtype=torch.uint8, device=dev)
+                    mtv = torch.empty(mt_bytes // 4, device=dev)
+                extra = (psv, mtv)
+            else:
+                extra = ()
             nv.call(self.attn_fwd_impl, q, self.hd, kv, kv[:, self.hd:], 2 * self.hd, r, self.hd, K,
                     S["u"], S["vb"], reset_u8, T, M, B, self.H, int(bool(same_length)), shift, scale,
-                    av, self.hd, lse, qu, qv)
+                    av, self.hd, lse, qu, qv, *extra)
             z1 = torch.empty(rows, self.dp, device=dev)
             # attn_out = self.drop(self.o_net(attn_vec)); w + attn_out  (model.py:348-352): dropout and residual are the
             # GEMM epilogue
@@ -279,7 +295,7 @@ class NativeLM:
                     nxt[M * B:], self.dp, mean2, rstd2)
             cats.append(nxt)
             if save:
-                layers_ctx.append(dict(kv=kv, r=r, av=av, lse=lse, qu=qu, qv=qv, z1=z1, mean1=mean1,
+                layers_ctx.append(dict(kv=kv, r=r, av=av, lse=lse, qu=qu, qv=qv, psv=psv, mtv=mtv, z1=z1, mean1=mean1,
                                        rstd1=rstd1, y1b=y1b, hdn=hdn, z2=z2, mean2=mean2, rstd2=rstd2))
             x = x_next
         # new memory: the last mem_len positions of [old mem ; this segment] for every layer input
@@ -420,10 +436,12 @@ class NativeLM:
             dkv = torch.empty(krows, 2 * self.hd, device=dev, dtype=bf)
             dr = torch.zeros(K, self.hd, device=dev)
             nv.call("commu_relattn_set_dropout", float(patt), site_seed(dbase, l, SITE_ATT))
+            ws = nv.attn_bwd_workspace(T, M, B, H, dev) if a.get("psv") is not None else None
             nv.call("commu_relattn_bwd", a["qu"], a["qv"], self.hd, a["kv"], a["kv"][:, self.hd:], 2 * self.hd,
                     a["r"], self.hd, K, c["reset_u8"], T, M, B, H, c["same_length"], c["shift"], c["scale"],
                     a["av"], self.hd, a["lse"], dav, self.hd, delta, dq, self.hd, dkv, dkv[:, self.hd:],
-                    2 * self.hd, dr, du, dvb)
+                    2 * self.hd, dr, du, dvb, a.get("psv"), a.get("mtv"), ws, ws.numel() if ws is not None else 0)
+            a["psv"] = a["mtv"] = None      # 2 GB per layer at the benchmark shape: release as soon as consumed
             g_qkv = grads[pre + "dec_attn.qkv_net.weight"]
             self._wgrad(dq, xb, self.hd, self.dp, rows, g_qkv[: H * Dh], rseg=Dh, rseg_pad=64)
             self._wgrad(dkv, cat, 2 * self.hd, self.dp, krows, g_qkv[H * Dh:], rseg=Dh, rseg_pad=64)

@@ -575,6 +575,7 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
                                  int shift, float scale, const void* out, int64_t ldo, const float* lse,
                                  const void* dout, int64_t lddo, float* delta_ws, void* dq, int64_t lddq,
                                  void* dk, void* dv, int64_t lddkv, float* dr, float* du, float* dvb,
+                                 const void* p_save, const float* mt_save, void* ws, int64_t ws_bytes,
                                  void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   attn::Params p = {};
@@ -608,6 +609,15 @@ extern "C" int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, co
                "relattn_bwd: out / dout must be 16-byte aligned with leading dims that are multiples of 8");
     attn_delta_kernel<<<(unsigned)((rows8 + 255) / 256), 256, 0, stream>>>(
         (const bf16*)out, ldo, (const bf16*)dout, lddo, T, B, H, delta_ws);
+  }
+  if (p_save) {   // product path: probabilities stored by the forward, dS materialised once (attn_bwd_mat.cu)
+    CB_REQUIRE(mt_save && ws, "relattn_bwd: p_save needs mt_save and a workspace");
+    int rcm = commu_relattn_bwd_mat(qu, qv, ldq, k, v, ldkv, r, ldr, kr, reset, T, M, B, H, same_length, shift, scale,
+                                    lse, dout, lddo, delta_ws, p_save, mt_save, ws, ws_bytes, dq, lddq, dk, dv,
+                                    lddkv, dr, du, dvb, stream_);
+    if (rcm) return rcm;
+    cb_host::count_launch(1);
+    return 0;
   }
   const int Ktot = T + M;
   // the tcgen05 dq and dR passes split d r_w_bias / d r_r_bias between them, so they are selected as a pair

@@ -16,6 +16,13 @@
 // by the two threads that own it).  Which block a 32-key chunk needs is warp-uniform except on the
 // diagonal chunk, so the re-read is `base - 2*lj` with immediate offsets.  T x K never exists in HBM.
 //
+// STORE (training): the probabilities are kept for the backward instead of being recomputed there.  Per key tile
+// the softmax threads also write P~ = bf16(exp2(s - m_tile)) - the very operand of the PV product, before the dropout
+// mask, with the SIGN bit set on dropped entries - into a 32 KB staging tile that warp 3 stores by TMA to
+// p_save [B*H, Tpad, Kp], and the running maximum m_tile the tile was taken at to mt_save [B*H, Kp/128, Tpad]; the
+// backward rebuilds P = P~ * exp2(m_tile - LSE) (attn_bwd_mat.cu).  2 bytes per score element, 2.1 GB per layer at
+// the benchmark shape, of the 180 GB.
+//
 // Replaces commu/model/model.py:312-345 (AC, BD, _rel_shift, mask, softmax, AV).
 #include <cuda_fp16.h>
 #include "api_common.h"
@@ -53,21 +60,28 @@ struct Smem {
   uint8_t qu[TILE_BYTES];
   uint8_t qv[TILE_BYTES];
   uint8_t k[2][TILE_BYTES];
-  uint8_t v[2][TILE_BYTES];
+  uint8_t v[TILE_BYTES];          // single buffer: V(t) is only needed at the end of tile t's softmax
   uint8_t r[2][TILE_BYTES];
   uint8_t bd[TM * STAGE_ROW];
+  uint8_t pst[2 * TILE_BYTES];    // STORE: P~ tile [key half][128 q rows][128 B] (128B swizzle), source of the TMA store
   float xch[4][TM];   // per-row partial max exchanged between the softmax warpgroups
   float xsum[4][TM];  // per-row partial sums (end of kernel)
   uint64_t q_ready;
-  uint64_t k_full[2], k_empty[2], v_full[2], v_empty[2], r_full[2], r_empty[2];
-  uint64_t s_full[2], s_empty[2], bd_full, bd_empty, p_full, o_full, o_empty;
+  uint64_t k_full[2], k_empty[2], v_full, v_empty, r_full[2], r_empty[2];
+  uint64_t s_full[2], s_empty[2], bd_full, bd_empty, p_full, o_full, o_empty, pst_full, pst_free;
   uint32_t tmem_base;
 };
 
-template <bool DROP>
+struct StoreArgs {
+  float* mt;        // [B*H, nkt, Tpad]
+  int Tpad, nkt;
+};
+
+template <bool DROP, bool STORE>
 __global__ void __launch_bounds__(NTHREADS, 1)
 relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
-                      const __grid_constant__ CUtensorMap tm_r, const Params p) {
+                      const __grid_constant__ CUtensorMap tm_r, const __grid_constant__ CUtensorMap tm_ps,
+                      const Params p, const StoreArgs sa) {
   extern __shared__ uint8_t smem_raw[];
   Smem& sm = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,10 +100,11 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     cb::mbar_init(&sm.q_ready, SOFT);
     for (int s = 0; s < 2; ++s) {
       cb::mbar_init(&sm.k_full[s], 1); cb::mbar_init(&sm.k_empty[s], 1);
-      cb::mbar_init(&sm.v_full[s], 1); cb::mbar_init(&sm.v_empty[s], 1);
       cb::mbar_init(&sm.r_full[s], 1); cb::mbar_init(&sm.r_empty[s], 1);
       cb::mbar_init(&sm.s_full[s], 1); cb::mbar_init(&sm.s_empty[s], SOFT);
     }
+    cb::mbar_init(&sm.v_full, 1); cb::mbar_init(&sm.v_empty, 1);
+    cb::mbar_init(&sm.pst_full, SOFT); cb::mbar_init(&sm.pst_free, 1);
     cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
     cb::mbar_init(&sm.p_full, SOFT);
     cb::mbar_init(&sm.o_full, 1); cb::mbar_init(&sm.o_empty, SOFT);
@@ -112,25 +127,30 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
   if (warp == 0) {
     // ============================== TMA producer ==============================
     if (cb::elect_one()) {
-      Ring rk, rv, rr;
+      Ring rk, rr;
       auto load_r = [&](int beta) {
         cb::mbar_wait(&sm.r_empty[rr.idx], rr.phase ^ 1);
         cb::mbar_arrive_expect_tx(&sm.r_full[rr.idx], TILE_BYTES);
         cb::tma_load_2d(sm.r[rr.idx], &tm_r, &sm.r_full[rr.idx], h * DH, dbase - TN * beta);
         rr.advance();
       };
-      load_r(0);
-      for (int t = 0; t < nt; ++t) {
-        const int j0 = (jt_first + t) * TN;
+      auto load_k = [&](int t) {
         cb::mbar_wait(&sm.k_empty[rk.idx], rk.phase ^ 1);
         cb::mbar_arrive_expect_tx(&sm.k_full[rk.idx], TILE_BYTES);
-        cb::tma_load_3d(sm.k[rk.idx], &tm_k, &sm.k_full[rk.idx], h * DH, b, j0);
+        cb::tma_load_3d(sm.k[rk.idx], &tm_k, &sm.k_full[rk.idx], h * DH, b, (jt_first + t) * TN);
         rk.advance();
-        load_r(t + 1);
-        cb::mbar_wait(&sm.v_empty[rv.idx], rv.phase ^ 1);
-        cb::mbar_arrive_expect_tx(&sm.v_full[rv.idx], TILE_BYTES);
-        cb::tma_load_3d(sm.v[rv.idx], &tm_v, &sm.v_full[rv.idx], h * DH, b, j0);
-        rv.advance();
+      };
+      load_r(0);
+      load_k(0);
+      load_r(1);
+      for (int t = 0; t < nt; ++t) {
+        if (t + 1 < nt) {          // the next tile's K and R never wait behind the single V buffer
+          load_k(t + 1);
+          load_r(t + 2);
+        }
+        cb::mbar_wait(&sm.v_empty, (t & 1) ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.v_full, TILE_BYTES);
+        cb::tma_load_3d(sm.v, &tm_v, &sm.v_full, h * DH, b, (jt_first + t) * TN);
       }
     }
   } else if (warp == 1) {
@@ -138,7 +158,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     if (cb::elect_one()) {
       const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);   // S, BD: both operands K-major
       const uint32_t idesc_o = cb::umma_idesc_bf16(TM, DH, 0, 1);   // PV: A in TMEM, B = V (MN-major)
-      Ring rk, rv, rr, rs;
+      Ring rk, rr, rs;
       uint32_t bd_phase = 0, p_phase = 0, o_phase = 0;
       const uint32_t a_qu = cb::smem_u32(sm.qu), a_qv = cb::smem_u32(sm.qv);
       cb::mbar_wait(&sm.q_ready, 0);
@@ -180,19 +200,33 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
           issue_bd();  // beta = t+2
         }
         cb::mbar_wait(&sm.p_full, p_phase);
-        cb::mbar_wait(&sm.v_full[rv.idx], rv.phase);
+        cb::mbar_wait(&sm.v_full, t & 1);
         cb::mbar_wait(&sm.o_empty, o_phase ^ 1);
         cb::tc_fence_after();
-        const uint64_t vd = cb::umma_smem_desc(cb::smem_u32(sm.v[rv.idx]), 8192, 1024);
+        const uint64_t vd = cb::umma_smem_desc(cb::smem_u32(sm.v), 8192, 1024);
 #pragma unroll
         for (int k = 0; k < TN / 16; ++k)
           umma_bf16_ts(tmem + COL_O, tmem + COL_P + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, k > 0);
-        cb::umma_commit(&sm.v_empty[rv.idx]);
+        cb::umma_commit(&sm.v_empty);
         cb::umma_commit(&sm.o_full);
-        rv.advance();
         p_phase ^= 1;
         o_phase ^= 1;
       }
+    }
+  } else if (warp == 3) {
+    // ============================== P~ store (TMA, shared -> global) ==============================
+    if (STORE && cb::elect_one()) {
+      const int row0 = (b * p.H + h) * sa.Tpad + i0;
+      for (int t = 0; t < nt; ++t) {
+        cb::mbar_wait(&sm.pst_full, t & 1);
+        const int j0 = (jt_first + t) * TN;
+        cb::tma_store_2d(&tm_ps, sm.pst, j0, row0);
+        cb::tma_store_2d(&tm_ps, sm.pst + TILE_BYTES, j0 + 64, row0);
+        cb::tma_store_commit();
+        cb::tma_store_wait_read<0>();
+        cb::mbar_arrive(&sm.pst_free);
+      }
+      cb::tma_store_wait<0>();
     }
   } else if (warp >= 4) {
     // ============================== softmax warpgroups ==============================
@@ -308,19 +342,38 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       m_run = mx;
       float rsum = 0.f;
       uint32_t pk[CPT / 2];
-#pragma unroll
-      for (int e = 0; e < CPT; e += 2) {
-        const float p0 = ex2(fmaf(s[e], sl2, -msafe)), p1 = ex2(fmaf(s[e + 1], sl2, -msafe));
-        rsum += p0 + p1;
-        pk[e / 2] = cb::pack_bf16(p0, p1);
+      uint32_t a_pst = 0;
+      if (STORE) {
+        if (t > 0) cb::mbar_wait(&sm.pst_free, (t - 1) & 1);      // the previous tile's TMA store has read the staging tile
+        a_pst = cb::smem_u32(sm.pst) + (g >> 1) * TILE_BYTES + li * 128;
+        if (g == 0 && i < p.T) sa.mt[((long long)(b * p.H + h) * sa.nkt + (jt_first + t)) * sa.Tpad + i] = msafe;
       }
-      if (DROP) {   // dropped probabilities feed P V only; the normaliser keeps every term (model.py:336-337)
 #pragma unroll
-        for (int q4 = 0; q4 < CPT / 4; ++q4) {
-          const uint2 rnd = drop::rand64((uint32_t)(jc0 >> 2) + q4, dkeys);
-          pk[2 * q4] &= drop::mask16x2(drop::keep_flags(rnd.x, p.drop_thr2));
-          pk[2 * q4 + 1] &= drop::mask16x2(drop::keep_flags(rnd.y, p.drop_thr2));
+      for (int c = 0; c < CPT / 8; ++c) {     // 8 keys = one 16-byte chunk of packed probabilities
+#pragma unroll
+        for (int e = c * 8; e < c * 8 + 8; e += 2) {
+          const float p0 = ex2(fmaf(s[e], sl2, -msafe)), p1 = ex2(fmaf(s[e + 1], sl2, -msafe));
+          rsum += p0 + p1;
+          pk[e / 2] = cb::pack_bf16(p0, p1);
         }
+        uint32_t ps0 = pk[4 * c], ps1 = pk[4 * c + 1], ps2 = pk[4 * c + 2], ps3 = pk[4 * c + 3];
+        if (DROP) {   // dropped probabilities feed P V only; the normaliser keeps every term (model.py:336-337)
+          const uint2 ra = drop::rand64((uint32_t)(jc0 >> 2) + 2 * c, dkeys);
+          const uint2 rb = drop::rand64((uint32_t)(jc0 >> 2) + 2 * c + 1, dkeys);
+          const uint32_t f0 = drop::keep_flags(ra.x, p.drop_thr2), f1 = drop::keep_flags(ra.y, p.drop_thr2);
+          const uint32_t f2 = drop::keep_flags(rb.x, p.drop_thr2), f3 = drop::keep_flags(rb.y, p.drop_thr2);
+          if (STORE) {  // sign bit = dropped (P~ >= 0, so the bit is free)
+            ps0 |= ~f0 & 0x80008000u; ps1 |= ~f1 & 0x80008000u;
+            ps2 |= ~f2 & 0x80008000u; ps3 |= ~f3 & 0x80008000u;
+          }
+          pk[4 * c] &= drop::mask16x2(f0); pk[4 * c + 1] &= drop::mask16x2(f1);
+          pk[4 * c + 2] &= drop::mask16x2(f2); pk[4 * c + 3] &= drop::mask16x2(f3);
+        }
+        if (STORE) sts_v4(a_pst + ((((g & 1) * 4 + c) ^ (li & 7)) << 4), ps0, ps1, ps2, ps3);
+      }
+      if (STORE) {
+        cb::fence_proxy_async();
+        cb::mbar_arrive(&sm.pst_full);
       }
       l_run = l_run * corr + rsum;
       // ---- fold the previous tile's partial O (scale of the previous max), then rescale ----
@@ -400,12 +453,19 @@ extern "C" int commu_relattn_set_dropout(float p, unsigned long long seed) {
   return 0;
 }
 
+namespace attn_tc {
+void psave_geometry(int T, int M, int* Tpad, int* Kp, int* nkt);   // attn_bwd_mat.cu
+}
+
 // Same contract as commu_relattn_fwd (the v1 warp-MMA kernel); this is the tcgen05 implementation.
+// p_save / mt_save (both or neither; sizes from commu_relattn_bwd_sizes): when given, the forward keeps the
+// un-normalised probabilities and the per-tile maxima for the materialised backward (commu_relattn_bwd).
 extern "C" int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                                     const void* r, int64_t ldr, int kr, const float* r_w_bias,
                                     const float* r_r_bias, const unsigned char* reset, int T, int M, int B,
                                     int H, int same_length, int shift, float scale, void* out, int64_t ldo,
-                                    float* lse, void* qu_save, void* qv_save, void* stream) {
+                                    float* lse, void* qu_save, void* qv_save, void* p_save, float* mt_save,
+                                    void* stream) {
   attn::Params p = {};
   p.q = (const bf16*)q; p.k = (const bf16*)k; p.v = (const bf16*)v; p.r = (const bf16*)r;
   p.qu_s = (bf16*)qu_save; p.qv_s = (bf16*)qv_save;
@@ -419,8 +479,10 @@ extern "C" int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, c
   if (rc) return rc;
   CB_REQUIRE(out && (ldo % 8 == 0), "relattn_fwd_tc: bad output");
   CB_REQUIRE((qu_save == nullptr) == (qv_save == nullptr), "relattn_fwd_tc: qu_save/qv_save must both be set or null");
+  CB_REQUIRE((p_save == nullptr) == (mt_save == nullptr), "relattn_fwd_tc: p_save/mt_save must both be set or null");
+  CB_REQUIRE(!p_save || lse, "relattn_fwd_tc: storing the probabilities needs the LSE output");
   const int Ktot = T + M;
-  CUtensorMap tk, tv, tr;
+  CUtensorMap tk, tv, tr, tps;
   // K and V live in the same [K*B, ldkv] matrix; each map starts at its own base pointer.  The column
   // extent is one head-row group of H*64 columns reachable from that base.
   rc = make_tmap_rows3d(&tk, k, (uint64_t)H * 64, B, Ktot, ldkv);
@@ -429,17 +491,34 @@ extern "C" int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, c
   if (rc) return rc;
   rc = cb_host::make_tmap_bf16_2d(&tr, r, (uint64_t)H * 64, kr, ldr, 64, 128);
   if (rc) return rc;
+  StoreArgs sa = {};
+  tps = tr;   // placeholder when nothing is stored (never dereferenced)
+  if (p_save) {
+    int Tpad, Kp, nkt;
+    psave_geometry(T, M, &Tpad, &Kp, &nkt);
+    sa.mt = mt_save; sa.Tpad = Tpad; sa.nkt = nkt;
+    rc = cb_host::make_tmap_bf16_2d(&tps, p_save, (uint64_t)Kp, (uint64_t)B * H * Tpad, Kp, 64, 128);
+    if (rc) return rc;
+  }
   static bool attr = false;
   const int smem_bytes = (int)sizeof(Smem) + 1024;
   if (!attr) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     attr = true;
   }
   dim3 grid(cb_host::ceil_div(T, TM), H, B);
-  cb_host::ProfScope prof(cb_host::PROF_ATTN_FWD, (cudaStream_t)stream);
-  if (p.drop_thr2) relattn_fwd_tc_kernel<true><<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(tk, tv, tr, p);
-  else relattn_fwd_tc_kernel<false><<<grid, NTHREADS, smem_bytes, (cudaStream_t)stream>>>(tk, tv, tr, p);
+  cudaStream_t st = (cudaStream_t)stream;
+  cb_host::ProfScope prof(cb_host::PROF_ATTN_FWD, st);
+  if (p.drop_thr2) {
+    if (p_save) relattn_fwd_tc_kernel<true, true><<<grid, NTHREADS, smem_bytes, st>>>(tk, tv, tr, tps, p, sa);
+    else relattn_fwd_tc_kernel<true, false><<<grid, NTHREADS, smem_bytes, st>>>(tk, tv, tr, tps, p, sa);
+  } else {
+    if (p_save) relattn_fwd_tc_kernel<false, true><<<grid, NTHREADS, smem_bytes, st>>>(tk, tv, tr, tps, p, sa);
+    else relattn_fwd_tc_kernel<false, false><<<grid, NTHREADS, smem_bytes, st>>>(tk, tv, tr, tps, p, sa);
+  }
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

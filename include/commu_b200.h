@@ -161,12 +161,16 @@ int commu_relattn_fwd(const void* q, int64_t ldq, const void* k, const void* v, 
                       float scale, void* out, int64_t ldo, float* lse, void* qu_save, void* qv_save,
                       void* stream);
 /* Same contract, tcgen05 implementation (TMA-staged K/V/R tiles, S / BD / PV accumulators in TMEM,
- * P fed to the PV MMA from TMEM).  Requires ldo % 8 == 0. */
+ * P fed to the PV MMA from TMEM).  Requires ldo % 8 == 0.
+ * p_save / mt_save (both or neither, sizes from commu_relattn_bwd_sizes): the forward additionally keeps, for the
+ * materialised backward, P~ = bf16(exp2(score - m_tile)) [B*H, Tpad, Kp] (sign bit = dropped by the attention
+ * dropout) and the per-(key tile, query row) maximum m_tile [B*H, Kp/128, Tpad] it was taken at (log2 domain);
+ * P = P~ * exp2(m_tile - LSE * log2 e). */
 int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, const void* v, int64_t ldkv,
                          const void* r, int64_t ldr, int kr, const float* r_w_bias, const float* r_r_bias,
                          const unsigned char* reset, int T, int M, int B, int H, int same_length, int shift,
                          float scale, void* out, int64_t ldo, float* lse, void* qu_save, void* qv_save,
-                         void* stream);
+                         void* p_save, float* mt_save, void* stream);
 /* Dropout on the attention probabilities (reference: self.dropatt, commu/model/model.py:211, 337) for the
  * subsequent tcgen05 attention calls of this process (forward and the three backward passes): p in [0, 1),
  * 0 = off.  Masks are a pure function of (seed, batch, head, query, key) and are recomputed in the backward, so
@@ -182,13 +186,29 @@ int commu_dropout(const void* x, int x_is_bf16, int64_t ldx, const float* res, i
                   void* stream);
 /* Backward of the above (the reference uses torch autograd).  dq: bf16 [T*B, lddq]; dk, dv: bf16
  * [K*B, lddkv] (every key row written); dr: fp32 [kr, H*64] and du, dvb: fp32 [H,64] are accumulated
- * (+=, caller zeroes); delta_ws: fp32 [B,H,T] workspace. */
+ * (+=, caller zeroes); delta_ws: fp32 [B,H,T] workspace.
+ * Product path (p_save, mt_save and ws given - what commu_relattn_fwd_tc stored): the score gradient is formed ONCE
+ * from the stored probabilities and written to the workspace in a coarse-sheared layout in which the relative shift
+ * is a TMA stride; dq, dR and the two bias gradients are then pure TMA + tcgen05.mma streams (csrc/attn_bwd_mat.cu).
+ * The first ws_zero_bytes of the workspace (commu_relattn_bwd_sizes) must be zero the first time it is used with a
+ * shape (T, M, B, H); the kernels keep it valid afterwards, so one buffer serves every layer and step of that shape.
+ * With p_save == NULL the three recompute passes run instead (no workspace). */
+int commu_relattn_bwd_sizes(int T, int M, int B, int H, int64_t* p_bytes, int64_t* mt_bytes, int64_t* ws_bytes,
+                            int64_t* ws_zero_bytes);
 int commu_relattn_bwd(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
                       int64_t ldkv, const void* r, int64_t ldr, int kr, const unsigned char* reset, int T,
                       int M, int B, int H, int same_length, int shift, float scale, const void* out,
                       int64_t ldo, const float* lse, const void* dout, int64_t lddo, float* delta_ws,
                       void* dq, int64_t lddq, void* dk, void* dv, int64_t lddkv, float* dr, float* du,
-                      float* dvb, void* stream);
+                      float* dvb, const void* p_save, const float* mt_save, void* ws, int64_t ws_bytes,
+                      void* stream);
+/* The materialised backward on its own (delta = rowsum(dO * O) [B,H,T] already computed). */
+int commu_relattn_bwd_mat(const void* qu, const void* qv, int64_t ldq, const void* k, const void* v,
+                          int64_t ldkv, const void* r, int64_t ldr, int kr, const unsigned char* reset, int T,
+                          int M, int B, int H, int same_length, int shift, float scale, const float* lse,
+                          const void* dout, int64_t lddo, const float* delta, const void* p_save,
+                          const float* mt_save, void* ws, int64_t ws_bytes, void* dq, int64_t lddq, void* dk,
+                          void* dv, int64_t lddkv, float* dr, float* du, float* dvb, void* stream);
 
 /* Run-time choice of the implementation of each backward pass used by commu_relattn_bwd:
  * 1 = tcgen05 kernel (default), 0 = v1 warp-MMA kernel, negative = leave unchanged. */

@@ -47,8 +47,11 @@ ATT_DROP_CASES = [
 ]
 
 
-@pytest.mark.parametrize("T,M,B,H,same_length,mem_len,with_reset", ATT_DROP_CASES)
-def test_relattn_dropout_fwd_bwd(T, M, B, H, same_length, mem_len, with_reset):
+@pytest.mark.parametrize("mat", [True, False])
+@pytest.mark.parametrize("T,M,B,H,same_length,mem_len,with_reset", ATT_DROP_CASES + [(2048, 2048, 1, 1, 0, 2048, 0)])
+def test_relattn_dropout_fwd_bwd(T, M, B, H, same_length, mem_len, with_reset, mat):
+    """mat: the product path (the forward stores the probabilities with the dropped entries flagged in the sign bit,
+    the backward never re-derives the mask); else the recompute passes (mask re-derived from the counter RNG)."""
     from commu import _native as nv
     p_att = 0.1
     seed = 0x0BAD_5EED_0000_0000 + T * 131 + M
@@ -79,13 +82,20 @@ def test_relattn_dropout_fwd_bwd(T, M, B, H, same_length, mem_len, with_reset):
     dr = torch.zeros(K, H * Dh, device=dev)
     du = torch.zeros(H, Dh, device=dev)
     dvb = torch.zeros(H, Dh, device=dev)
+    psv = mtv = ws = None
+    if mat:
+        p_bytes, mt_bytes, _, _ = nv.attn_sizes(T, M, B, H)
+        psv = torch.full((p_bytes // 2,), float("nan"), dtype=torch.bfloat16, device=dev)
+        mtv = torch.full((mt_bytes // 4,), float("nan"), device=dev)
+        ws = nv.attn_bwd_workspace(T, M, B, H, dev)
     nv.call("commu_relattn_set_dropout", p_att, seed)
     try:
         nv.call("commu_relattn_fwd_tc", q, H * Dh, k_t, v_t, 2 * H * Dh, r, H * Dh, K, u, vb, reset_u8,
-                T, M, B, H, same_length, shift, scale, out, H * Dh, lse, qu_s, qv_s)
+                T, M, B, H, same_length, shift, scale, out, H * Dh, lse, qu_s, qv_s, psv, mtv)
         nv.call("commu_relattn_bwd", qu_s, qv_s, H * Dh, k_t, v_t, 2 * H * Dh, r, H * Dh, K, reset_u8,
                 T, M, B, H, same_length, shift, scale, out, H * Dh, lse, dout, H * Dh, delta,
-                dq, H * Dh, dkv[:, :, 0], dkv[:, :, 1], 2 * H * Dh, dr, du, dvb)
+                dq, H * Dh, dkv[:, :, 0], dkv[:, :, 1], 2 * H * Dh, dr, du, dvb, psv, mtv, ws,
+                ws.numel() if ws is not None else 0)
     finally:
         nv.call("commu_relattn_set_dropout", 0.0, 0)
     torch.cuda.synchronize()

@@ -69,8 +69,9 @@ def test_relattn_fwd(T, M, B, H, same_length, mem_len, with_reset, impl):
     k_t = kv[:, :, 0]
     v_t = kv[:, :, 1]
     reset_u8 = reset.to(torch.uint8) if reset is not None else None
+    extra = (None, None) if impl == "commu_relattn_fwd_tc" else ()      # p_save, mt_save (tcgen05 entry point only)
     nv.call(impl, q, H * Dh, k_t, v_t, 2 * H * Dh, r, H * Dh, K, u, vb, reset_u8,
-            T, M, B, H, same_length, shift, scale, out, H * Dh, lse, None, None)
+            T, M, B, H, same_length, shift, scale, out, H * Dh, lse, None, None, *extra)
     torch.cuda.synchronize()
     ref, ref_lse, _, _ = _relattn_ref(q.float(), k_t.float(), v_t.float(), r.float(), u, vb, reset, T, M,
                                       B, H, Dh, same_length, shift, scale)
@@ -82,10 +83,15 @@ def test_relattn_fwd(T, M, B, H, same_length, mem_len, with_reset, impl):
 
 @pytest.mark.parametrize("T,M,B,H,same_length,mem_len,with_reset", ATT_CASES + [(300, 500, 2, 2, 0, 512, 1),
                                                                          (384, 384, 1, 2, 1, 384, 0)])
-@pytest.mark.parametrize("impl", ["tc", "v1"])
+@pytest.mark.parametrize("impl", ["mat", "tc", "v1"])
 def test_relattn_bwd(T, M, B, H, same_length, mem_len, with_reset, impl):
+    """mat = product path (probabilities stored by the tcgen05 forward, dS materialised once, band GEMMs);
+    tc / v1 = the recompute passes (tcgen05 / warp-MMA)."""
     from commu import _native as nv
     L = nv.lib()
+    if impl == "mat":
+        _relattn_bwd_case(nv, T, M, B, H, same_length, mem_len, with_reset, fwd_impl="commu_relattn_fwd_tc", mat=True)
+        return
     flag = 1 if impl == "tc" else 0
     L.commu_relattn_bwd_set_impl(flag, flag, flag)
     try:
@@ -94,7 +100,7 @@ def test_relattn_bwd(T, M, B, H, same_length, mem_len, with_reset, impl):
         L.commu_relattn_bwd_set_impl(1, 1, 1)
 
 
-def _relattn_bwd_case(nv, T, M, B, H, same_length, mem_len, with_reset, fwd_impl="commu_relattn_fwd"):
+def _relattn_bwd_case(nv, T, M, B, H, same_length, mem_len, with_reset, fwd_impl="commu_relattn_fwd", mat=False):
     torch.manual_seed(T * 17 + M)
     dev = "cuda"
     K = T + M
@@ -116,8 +122,18 @@ def _relattn_bwd_case(nv, T, M, B, H, same_length, mem_len, with_reset, fwd_impl
     qv_s = torch.zeros_like(qu_s)
     k_t, v_t = kv[:, :, 0], kv[:, :, 1]
     reset_u8 = reset.to(torch.uint8) if reset is not None else None
+    psv = mtv = ws = None
+    extra = ()
+    if fwd_impl == "commu_relattn_fwd_tc":
+        if mat:
+            p_bytes, mt_bytes, _, _ = nv.attn_sizes(T, M, B, H)
+            # poisoned, not zeroed: the backward may only read what the forward wrote
+            psv = torch.full((p_bytes // 2,), float("nan"), dtype=torch.bfloat16, device=dev)
+            mtv = torch.full((mt_bytes // 4,), float("nan"), device=dev)
+            ws = nv.attn_bwd_workspace(T, M, B, H, dev)
+        extra = (psv, mtv)
     nv.call(fwd_impl, q, H * Dh, k_t, v_t, 2 * H * Dh, r, H * Dh, K, u, vb, reset_u8,
-            T, M, B, H, same_length, shift, scale, out, H * Dh, lse, qu_s, qv_s)
+            T, M, B, H, same_length, shift, scale, out, H * Dh, lse, qu_s, qv_s, *extra)
     dout = (torch.randn(T, B, H * Dh, device=dev) * 0.5).bfloat16()
     delta = torch.empty(B, H, T, device=dev)
     dq = torch.zeros(T, B, H * Dh, device=dev, dtype=torch.bfloat16)
@@ -127,7 +143,8 @@ def _relattn_bwd_case(nv, T, M, B, H, same_length, mem_len, with_reset, fwd_impl
     dvb = torch.zeros(H, Dh, device=dev)
     nv.call("commu_relattn_bwd", qu_s, qv_s, H * Dh, k_t, v_t, 2 * H * Dh, r, H * Dh, K, reset_u8,
             T, M, B, H, same_length, shift, scale, out, H * Dh, lse, dout, H * Dh, delta,
-            dq, H * Dh, dkv[:, :, 0], dkv[:, :, 1], 2 * H * Dh, dr, du, dvb)
+            dq, H * Dh, dkv[:, :, 0], dkv[:, :, 1], 2 * H * Dh, dr, du, dvb, psv, mtv, ws,
+            ws.numel() if ws is not None else 0)
     torch.cuda.synchronize()
     # autograd reference on the same bf16-rounded operands (qu, qv are leaves: d/dq = d/dqu + d/dqv)
     quf = qu_s.view(T, B, H, Dh).float().requires_grad_(True)
@@ -182,10 +199,11 @@ def test_relattn_fwd_bench_shapes(T, M, B, H, same_length, mem_len, with_reset):
     test_relattn_fwd(T, M, B, H, same_length, mem_len, with_reset, "commu_relattn_fwd_tc")
 
 
+@pytest.mark.parametrize("mat", [True, False])
 @pytest.mark.parametrize("T,M,B,H,same_length,mem_len,with_reset", BIG_CASES)
-def test_relattn_bwd_bench_shapes(T, M, B, H, same_length, mem_len, with_reset):
+def test_relattn_bwd_bench_shapes(T, M, B, H, same_length, mem_len, with_reset, mat):
     from commu import _native as nv
-    _relattn_bwd_case(nv, T, M, B, H, same_length, mem_len, with_reset, fwd_impl="commu_relattn_fwd_tc")
+    _relattn_bwd_case(nv, T, M, B, H, same_length, mem_len, with_reset, fwd_impl="commu_relattn_fwd_tc", mat=mat)
 
 
 @pytest.mark.parametrize("r_std", [4.0, 8.0])
@@ -208,7 +226,7 @@ def test_relattn_fwd_large_position_scores(r_std):
     lse = torch.zeros(B, H, T, device=dev)
     k_t, v_t = kv[:, :, 0], kv[:, :, 1]
     nv.call("commu_relattn_fwd_tc", q, H * Dh, k_t, v_t, 2 * H * Dh, r, H * Dh, K, u, vb, None,
-            T, M, B, H, 0, T, scale, out, H * Dh, lse, None, None)
+            T, M, B, H, 0, T, scale, out, H * Dh, lse, None, None, None, None)
     torch.cuda.synchronize()
     ref, ref_lse, _, s = _relattn_ref(q.float(), k_t.float(), v_t.float(), r.float(), u, vb, None, T, M,
                                       B, H, Dh, 0, T, scale)

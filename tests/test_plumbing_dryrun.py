@@ -126,6 +126,7 @@ def _cpu_init(cls):
         self._pos_cache = {}
         self.saved = None
         self.attn_fwd_impl = "commu_relattn_fwd"
+        self.bwd_materialise = False
     return init
 
 
