@@ -263,6 +263,154 @@ class InferenceTask:
                     notes += 1
         return notes > 0
 
+    # ------------------------------------------------------------------------------------------------
+    # batched generation: the SAME loop, one coroutine per sequence, lock-stepped on the
+    # batch decode engine.  Every sequence asks for a model step exactly where the reference calls
+    # calc_logits_and_mems and for a token where it calls infer_token; all sequences of a batch receive their
+    # step from ONE launch sequence (one token each), their samples from one sampler launch with per-sequence
+    # wrong-token masks on the device, and the host sees one [B] token copy per wave instead of one .item() per
+    # token and sequence.  Quirks kept: Q1 (the first step's memory is dropped: the shared ring state is rewound
+    # once), Q2 (a forced token is fed again by the next ordinary iteration), Q3 (re-used logits are divided by the
+    # temperature again: the sampler gets temperature ** k), Q4 (token 0 never sampled), Q5 (sampling failure
+    # discards the sequence).
+    # ------------------------------------------------------------------------------------------------
+    def _sequence_steps(self, seq):
+        """generate_sequence (reference midi_inferrer.py:239-320) as a coroutine.  Yields ("step", token, keep) /
+        ("sample", k, wrong_tokens); returns the finished sequence or None."""
+        teacher = TeacherForceTask(self.input_data)
+        first, have_logits, ndiv = True, False, 0
+        for _ in range(self.inference_cfg.GENERATION.generation_length):
+            if seq[-1] == _T["EOS"]:
+                break
+            if teacher.next_tokens_forced:
+                seq.append(teacher.next_tokens_forced.pop(0))
+                yield ("step", seq[-1], True)
+                have_logits, ndiv = True, 0
+                continue
+            if teacher.no_sequence_appended:
+                assert have_logits
+                teacher.no_sequence_appended = False
+            elif first:
+                yield ("step", seq[-1], False)
+                first, have_logits, ndiv = False, True, 0
+            else:
+                yield ("step", seq[-1], True)
+                have_logits, ndiv = True, 0
+            ndiv += 1                                            # calc_probs: logits /= temperature, in place
+            if not teacher.incomplete_filled:
+                teacher.incomplete_filled = seq.count(_T["BAR"]) > 1
+            if teacher.check_first_position(seq):
+                teacher.teach_first_position()
+                continue
+            if teacher.check_one_chord_per_bar_case(seq) or teacher.check_mul_chord_per_bar_case(seq):
+                teacher.teach_chord_token()
+                continue
+            token = yield ("sample", ndiv, list(teacher.wrong_tokens))
+            if token < 0:                                        # all mass rejected (reference: RuntimeError)
+                logger.error("Sampling Error: probability tensor contains either `inf`, `nan` or element < 0")
+                return None
+            if teacher.check_chord_position_passed(token):
+                teacher.teach_chord_position()
+            elif teacher.check_wrong_chord_token_generated(token):
+                teacher.teach_wrong_chord_token(token)
+            elif teacher.check_wrong_eos_generated(token):
+                teacher.teach_remnant_chord()
+            elif teacher.check_wrong_bar_token_generated(token):
+                teacher.teach_eos()
+            else:
+                seq.append(token)
+        try:
+            teacher.validate_teacher_forced_sequence(seq)
+        except Exception as err:  # noqa: BLE001 - same catch-all as the reference
+            logger.error(err)
+            return None
+        return seq
+
+    @torch.no_grad()
+    def generate_batch(self, encoded_meta: List[int], n: int):
+        """Runs n sequences of the same metadata together.  Returns a list of n entries (sequence or None)."""
+        eng = self._batch_engine(n)
+        B, V, dev = eng.B, eng.V, self.device
+        temp = float(self.input_data.temperature)
+        top_k = int(self.input_data.top_k)
+        top_p = float(getattr(self.input_data, "top_p", 0.0) or 0.0)
+        ctx = [0] + list(encoded_meta)
+        state = DecodeState()
+        for t in ctx[:-1]:                                       # init_seq_and_mems: memory of [0] + meta[:-1]
+            _, state = eng.step(torch.full((B,), t, dtype=torch.int64, device=dev), state)
+        gens = [self._sequence_steps(list(ctx)) for _ in range(n)]
+        done = [None] * n
+        live = {}
+
+        def advance(row, value=None):
+            """Runs sequence `row` up to its next request (or to its end)."""
+            try:
+                live[row] = gens[row].send(value) if row in live else next(gens[row])
+            except StopIteration as fin:
+                live.pop(row, None)
+                done[row] = fin.value
+        for row in range(n):
+            advance(row)
+        tok_h = torch.zeros(B, dtype=torch.int64).pin_memory()
+        wrong = torch.zeros(B, V, dtype=torch.uint8, device=dev)
+        toks_d = torch.empty(B, dtype=torch.int64, device=dev)
+        while live:
+            # ---- one model step for every live sequence ----
+            keeps = {req[2] for req in live.values()}
+            assert all(req[0] == "step" for req in live.values()) and len(keeps) == 1
+            tok_h.zero_()
+            for row, req in live.items():
+                tok_h[row] = req[1]
+            logits, new_state = eng.step(tok_h.to(dev), state)
+            if keeps.pop():
+                state = new_state                                # (Q1: the first step's memory is dropped)
+            for row in list(live):
+                advance(row)
+            # ---- sampling waves: first draws together, re-draws after a rejected token as they come ----
+            while any(req[0] == "sample" for req in live.values()):
+                rows = [r for r, req in live.items() if req[0] == "sample"]
+                k = min(live[r][1] for r in rows)
+                rows = [r for r in rows if live[r][1] == k]
+                wrong.zero_()
+                for r in rows:
+                    if live[r][2]:
+                        wrong[r, live[r][2]] = 1
+                self._draws += 1
+                nv.call("commu_sample", logits, logits.stride(0), B, V, temp ** k if temp != 0 else 0.0, top_k, top_p,
+                        wrong, self.seed, self._draws, toks_d, None, V, None)
+                got = toks_d.cpu()
+                for r in rows:
+                    advance(r, int(got[r]))
+        return done
+
+    def _batch_engine(self, n):
+        if n > 64:
+            raise ValueError("generate_batch: at most 64 sequences per batch")
+        eng = getattr(self, "_beng", None)
+        if eng is None or eng.B < n:
+            eng = DecodeEngine(self.model, batch=n, mem_len=self.model.mem_len, same_length=self.model.same_length,
+                               precision=self.precision)
+            self._beng = eng
+        return eng
+
+    def execute_batched(self, encoded_meta, max_rounds=None) -> List[List[int]]:
+        """execute() with the sequences of a round generated together; failed sequences (teacher-forcing
+        validation, empty sequence, sampling failure) are regenerated in the next round, like the reference."""
+        want = int(self.input_data.num_generate)
+        sequences, rounds = [], 0
+        while len(sequences) < want and (max_rounds is None or rounds < max_rounds):
+            rounds += 1
+            n = min(want - len(sequences), 64)
+            logger.info("Generating %d sequence(s) together (round %d)" % (n, rounds))
+            for seq in self.generate_batch(encoded_meta, n):
+                if seq is None:
+                    continue
+                if not self.validate_generated_sequence(seq):
+                    logger.error("Empty sequence generated")
+                    continue
+                sequences.append(seq)
+        return sequences[:want]
+
     def execute(self, encoded_meta) -> List[List[int]]:
         n_cond = len(encoded_meta)
         sequences = []

@@ -60,47 +60,79 @@ class ComMUDataset:
         pin = torch.cuda.is_available() and torch.device(device).type == "cuda"
 
         def gen():
+            """Batches are produced ONE AHEAD of the consumer: batch k+1 is packed into the next pinned staging set
+            and its host->device copy is issued on a side stream before batch k is handed out, so packing and the
+            copy overlap the training step of batch k.  A staging set is reused only after the
+            copy that read it has completed (one CUDA event per set) - there is no per-batch stream synchronise."""
             assert batch_size < n
             order = np.arange(n)
             rng = np.random.RandomState(seed) if do_shuffle else None
             if do_shuffle:
                 rng.shuffle(order)
-            cur_sample = list(range(batch_size))     # per column: index into `order`
-            cur_pos = [0] * batch_size
-            upcoming = batch_size
-            data = torch.empty(bptt, batch_size, dtype=torch.int64, pin_memory=pin)
-            target = torch.empty(bptt, batch_size, dtype=torch.int64, pin_memory=pin)
-            reset = torch.empty(batch_size, dtype=torch.bool, pin_memory=pin)
-            while True:
-                data.fill_(pad)
-                target.fill_(pad)
-                reset.fill_(False)
-                n_tok = 0
-                for col in range(batch_size):
-                    # a column whose sample is exhausted moves to the next unclaimed sample
-                    while cur_sample[col] < n and cur_pos[col] + 1 >= lens[order[cur_sample[col]]]:
-                        cur_sample[col], cur_pos[col] = upcoming, 0
-                        upcoming += 1
-                        reset[col] = True
-                    if cur_sample[col] >= n:
-                        continue
-                    seq = seqs[order[cur_sample[col]]]
-                    p = cur_pos[col]
-                    take = min(len(seq) - 1 - p, bptt)
-                    data[:take, col] = seq[p:p + take]
-                    target[:take, col] = seq[p + 1:p + 1 + take]
-                    cur_pos[col] = p + take
-                    n_tok += take
-                if n_tok == 0:
+            st = dict(cur_sample=list(range(batch_size)), cur_pos=[0] * batch_size, upcoming=batch_size, k=0)
+            depth = 3
+            stage = [(torch.empty(bptt, batch_size, dtype=torch.int64, pin_memory=pin),
+                      torch.empty(bptt, batch_size, dtype=torch.int64, pin_memory=pin),
+                      torch.empty(batch_size, dtype=torch.bool, pin_memory=pin)) for _ in range(depth if pin else 1)]
+            copied = [None] * len(stage)
+            copy_stream = torch.cuda.Stream(device) if pin else None
+
+            def produce():
+                slot = st["k"] % len(stage)
+                st["k"] += 1
+                data, target, reset = stage[slot]
+                if copied[slot] is not None:
+                    copied[slot].synchronize()           # the copy issued `depth` batches ago has read this set
+                while True:
+                    data.fill_(pad)
+                    target.fill_(pad)
+                    reset.fill_(False)
+                    n_tok = 0
+                    cur_sample, cur_pos = st["cur_sample"], st["cur_pos"]
+                    for col in range(batch_size):
+                        # a column whose sample is exhausted moves to the next unclaimed sample
+                        while cur_sample[col] < n and cur_pos[col] + 1 >= lens[order[cur_sample[col]]]:
+                            cur_sample[col], cur_pos[col] = st["upcoming"], 0
+                            st["upcoming"] += 1
+                            reset[col] = True
+                        if cur_sample[col] >= n:
+                            continue
+                        seq = seqs[order[cur_sample[col]]]
+                        p = cur_pos[col]
+                        take = min(len(seq) - 1 - p, bptt)
+                        data[:take, col] = seq[p:p + take]
+                        target[:take, col] = seq[p + 1:p + 1 + take]
+                        cur_pos[col] = p + take
+                        n_tok += take
+                    if n_tok > 0:
+                        break
                     if not do_shuffle:
-                        return
+                        return None
                     rng.shuffle(order)
-                    cur_sample, cur_pos, upcoming = list(range(batch_size)), [0] * batch_size, batch_size
-                    continue
-                yield (data.to(device, non_blocking=pin), target.to(device, non_blocking=pin),
-                       reset.to(device, non_blocking=pin), n_tok)
+                    st["cur_sample"], st["cur_pos"], st["upcoming"] = list(range(batch_size)), [0] * batch_size, batch_size
+                if not pin:      # (a CPU "copy" would alias the staging set that the look-ahead overwrites)
+                    return (data.to(device, copy=True), target.to(device, copy=True), reset.to(device, copy=True), n_tok)
+                with torch.cuda.stream(copy_stream):
+                    out = (data.to(device, non_blocking=True), target.to(device, non_blocking=True),
+                           reset.to(device, non_blocking=True))
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                copied[slot] = ev
+                return out + (n_tok, ev)
+
+            nxt = produce()
+            while nxt is not None:
+                cur = nxt
+                nxt = produce()                          # pack + copy the next batch before this one is consumed
                 if pin:
-                    torch.cuda.current_stream().synchronize()   # staging buffers are reused next batch
+                    d_, t_, r_, n_tok, ev = cur
+                    consumer = torch.cuda.current_stream(device)
+                    consumer.wait_event(ev)
+                    for x in (d_, t_, r_):
+                        x.record_stream(consumer)
+                    yield d_, t_, r_, n_tok
+                else:
+                    yield cur
 
         return gen
 

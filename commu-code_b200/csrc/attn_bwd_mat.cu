@@ -130,9 +130,18 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
         cb::tma_load_3d(sm.dout[bi], &tm_do, &sm.q_full[bi], h * DH, b, i0);
         cb::tma_load_3d(sm.qu[bi], &tm_qu, &sm.q_full[bi], h * DH, b, i0);
       };
+      // the P~ stream comes from HBM and the two-stage ring only covers one tile of latency: pull the tiles two and
+      // three steps ahead into L2 (no shared memory needed), so the staged load that follows is an L2 hit
+      auto prefetch_p = [&](int n) {
+        const int i0 = (it_first + n) * TM;
+        cb::tma_prefetch_2d(&tm_p, j0, bh * p.Tpad + i0);
+        cb::tma_prefetch_2d(&tm_p, j0 + 64, bh * p.Tpad + i0);
+      };
       load_q(0);
+      for (int n = 1; n < 4 && n < nq; ++n) prefetch_p(n);
       for (int n = 0; n < nq; ++n) {
         if (n + 1 < nq) load_q(n + 1);
+        if (n + 4 < nq) prefetch_p(n + 4);
         const int bi = n & 1;
         const int i0 = (it_first + n) * TM;
         cb::mbar_wait(&sm.pds_full[bi], (n >> 1) & 1);
@@ -623,7 +632,7 @@ extern "C" int commu_relattn_bwd_mat(const void* qu, const void* qv, int64_t ldq
   const Geo g = geometry(T, M, B, H);
   CB_REQUIRE(ws_bytes >= g.ds_bytes + g.rrev_bytes + g.da_bytes, "relattn_bwd_mat: workspace too small (%lld < %lld)",
              (long long)ws_bytes, (long long)(g.ds_bytes + g.rrev_bytes + g.da_bytes));
-  CB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 1023) == 0, "relattn_bwd_mat: workspace must be 1024-byte aligned");
+  CB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 127) == 0, "relattn_bwd_mat: workspace must be 128-byte aligned");
   bf16* ds = (bf16*)ws;
   bf16* rrev = (bf16*)((uint8_t*)ws + g.ds_bytes);
   float* da = (float*)((uint8_t*)ws + g.ds_bytes + g.rrev_bytes);

@@ -305,6 +305,65 @@ def gen_teacher_case(name):
     print("wrote", name)
 
 
+GENERATE_META = [574, 623, 627, 635, 639, 642, 651, 684, 694, 720, 727]
+GENERATE_SCENARIOS = {
+    # name: (weight seed, weight std, logit bias of BAR, num_measures, chord tokens, chord positions, generation_length)
+    "a": (1, 0.35, 3.0, 4, [200, 210, 220, 230, 240], [432, 496, 432, 432, 480], 200),
+    "b": (4, 0.35, 3.0, 4, [200, 210, 220, 230, 240], [432, 496, 432, 432, 480], 200),
+    "c": (1, 0.5, 4.0, 4, [200, 210, 220, 230, 240], [432, 496, 432, 432, 480], 200),     # 67 tokens > mem_len 48
+}
+GENERATE_CFG = dict(n_layer=2, n_head=4, d_model=64, d_inner=128, tgt_len=1, mem_len=48, same_length=True, clamp_len=-1)
+
+
+def generate_logit_bias(bar):
+    """Output-bias pattern that makes a random tiny model emit bars, positions and an end-of-sequence now and then,
+    so that the greedy run walks through the teacher-forcing branches."""
+    bias = {2: bar, 1: bar - 1.5}
+    bias.update({t: 1.5 for t in range(433, 560, 5)})
+    return bias
+
+
+def gen_generate_case(name):
+    """REAL tiny reference model + the reference's own InferenceTask.generate_sequence at temperature 0 (chord teacher
+    forcing: first position, one-chord / inter-chord cases, skipped chord position, end of sequence).  The raw
+    sequence is recorded before validate_teacher_forced_sequence judges it (a random model rarely produces the
+    right number of bars), so the test compares every generated and forced token."""
+    _stub_modules()
+    from commu.midi_generator.midi_inferrer import InferenceTask, TeacherForceTask
+    out = {"meta": np.array(GENERATE_META, dtype=np.int64)}
+    for sc, (seed, std, bar, nm, ctok, cpos, gen_len) in GENERATE_SCENARIOS.items():
+        model = build_ref_model(GENERATE_CFG, 729, seed, std)
+        with torch.no_grad():
+            for tok, val in generate_logit_bias(bar).items():
+                model.crit.out_layers[0].bias[tok] = val
+        model.eval()
+        model.reset_length(1, GENERATE_CFG["mem_len"])
+        task = InferenceTask(torch.device("cpu"))
+        task(model, SimpleNamespace(num_measures=nm, temperature=0.0, top_k=32, num_generate=1,
+                                    chord_token_components={"chord_token": list(ctok), "chord_position": list(cpos)}),
+             SimpleNamespace(GENERATION=SimpleNamespace(generation_length=gen_len)))
+        keep = {}
+        orig = TeacherForceTask.validate_teacher_forced_sequence
+
+        def record(self, seq, keep=keep, orig=orig):
+            keep["seq"] = list(seq)
+            return orig(self, seq)
+        TeacherForceTask.validate_teacher_forced_sequence = record
+        try:
+            with torch.no_grad():
+                seq, mems = task.init_seq_and_mems(list(GENERATE_META), len(GENERATE_META))
+                verdict = task.generate_sequence(seq, mems)
+        finally:
+            TeacherForceTask.validate_teacher_forced_sequence = orig
+        for k, v in state_np(model).items():
+            out[sc + "/" + k] = v
+        out[sc + "/raw"] = np.array(keep["seq"], dtype=np.int64)
+        out[sc + "/valid"] = np.array([verdict is not None])
+        print(" generate", sc, "->", len(keep["seq"]), "tokens,", "valid" if verdict is not None else "rejected by validation")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def main():
     sys.path.insert(0, REF)
     torch.set_num_threads(4)
@@ -322,6 +381,7 @@ def main():
     gen_sampler_case("sampler_probs", seed=14)
     gen_dataset_case("dataset_batches", seed=16)
     gen_teacher_case("teacher_forcing")
+    gen_generate_case("generate_greedy")
     cfgE = dict(n_layer=2, n_head=2, d_model=32, d_inner=64, tgt_len=10, mem_len=10,
                 same_length=False, clamp_len=-1)
     gen_train_case("train_steps", cfgE, n_token=61, B=4, chunks=2, n_steps=6, seed=15, std=0.05,

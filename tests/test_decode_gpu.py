@@ -275,8 +275,9 @@ def test_decode_greedy_512_tokens_at_bench_shape(precision):
     oracle's tokens so a disagreement cannot hide later ones.
       fp32 engine: the identical token at every step whose oracle top-2 margin exceeds fp32 summation-order noise (1e-4).
       bf16 engine (throughput mode; bf16 K/V cache and weights): logits within the bf16 tolerance, identical tokens
-      wherever the margin exceeds 4x the measured logit error - it is NOT bit-exact by construction, which is why
-      bench.py's headline decode number is the fp32 engine."""
+      wherever the margin exceeds twice the step's measured logit error (the two leading logits can move against each
+      other by at most that much) - it is NOT bit-exact by construction, which is why bench.py's headline decode
+      number is the fp32 engine."""
     from commu.engine.decode import DecodeEngine
     assert not torch.backends.cuda.matmul.allow_tf32
     L, H, d, Di, V, mem_len, B = 12, 8, 512, 2048, 729, 2048, 2
@@ -289,7 +290,7 @@ def test_decode_greedy_512_tokens_at_bench_shape(precision):
     eng = DecodeEngine(model, batch=B, mem_len=mem_len, same_length=True, precision=precision)
     g = torch.Generator().manual_seed(5)
     ctx = torch.randint(1, V, (mem_len + 1, B), generator=g).cuda()
-    worst, scale, thin, wrong = 0.0, 0.0, 0, 0
+    worst, scale, thin, wrong, same = 0.0, 0.0, 0, 0, 0
     with torch.no_grad():
         _, mems = orc.forward_generate(cfg, Pg, ctx[:-1], None)
         _, st = eng.prefill(ctx[:-1])
@@ -304,7 +305,8 @@ def test_decode_greedy_512_tokens_at_bench_shape(precision):
             margin = (top2[:, 0] - top2[:, 1])
             err = float((lg - ref).abs().max())
             worst, scale = max(worst, err), max(scale, float(ref.abs().max()))
-            bound = 1e-4 if precision == "fp32" else 4 * max(err, 1e-3)
+            bound = 1e-4 if precision == "fp32" else 2 * err
+            same += int((tok_n == tok_o).sum())
             for b in range(B):
                 if float(margin[b]) > bound:
                     wrong += int(tok_n[b]) != int(tok_o[b])
@@ -317,4 +319,9 @@ def test_decode_greedy_512_tokens_at_bench_shape(precision):
         assert thin <= 4, thin
     else:
         assert worst < 0.06 * scale + 0.02, (worst, scale)
-        assert thin <= 0.2 * 512 * B, thin
+        assert same >= 0.6 * 512 * B, (same, thin)      # most greedy tokens still agree (recorded, not a parity claim)
+    import json, os
+    from helpers import ROOT
+    with open(os.path.join(ROOT, "gpurun_out", "decode_parity_%s.json" % precision), "w") as f:
+        json.dump({"precision": precision, "steps": 512, "batch": B, "identical_tokens": same, "thin_margin_steps": thin,
+                   "wrong_with_margin": wrong, "worst_logit_err": worst, "logit_scale": scale}, f)

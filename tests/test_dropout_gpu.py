@@ -141,7 +141,7 @@ def test_relattn_dropout_fwd_bwd(T, M, B, H, same_length, mem_len, with_reset, m
     close(dvb, qvf.grad.sum((0, 1)), "dvb")
     # the mask really bites: without it the output differs
     o_nodrop = torch.einsum("bhij,jbhd->ibhd", pr, vf).detach()
-    assert (o_nodrop - o_ref.detach()).abs().max().item() > 0.05
+    assert (o_nodrop - o_ref.detach()).abs().max().item() > (0.05 if K <= 1024 else 0.02)   # (long rows average the mask out)
 
 
 def _tiny_model(dropout, dropatt):

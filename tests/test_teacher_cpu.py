@@ -71,3 +71,129 @@ def test_teacher_predicates():
     assert t.check_wrong_chord_token_generated(195) and t.check_wrong_eos_generated(1)
     t.teach_remnant_chord()
     assert t.next_tokens_forced[-1] == 496
+
+
+def _scripted_sampler(script_state, script, logits, temperature, k, top_k, wrong):
+    """What the sampler kernel does with one row (softmax(l / T^k) -> top-k -> wrong-token mask -> renormalise),
+    followed by the scripted 'draw' of the golden generator (arg-max; advances the script pointer)."""
+    lg = logits / (temperature ** k)
+    probs = F.pad(F.softmax(lg, dim=-1), [1, 0])
+    _, idx = torch.topk(probs, top_k)
+    mask = torch.zeros_like(probs)
+    mask[idx] = 1.0
+    for w in wrong or []:
+        mask[w] = 0.0
+    probs = probs * mask
+    probs = probs / probs.sum()
+    script_state["ptr"] += 1
+    return int(torch.argmax(probs))
+
+
+def test_sequence_coroutine_matches_reference():
+    """The per-sequence coroutine of the batched generation (InferenceTask._sequence_steps) asks for model steps and
+    samples at exactly the points the reference loop does: driven by the golden generator's scripted stand-in it
+    reproduces the reference sequences (teacher forcing, rejected chord tokens with the logits re-used and divided
+    by the temperature again, forced tokens fed twice)."""
+    from commu.midi_generator.midi_inferrer import InferenceTask
+    z = np.load(os.path.join(GOLDEN, "teacher_forcing.npz"))
+    for name, (nm, ctok, cpos, script) in TEACHER_SCENARIOS.items():
+        task = InferenceTask(torch.device("cpu"))
+        task.input_data = SimpleNamespace(num_measures=nm, temperature=0.95, top_k=32, num_generate=1,
+                                          chord_token_components={"chord_token": list(ctok), "chord_position": list(cpos)})
+        task.inference_cfg = SimpleNamespace(GENERATION=SimpleNamespace(generation_length=200))
+        st = fake_model_patch(task, script)
+        gen = task._sequence_steps([0, 574, 623, 627, 635, 639, 642, 651, 684, 694, 720, 727])
+        logits, seq, n_first = None, None, 0
+        try:
+            req = next(gen)
+            while True:
+                if req[0] == "step":
+                    n_first += int(req[2] is False)
+                    logits, _ = task.calc_logits_and_mems(None, 0)
+                    req = gen.send(None)
+                else:
+                    tok = _scripted_sampler(st, script, logits, 0.95, req[1], 32, req[2])
+                    req = gen.send(tok)
+        except StopIteration as fin:
+            seq = fin.value
+        assert n_first == 1, name                     # Q1: exactly one step whose memory is dropped
+        assert seq == z[name].tolist(), name
+
+
+def test_generate_batch_lockstep(monkeypatch):
+    """generate_batch: three sequences with different scripts share one (stubbed) batch engine; every live sequence
+    gets exactly one token step per engine step, the first step's state is dropped for the whole batch, rejected
+    tokens are re-drawn in extra sampler waves with the row's wrong-token mask and temperature ** k."""
+    import commu.midi_generator.midi_inferrer as mi
+    z = np.load(os.path.join(GOLDEN, "teacher_forcing.npz"))
+    names = list(TEACHER_SCENARIOS)
+    nm, ctok, cpos, script = TEACHER_SCENARIOS[names[0]]
+    B, V = 3, 729
+    # all rows run scenario 0's metadata (one input_data per call, like the reference) but row-specific noise
+    scripts = [script, script, script]
+    states = [{"calls": 0, "ptr": 0} for _ in range(B)]
+
+    class FakeEngine:
+        def __init__(self):
+            self.B, self.V, self.steps, self.rewinds = B, V, 0, 0
+            self.logits = torch.zeros(B, V)
+
+        def step(self, tokens, state):
+            assert tokens.shape == (B,)
+            self.steps += 1
+            if state.count < 11:                      # memory pre-fill of [0] + meta[:-1]: not a scripted call
+                return self.logits, mi.DecodeState(state.count + 1, state.slot + 1)
+            for r in range(B):
+                states[r]["calls"] += 1
+                g = torch.Generator().manual_seed(1000 + states[r]["calls"])
+                base = torch.randn(728, generator=g)
+                want = scripts[r][states[r]["ptr"]] if states[r]["ptr"] < len(scripts[r]) else 1
+                base[want - 1] += 20.0
+                self.logits[r, 0] = 0.0
+                self.logits[r, 1:] = base
+            return self.logits, mi.DecodeState(state.count + 1, state.slot + 1)
+
+    def fake_call(name, logits, ld, b, v, temp, top_k, top_p, wrong, seed, offset, toks, probs, ldp, dstate):
+        assert name == "commu_sample" and b == B
+        for r in range(B):
+            w = torch.nonzero(wrong[r]).flatten().tolist()
+            lg = logits[r, 1:] / temp
+            pr = F.pad(F.softmax(lg, dim=-1), [1, 0])
+            _, idx = torch.topk(pr, top_k)
+            mask = torch.zeros_like(pr)
+            mask[idx] = 1.0
+            mask[w] = 0.0
+            toks[r] = int(torch.argmax(pr * mask))
+    task = mi.InferenceTask(torch.device("cpu"))
+    task.input_data = SimpleNamespace(num_measures=nm, temperature=0.95, top_k=32, num_generate=B,
+                                      chord_token_components={"chord_token": list(ctok), "chord_position": list(cpos)})
+    task.inference_cfg = SimpleNamespace(GENERATION=SimpleNamespace(generation_length=200))
+    eng = FakeEngine()
+    monkeypatch.setattr(task, "_batch_engine", lambda n: eng)
+    monkeypatch.setattr(mi.nv, "call", fake_call)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    orig_adv = None
+    # the scripted draw advances the row's pointer whenever the row consumed a sample: emulate through a wrapper
+    real = task._sequence_steps
+
+    def counting(seq):
+        row = counting.n
+        counting.n += 1
+        gen = real(seq)
+        try:
+            req = next(gen)
+            while True:
+                val = yield req
+                if req[0] == "sample":
+                    states[row]["ptr"] += 1
+                req = gen.send(val)
+        except StopIteration as fin:
+            return fin.value
+    counting.n = 0
+    monkeypatch.setattr(task, "_sequence_steps", counting)
+    meta = [574, 623, 627, 635, 639, 642, 651, 684, 694, 720, 727]
+    out = task.generate_batch(meta, B)
+    assert all(s is not None for s in out)
+    for s in out:
+        assert s == z[names[0]].tolist()
+    assert task.validate_generated_sequence(out[0])
