@@ -25,9 +25,28 @@ sys.path.insert(0, os.path.join(ROOT, "commu-code_b200"))
 
 import torch  # noqa: E402
 
-CFG = dict(n_layer=12, n_head=8, d_model=512, d_inner=2048, tgt_len=2048, mem_len=2048, n_token=729)
+CONFIGS = {
+    # BASELINE.json configs[1] / [2]: the headline
+    "c2": dict(cfg=dict(n_layer=12, n_head=8, d_model=512, d_inner=2048, tgt_len=2048, mem_len=2048, n_token=729),
+               batch=16, metric="train tokens/sec @12L d512 seq2048 mem2048",
+               workload="BASELINE configs[1]: 12L d512 H8 Di2048 T=2048 M=2048 V=729"),
+    # BASELINE.json configs[4]: the scaled stress run (SURVEY.md 8d "C5": B = 2 per GPU)
+    "c5": dict(cfg=dict(n_layer=24, n_head=16, d_model=1024, d_inner=4096, tgt_len=4096, mem_len=4096, n_token=729),
+               batch=2, metric="train tokens/sec @24L d1024 seq4096 mem4096",
+               workload="BASELINE configs[4]: 24L d1024 H16 Di4096 T=4096 M=4096 V=729"),
+}
+CFG = dict(CONFIGS["c2"]["cfg"])
 B_PER_GPU = int(os.environ.get("COMMU_BENCH_BATCH", "16"))
-METRIC = "train tokens/sec @12L d512 seq2048 mem2048"
+METRIC = CONFIGS["c2"]["metric"]
+WORKLOAD = CONFIGS["c2"]["workload"]
+
+
+def select_config(name):
+    global CFG, B_PER_GPU, METRIC, WORKLOAD
+    c = CONFIGS[name]
+    CFG = dict(c["cfg"])
+    B_PER_GPU = int(os.environ.get("COMMU_BENCH_BATCH", str(c["batch"])))
+    METRIC, WORKLOAD = c["metric"], c["workload"]
 
 
 def algorithmic_flops_per_token(L, d, Di, T, M, B, V):
@@ -36,7 +55,7 @@ def algorithmic_flops_per_token(L, d, Di, T, M, B, V):
     macs_fwd_layer = d * d + 2 * d * d * K / T + d * d * K / (T * B) + 3 * d * (M + (T + 1) / 2) + d * d + 2 * d * Di
     f_fwd = 2 * (L * macs_fwd_layer + d * V)
     f_train = 3 * f_fwd - 2 * L * 2 * d * d * M / T
-    attn_fwd_flops_per_bh = 2 * 3 * (d // 8) * (T * M + T * (T + 1) / 2)   # per (b, h): AC + BD + AV
+    attn_fwd_flops_per_bh = 2 * 3 * 64 * (T * M + T * (T + 1) / 2)   # per (b, h), head dim 64: AC + BD + AV
     return f_fwd, f_train, attn_fwd_flops_per_bh
 
 
@@ -243,18 +262,19 @@ def run_native(args):
             roof = dict(kernel=dom, bound="tensor", achieved=round(ach, 2), peak=pk["bf16"], unit="TFLOP/s",
                         frac=round(ach / pk["bf16"], 4), traffic=ncu_traffic(dom), peak_source=pk["source"],
                         flops_per_launch=fl, avg_launch_ms=round(dur * 1e3, 4),
-                        launch_unit={"attn_bwd": "one layer's attention backward = dq + dk/dv + dR passes + delta",
+                        launch_unit={"attn_bwd": "one layer's attention backward (commu_relattn_bwd) = delta + pass 1 "
+                                                 "(dS, dK, dV) + the three band GEMMs (dq_A, dq_C, dR)",
                                      "attn_fwd": "one layer's attention forward"}.get(dom, dom))
         out = {
             "metric": METRIC, "value": round(value, 1), "unit": "tokens/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": round(ms_dev / K, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: 12L d512 H8 Di2048 T=2048 M=2048 V=729 train step "
-                                   "(fwd+bwd+clip+Adam), dropout %g / attention_dropout %g (reference default 0.1), "
-                                   "batch_chunk %d" % (args.dropout, args.dropout, args.batch_chunk),
+            "config": {"workload": WORKLOAD + " train step (fwd+bwd+clip+Adam), dropout %g / attention_dropout %g "
+                                   "(reference default 0.1), batch_chunk %d" % (args.dropout, args.dropout, args.batch_chunk),
                        "global_batch": B * world, "per_gpu_batch": B, "seq_len": T, "mem_len": CFG["mem_len"],
                        "parallelism": "dp%d" % world,
-                       "l2": "per-step working set (activations ~%d MB/GPU) >> 126 MB L2" % int(0.64 * 12 * B / 16 * 1000)},
+                       "l2": "per-step working set (saved activations + stored attention probabilities: tens of GB per "
+                             "GPU) >> 126 MB L2"},
             "e2e": {"value": round(e2e, 1), "unit": "tokens/s", "ms_per_step": round(ms_e2e / K, 3),
                     "h2d_bytes_per_step": int(2 * T * B * 8 + B), "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
@@ -266,14 +286,14 @@ def run_native(args):
             "clocks": clocks,
             "final_loss": round(final_loss, 5),
         }
-        if world == 1 and not args.no_decode:
+        if world == 1 and not args.no_decode and args.config == "c2":
             try:
                 out["decode"] = decode_bench(model, dev, pk)
             except Exception as e:      # the decode arm must never hide the training metric
                 out["decode"] = {"error": repr(e)[:300]}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.config == "c2":
             out["cpu_baseline"] = cpu_baseline(1, 1, args.dropout)
-        if world == 1 and not args.no_reference_gpu:
+        if world == 1 and not args.no_reference_gpu and args.config == "c2":
             del tr, model
             torch.cuda.empty_cache()
             try:
@@ -294,10 +314,153 @@ def run_native(args):
         dist.destroy_process_group()
 
 
-def decode_bench(model, dev, pk, n_new=256, batch=64, mem_len=2048, precision="bf16"):
-    """BASELINE configs[3]: batch 64, 12L d512, mem_len 2048 (pre-filled), top-p 0.9 / T 0.95.
-    Returns tokens/s/sequence, the HBM roofline fraction of the decode-attention kernel, and the whole
-    step's fraction of the algorithmic 52 MB/token/sequence."""
+def run_check(args):
+    """bench.py --gpus N --check (under torch.distributed.run, N >= 2): on-hardware correctness of the data-parallel
+    path (SURVEY.md 8(a) row a14 / section 4 "distributed").
+      1. gradient exchange: the flat gradient after the native NCCL exchange (per-layer all-reduces overlapped with the
+         backward, and the single all-reduce) == the sum of the ranks' local gradients (gathered with torch.distributed).
+      2. N-rank data-parallel training == one GPU on the same GLOBAL batch: per-step loss and the weight update after a
+         few optimizer steps (reference semantics: DDP averages the gradients, train.py:155, 467-473)."""
+    import torch.distributed as dist
+    from types import SimpleNamespace as NS
+    from commu.engine.trainer import GradComm, Trainer
+    from commu.model.model import MemTransformerLM
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world < 2:
+        raise SystemExit("bench.py --check needs >= 2 ranks (python -m torch.distributed.run --nproc-per-node 2 ...)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+    comm = GradComm(rank, world, dev)
+    L, H, d, Di, T, M, b, V = 3, CFG["n_head"], CFG["d_model"], CFG["d_inner"], 256, 256, 2, CFG["n_token"]
+
+    class Vocab:
+        def __len__(self):
+            return V
+    cfg = NS(MODEL=NS(num_layers=L, num_heads=H, units=d, inner_size=Di, dropout=0.0, attention_dropout=0.0,
+                      same_length=False, clamp_len=-1), TRAIN=NS(tgt_length=T, mem_length=M))
+
+    def fresh_model():
+        torch.manual_seed(1234)                       # identical weights on every rank
+        m = MemTransformerLM(cfg, Vocab())
+        with torch.no_grad():
+            for n, p in m.named_parameters():
+                if n.endswith("layer_norm.weight"):
+                    p.normal_(1.0, 0.02)
+                elif n.endswith(".bias") and p.dim() == 1:
+                    p.zero_()
+                else:
+                    p.normal_(0.0, 0.02)
+        return m.to(dev).train()
+    gen = torch.Generator().manual_seed(99)
+    steps = 3
+    tok = torch.randint(2, 560, (steps + 1, T + 1, b * world), generator=gen)
+    glob = [(tok[s, :-1].contiguous().to(dev), tok[s, 1:].contiguous().to(dev)) for s in range(steps + 1)]
+    mine = slice(rank * b, (rank + 1) * b)
+    res = {"check": "ok", "world": world, "shape": "L%d d%d H%d Di%d T%d M%d, %d columns per rank" % (L, d, H, Di, T, M, b)}
+    # ---- 1. gradient exchange ----
+    tr = Trainer(fresh_model(), lr=0.004, warmup_step=0, lr_min=1e-4, clip=1.0, world=world, comm=comm)
+    tr.accumulate_gradients(glob[0][0][:, mine].contiguous(), glob[0][1][:, mine].contiguous(), None)   # fills the memory
+    tr.apply_update()
+    saved_mems = list(tr.mems)
+    d1, t1 = glob[1][0][:, mine].contiguous(), glob[1][1][:, mine].contiguous()
+    tr.accumulate_gradients(d1, t1, None, exchange=False)
+    g_local = tr.flat_g.clone()
+    parts = [torch.empty_like(g_local) for _ in range(world)]
+    dist.all_gather(parts, g_local)
+    g_sum = torch.stack(parts).double().sum(0)
+    scale = float(g_sum.abs().max())
+    for mode, overlap in (("overlapped per-layer all-reduces", True), ("single all-reduce", False)):
+        tr.mems = list(saved_mems)
+        tr.overlap = overlap
+        tr.accumulate_gradients(d1, t1, None, exchange=True)
+        torch.cuda.synchronize()
+        err = float((tr.flat_g.double() - g_sum).abs().max())
+        # (the backward accumulates weight gradients with fp32 atomics: two runs of the SAME rank differ at this level)
+        tr.mems = list(saved_mems)
+        tr.accumulate_gradients(d1, t1, None, exchange=False)
+        noise = float((tr.flat_g - g_local).abs().max())
+        res["exchange: " + mode] = {"max_abs_err": err, "grad_max": scale, "run_to_run_noise_one_rank": noise}
+        if not err <= 1e-4 * scale + 4 * world * noise:
+            res["check"] = "FAILED: " + mode
+    tr.overlap = True
+    # ---- 2. data parallel == one GPU at the same global batch ----
+    m_dp = fresh_model()
+    p0 = {n: p.detach().clone() for n, p in m_dp.named_parameters()}
+    tr_dp = Trainer(m_dp, lr=0.004, warmup_step=0, lr_min=1e-4, clip=1.0, world=world, comm=comm)
+    dp_losses = []
+    for s in range(steps):
+        loss, _ = tr_dp.train_step(glob[s][0][:, mine].contiguous(), glob[s][1][:, mine].contiguous(), None)
+        l = loss.detach().clone()
+        dist.all_reduce(l)
+        dp_losses.append(float(l) / world)
+    if rank == 0:
+        m_1 = fresh_model()
+        tr_1 = Trainer(m_1, lr=0.004, warmup_step=0, lr_min=1e-4, clip=1.0)
+        one_losses = [float(tr_1.train_step(glob[s][0], glob[s][1], None)[0]) for s in range(steps)]
+        num = den = 0.0
+        for (n, a), (_, c) in zip(m_dp.named_parameters(), m_1.named_parameters()):
+            num += float(((a - c).double() ** 2).sum())
+            den += float(((c - p0[n]).double() ** 2).sum())
+        upd_err = (num / max(den, 1e-30)) ** 0.5
+        loss_err = max(abs(x - y) / y for x, y in zip(dp_losses, one_losses))
+        res["data_parallel_vs_one_gpu"] = {"dp_losses": dp_losses, "one_gpu_losses": one_losses,
+                                           "max_rel_loss_err": loss_err, "rel_err_of_weight_update": upd_err}
+        if not (loss_err < 1e-3 and upd_err < 0.05):
+            res["check"] = "FAILED: data parallel vs one GPU"
+        print(json.dumps(res), flush=True)
+    ok = torch.tensor([1 if res["check"] == "ok" else 0], device=dev)
+    dist.broadcast(ok, 0)
+    comm.close()
+    dist.destroy_process_group()
+    if int(ok) != 1:
+        raise SystemExit(1)
+
+
+def decode_cpu_baseline(n_tokens=16, mem_len=2048):
+    """The reference decode path (forward_generate over [memory ; token] per generated token,
+    midi_inferrer.py:199-207) on the host cores through the oracle port: batch 1, memory pre-filled, greedy."""
+    from oracle import transfoxl_oracle as orc
+    nthreads = pick_cpu_threads()
+    cfg = orc.make_cfg(CFG["n_layer"], CFG["n_head"], CFG["d_model"], CFG["d_inner"], 1, mem_len, True, -1, CFG["n_token"])
+    P = orc.init_params(cfg, seed=1111, std=0.01)
+    gen = torch.Generator().manual_seed(3)
+    ctx = torch.randint(2, 560, (mem_len + 1, 1), generator=gen)
+    with torch.no_grad():
+        _, mems = orc.forward_generate(cfg, P, ctx[:-1], None)
+        cur = ctx[-1:]
+        t0 = time.time()
+        for _ in range(n_tokens):
+            lg, mems = orc.forward_generate(cfg, P, cur, mems)
+            cur = (1 + lg[-1, :, 1:].argmax(-1))[None]
+        dt = time.time() - t0
+    return {"value": round(n_tokens / dt, 2), "unit": "tokens/s/seq", "cores": nthreads, "kind": "port",
+            "os_cpu_count": os.cpu_count(),
+            "sample": "%d greedy tokens, batch 1, memory %d pre-filled, %.1f s" % (n_tokens, mem_len, dt)}
+
+
+def decode_bench(model, dev, pk, n_new=512, batch=64, mem_len=2048):
+    """BASELINE configs[3]: batch 64, 12L d512, mem_len 2048 (pre-filled), top-p 0.9 / T 0.95, 512 new tokens.
+    The headline is the fp32 engine - the one whose greedy tokens are identical to the fp32 reference
+    (tests/test_decode_gpu.py at this shape); the bf16 engine (half the streamed bytes, NOT token-exact) is reported
+    beside it as the throughput mode.  `e2e`: the same loop with every step's token ids copied to pinned host memory;
+    `cpu_baseline`: the reference decode path on the host cores (oracle port, batch 1, 16 tokens)."""
+    res = _decode_one(model, dev, pk, n_new, batch, mem_len, "fp32")
+    try:
+        res["bf16_throughput_mode"] = _decode_one(model, dev, pk, n_new, batch, mem_len, "bf16")
+    except Exception as e:
+        res["bf16_throughput_mode"] = {"error": repr(e)[:200]}
+    try:
+        res["cpu_baseline"] = decode_cpu_baseline(16, mem_len)
+    except Exception as e:
+        res["cpu_baseline"] = {"error": repr(e)[:200]}
+    return res
+
+
+def _decode_one(model, dev, pk, n_new, batch, mem_len, precision):
     import ctypes
     from commu import _native as nv
     from commu.engine.decode import DecodeEngine, DecodeState
@@ -342,6 +505,16 @@ def decode_bench(model, dev, pk, n_new=256, batch=64, mem_len=2048, precision="b
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    # end to end: every step's token ids leave the device (pinned host buffer, one async copy per step)
+    host_tokens = torch.empty(n_new, batch, dtype=torch.int64).pin_memory()
+    e0.record()
+    for t in range(n_new):
+        graph.replay()
+        host_tokens[t].copy_(cur, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    assert int(host_tokens.min()) >= 1 and int(host_tokens.max()) < eng.V
     # duration of the decode-attention kernel: the 12 layers' launches captured alone in a CUDA graph (each layer streams
     # its own 268 MB cache, far above the 126 MB L2) and replayed back to back with events around the replays, so the
     # per-launch figure carries the same launch gaps as the real step and no host-side launch latency
@@ -380,6 +553,9 @@ def decode_bench(model, dev, pk, n_new=256, batch=64, mem_len=2048, precision="b
     attn_bytes = batch * H * mem_len * 64 * esz * 2 + H * mem_len * 64 * esz     # K + V per sequence, R once (8d)
     step_bytes = L * attn_bytes + 41.3e6 * esz
     res = {"tokens_per_s_per_seq": round(n_new / (ms / 1e3), 1), "batch": batch, "new_tokens": n_new,
+           "e2e": {"value": round(n_new / (ms_e2e / 1e3), 1), "unit": "tokens/s/seq", "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": batch * 8},
+           "token_exact_vs_fp32_reference": precision == "fp32",
            "ms_per_token_step": round(ms / n_new, 4), "precision": precision, "sampler": "top_p=0.9 T=0.95",
            "aggregate_tokens_per_s": round(n_new * batch / (ms / 1e3), 1),
            "step_hbm_frac": round(step_bytes / (ms / n_new / 1e3) / 1e9 / pk["hbm"], 4)}
@@ -392,32 +568,24 @@ def decode_bench(model, dev, pk, n_new=256, batch=64, mem_len=2048, precision="b
 
 
 def pick_cpu_threads():
-    """The box reports far more logical CPUs than the container may use (a 128-thread run was measured
-    ~500x slower than a 16-thread run on the same host), so the CPU arm calibrates itself: a small forward of
-    the oracle is timed at a few thread counts and the fastest is used for the baseline."""
-    from oracle import transfoxl_oracle as orc
+    """Thread count of the CPU arms, PINNED (no timing-based calibration: that made the count, and with it the
+    baseline, vary from run to run): the CPU share the container is actually given - the cgroup quota if one is set,
+    else the affinity mask - capped at 32 (the box reports far more logical CPUs than the container may use; a
+    128-thread run was measured ~500x slower than a 16-thread run on the same host).  COMMU_CPU_THREADS overrides."""
     n_cpu = os.cpu_count() or 1
     try:
         n_cpu = min(n_cpu, len(os.sched_getaffinity(0)))
     except (AttributeError, OSError):
         pass
-    cfg = orc.make_cfg(2, 8, 512, 2048, 256, 256, False, -1, 729)
-    P = orc.init_params(cfg, seed=1, std=0.01)
-    tok = torch.randint(2, 560, (257, 1))
-    best, best_t = 1, float("inf")
-    for nt in sorted({c for c in (4, 8, 16, 32, 64, n_cpu) if c <= n_cpu}):
-        torch.set_num_threads(nt)
-        with torch.no_grad():
-            orc.forward_loss(cfg, P, tok[:-1], tok[1:], None, None)
-            t0 = time.time()
-            orc.forward_loss(cfg, P, tok[:-1], tok[1:], None, None)
-            dt = time.time() - t0
-        if dt < best_t:
-            best, best_t = nt, dt
-        if dt > 20 * best_t:      # hopeless oversubscription: stop probing larger counts
-            break
-    torch.set_num_threads(best)
-    return best
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n_cpu = min(n_cpu, max(1, int(math.ceil(int(quota) / int(period)))))
+    except (OSError, ValueError):
+        pass
+    n = int(os.environ.get("COMMU_CPU_THREADS", "0")) or min(n_cpu, 32 if n_cpu <= 32 else 16)
+    torch.set_num_threads(n)
+    return n
 
 
 def cpu_baseline(steps, warmup, p_drop=0.1):
@@ -446,7 +614,7 @@ def cpu_baseline(steps, warmup, p_drop=0.1):
             times.append(time.time() - t0)
     tot = sum(times)
     return {"value": round(T * len(times) / tot, 2), "unit": "tokens/s", "cores": torch.get_num_threads(),
-            "kind": "port", "sample": "%d step(s) of B=1 x T=2048 (M=2048) fwd+bwd+clip+Adam, dropout %g, %.1f s" %
+            "os_cpu_count": os.cpu_count(), "kind": "port", "sample": "%d step(s) of B=1 x T=2048 (M=2048) fwd+bwd+clip+Adam, dropout %g, %.1f s" %
                                       (len(times), p_drop, tot)}
 
 
@@ -538,6 +706,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS),
+                    help="c2 = BASELINE configs[1] (headline, default); c5 = configs[4], 24L d1024 T=M=4096, B=2 per GPU")
+    ap.add_argument("--check", action="store_true",
+                    help="multi-GPU correctness instead of timing: all-reduced gradient == sum of the ranks' gradients, "
+                         "data-parallel loss / weights == one GPU at the same global batch")
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
@@ -550,6 +723,9 @@ def main():
     ap.add_argument("--no-reference-gpu", action="store_true")
     ap.add_argument("--decode-only", action="store_true")
     args = ap.parse_args()
+    select_config(args.config)
+    if args.check:
+        return run_check(args)
     if args.warmup < 3 and args.impl == "native" and os.environ.get("COMMU_BENCH_PROFILE") != "1":
         args.warmup = 3          # (COMMU_BENCH_PROFILE=1: launch-list runs under ncu, whose numbers are never reported)
     if args.impl == "reference":

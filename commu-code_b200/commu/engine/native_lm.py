@@ -365,9 +365,11 @@ class NativeLM:
                 cseg or n_real, cseg_pad or n_real, grad, grad.stride(0), 1.0)
 
     @torch.no_grad()
-    def backward(self, dloss, grads):
+    def backward(self, dloss, grads, layer_done=None):
         """dloss: fp32 [T,B] gradient of the per-token NLL.  Accumulates (+=) into `grads`
-        (dict: reference parameter name -> fp32 tensor of the parameter's shape)."""
+        (dict: reference parameter name -> fp32 tensor of the parameter's shape).
+        layer_done(l), if given, is called right after the last gradient of decoder layer l has been issued (layers
+        run L-1 .. 0): the data-parallel trainer starts that layer's share of the gradient exchange there."""
         c = self.saved
         if c is None:
             raise RuntimeError("commu_b200: backward() without a saved forward")
@@ -452,6 +454,8 @@ class NativeLM:
             # gradient of the layer input: residual + through Wq (all rows) + through Wkv (segment rows)
             nv.gemm(dq, s["wq"], m=rows, n=self.dp, k=self.hd, b_mn=True, add_f32=dz1, out_f32=dx)
             nv.gemm(dkv[M * B:], s["wkv"], m=rows, n=self.dp, k=2 * self.hd, b_mn=True, add_f32=dx, out_f32=dx)
+            if layer_done is not None:
+                layer_done(l)
         nv.call("commu_relattn_set_dropout", 0.0, 0)
         if pd > 0:
             self._drop(dx, rows, self.dp, pd, site_seed(dbase, 0, SITE_EMB), out_f32=dx)

@@ -101,6 +101,21 @@ class Trainer:
             p.grad = g
             self.grads[n] = g
         self.offsets = dict(zip(names, offs))
+        # [lo, hi) of every decoder layer inside the flat arenas (a layer's parameters are consecutive), and the rest
+        self.layer_spans = []
+        for l in range(self.model.n_layer):
+            idx = [i for i, n in enumerate(names) if n.startswith("layers.%d." % l)]
+            lo, last = offs[idx[0]], idx[-1]
+            hi = offs[last + 1] if last + 1 < len(offs) else total
+            assert idx == list(range(idx[0], last + 1))
+            self.layer_spans.append((lo, hi))
+        covered = sorted(self.layer_spans)
+        self.other_spans, pos = [], 0
+        for lo, hi in covered + [(total, total)]:
+            if lo > pos:
+                self.other_spans.append((pos, lo))
+            pos = max(pos, hi)
+        self.side = torch.cuda.Stream(dev) if dev.type == "cuda" else None
         self.gnorm_sq = torch.zeros(1, device=dev)
         self.gnorm = torch.zeros(1, device=dev)
         self.engine = self.model._engine()
@@ -114,15 +129,22 @@ class Trainer:
         """data/target: int64 [T, B] device tensors, reset: bool [B] (or None).
         Returns (loss, grad_norm) as 0-d device tensors: loss = sum over chunks of the reference's
         `loss[target != pad].mean() / batch_chunk` (train.py:148-149)."""
+        total = self.accumulate_gradients(data, target, reset)
+        return total, self.apply_update()
+
+    @torch.no_grad()
+    def accumulate_gradients(self, data, target, reset, exchange=True):
+        """Forward / backward of every micro-batch into the flat gradient arena; with `exchange` (and a communicator)
+        the arena then holds the SUM over ranks (the 1 / world factor is folded into apply_update)."""
         m = self.model
         eng = self.engine
         C = self.batch_chunk
-        lr = self.current_lr()
         self.flat_g.zero_()
         dcs = torch.chunk(data, C, 1)
         tcs = torch.chunk(target, C, 1)
         rcs = torch.chunk(reset, C, 0) if reset is not None else [None] * C
         total = torch.zeros((), device=data.device)
+        dist_on = exchange and self.comm is not None and self.world > 1
         for i in range(C):
             d_i, t_i = dcs[i].contiguous(), tcs[i].contiguous()
             r_i = rcs[i].contiguous() if rcs[i] is not None else None
@@ -131,17 +153,44 @@ class Trainer:
             mask = (t_i != self.pad_id).float()
             w = mask / (mask.sum() * C)
             total += (nll * w).sum()
-            eng.backward(w, self.grads)
-        if self.comm is not None and self.world > 1:
-            self.comm.allreduce_(self.flat_g)
+            overlap = dist_on and i == C - 1 and self.overlap
+            eng.backward(w, self.grads, layer_done=self._exchange_layer if overlap else None)
+        if dist_on:
+            if self.overlap:
+                # the layers' shares went out on the side stream while the backward was still running (layer l's
+                # share as soon as its last gradient was issued); what is left is the embedding / bias remainder
+                for lo, hi in self.other_spans:
+                    self._exchange(lo, hi)
+                torch.cuda.current_stream().wait_stream(self.side)
+            else:
+                self.comm.allreduce_(self.flat_g)
+        return total
+
+    @torch.no_grad()
+    def apply_update(self):
+        """clip_grad_norm_(clip) + Adam on the flat arenas, bf16 shadow refresh; returns the gradient norm."""
+        lr = self.current_lr()
         self.step += 1
         self.gnorm_sq.zero_()
         nv.call("commu_sumsq", self.flat_g, self.flat_g.numel(), self.gnorm_sq)
         nv.call("commu_clip_adam", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_p.numel(),
                 lr, self.betas[0], self.betas[1], self.eps, self.step, self.gnorm_sq, self.clip,
                 1.0 / self.world, self.weight_decay, self.gnorm)
-        eng.refresh_shadow()
-        return total, self.gnorm[0].clone()
+        self.engine.refresh_shadow()
+        return self.gnorm[0].clone()
+
+    # ---- gradient exchange overlapped with the backward (one NCCL sum all-reduce per layer span, side stream) ----
+    overlap = True
+
+    def _exchange(self, lo, hi):
+        ev = torch.cuda.Event()
+        ev.record()                                  # everything that wrote flat_g[lo:hi] is in the stream before this
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            self.comm.allreduce_(self.flat_g[lo:hi])
+
+    def _exchange_layer(self, l):
+        self._exchange(*self.layer_spans[l])
 
     def optimizer_state_dict(self):
         """Same structure as torch.optim.Adam.state_dict() so reference-style checkpoints load."""

@@ -69,11 +69,11 @@ constexpr int COL_DP = 0, COL_DV = 256, COL_DK = 320;
 
 struct P1Smem {
   uint8_t v[TILE16];
-  uint8_t pt[2][TILE32];     // P~ tile as loaded ([key half][128 q rows][128 B], 128B swizzle); rewritten in place as P
-  uint8_t ds[2][TILE32];     // dS tile, same layout: MN-major operand of dK and the source of the TMA stores
-  uint8_t dout[2][TILE16];
+  uint8_t pt[3][TILE32];     // P~ tile ring (HBM stream, 3 deep): [key half][128 q rows][128 B], 128B swizzle; rewritten in place as P
+  uint8_t ds[TILE32];        // dS tile, same layout: MN-major operand of dK and the source of the TMA stores
+  uint8_t dout[2][TILE16];   // dO / (q+u) tiles: small, L2-resident, 2 deep
   uint8_t qu[2][TILE16];
-  uint64_t v_full, q_full[2], q_empty[2], dp_full[2], dp_free[2], pds_full[2], st_done[2], acc_full;
+  uint64_t v_full, p_full[3], p_empty[3], q_full[2], q_empty[2], dp_full[2], dp_free[2], pds_full[2], ds_mma, ds_st, acc_full;
   uint32_t tmem_base;
 };
 
@@ -98,11 +98,13 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
 
   if (threadIdx.x == 0) {
     cb::mbar_init(&sm.v_full, 1);
+    for (int s = 0; s < 3; ++s) { cb::mbar_init(&sm.p_full[s], 1); cb::mbar_init(&sm.p_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
       cb::mbar_init(&sm.q_full[s], 1); cb::mbar_init(&sm.q_empty[s], 1);
       cb::mbar_init(&sm.dp_full[s], 1); cb::mbar_init(&sm.dp_free[s], P1_SOFT);
-      cb::mbar_init(&sm.pds_full[s], P1_SOFT); cb::mbar_init(&sm.st_done[s], 1);
+      cb::mbar_init(&sm.pds_full[s], P1_SOFT);
     }
+    cb::mbar_init(&sm.ds_mma, 1); cb::mbar_init(&sm.ds_st, 1);
     cb::mbar_init(&sm.acc_full, 1);
     cb::fence_barrier_init();
   }
@@ -120,43 +122,48 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
     if (cb::elect_one()) {
       cb::mbar_arrive_expect_tx(&sm.v_full, TILE16);
       cb::tma_load_3d(sm.v, &tm_v, &sm.v_full, h * DH, b, j0);
-      auto load_q = [&](int n) {   // stage n & 1, its (n >> 1)-th use
+      auto load_p = [&](int n) {   // P~ ring: stage n % 3, its (n / 3)-th use
+        const int st = n % 3;
+        const int i0 = (it_first + n) * TM;
+        cb::mbar_wait(&sm.p_empty[st], ((n / 3) & 1) ^ 1);
+        cb::mbar_arrive_expect_tx(&sm.p_full[st], TILE32);
+        cb::tma_load_2d(sm.pt[st], &tm_p, &sm.p_full[st], j0, bh * p.Tpad + i0);
+        cb::tma_load_2d(sm.pt[st] + TILE16, &tm_p, &sm.p_full[st], j0 + 64, bh * p.Tpad + i0);
+      };
+      auto load_q = [&](int n) {   // dO / (q+u) ring: stage n & 1, its (n >> 1)-th use
         const int bi = n & 1;
         const int i0 = (it_first + n) * TM;
         cb::mbar_wait(&sm.q_empty[bi], ((n >> 1) & 1) ^ 1);
-        cb::mbar_arrive_expect_tx(&sm.q_full[bi], TILE32 + 2 * TILE16);
-        cb::tma_load_2d(sm.pt[bi], &tm_p, &sm.q_full[bi], j0, bh * p.Tpad + i0);
-        cb::tma_load_2d(sm.pt[bi] + TILE16, &tm_p, &sm.q_full[bi], j0 + 64, bh * p.Tpad + i0);
+        cb::mbar_arrive_expect_tx(&sm.q_full[bi], 2 * TILE16);
         cb::tma_load_3d(sm.dout[bi], &tm_do, &sm.q_full[bi], h * DH, b, i0);
         cb::tma_load_3d(sm.qu[bi], &tm_qu, &sm.q_full[bi], h * DH, b, i0);
       };
-      // the P~ stream comes from HBM and the two-stage ring only covers one tile of latency: pull the tiles two and
-      // three steps ahead into L2 (no shared memory needed), so the staged load that follows is an L2 hit
+      // the P~ stream comes from HBM: besides the 3-deep ring, the tiles a few steps further ahead are pulled into L2
       auto prefetch_p = [&](int n) {
         const int i0 = (it_first + n) * TM;
         cb::tma_prefetch_2d(&tm_p, j0, bh * p.Tpad + i0);
         cb::tma_prefetch_2d(&tm_p, j0 + 64, bh * p.Tpad + i0);
       };
+      load_p(0);
       load_q(0);
-      for (int n = 1; n < 4 && n < nq; ++n) prefetch_p(n);
+      if (nq > 1) load_p(1);
+      for (int n = 3; n < 6 && n < nq; ++n) prefetch_p(n);
       for (int n = 0; n < nq; ++n) {
+        if (n + 2 < nq) load_p(n + 2);
         if (n + 1 < nq) load_q(n + 1);
-        if (n + 4 < nq) prefetch_p(n + 4);
-        const int bi = n & 1;
+        if (n + 6 < nq) prefetch_p(n + 6);
         const int i0 = (it_first + n) * TM;
-        cb::mbar_wait(&sm.pds_full[bi], (n >> 1) & 1);
+        cb::mbar_wait(&sm.pds_full[n & 1], (n >> 1) & 1);
         // coarse-sheared store: the 8-row group g of the tile goes to column j0 + X - (i0 + 8g)
 #pragma unroll 1
         for (int half = 0; half < 2; ++half)
 #pragma unroll 4
           for (int g = 0; g < 16; ++g)
-            cb::tma_store_2d(&tm_ds, sm.ds[bi] + half * TILE16 + g * 1024, j0 + 64 * half + p.X - (i0 + 8 * g),
+            cb::tma_store_2d(&tm_ds, sm.ds + half * TILE16 + g * 1024, j0 + 64 * half + p.X - (i0 + 8 * g),
                              bh * p.Tpad + i0 + 8 * g);
         cb::tma_store_commit();
-        if (n >= 1) {   // the previous tile's stores have finished reading their shared-memory source
-          cb::tma_store_wait_read<1>();
-          cb::mbar_arrive(&sm.st_done[(n - 1) & 1]);
-        }
+        cb::tma_store_wait_read<0>();       // the single dS tile may be rewritten (the next tile needs it ~1000 cycles later)
+        cb::mbar_arrive(&sm.ds_st);
       }
       cb::tma_store_wait<0>();
     }
@@ -168,21 +175,23 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
       cb::mbar_wait(&sm.v_full, 0);
       const uint32_t a_v = cb::smem_u32(sm.v);
       auto back = [&](int m) {   // dV += P^T dO ; dK += dS^T (q+u) of tile m
-        const int bj = m & 1;
+        const int bj = m & 1, sp = m % 3;
         cb::mbar_wait(&sm.pds_full[bj], (m >> 1) & 1);
         cb::tc_fence_after();
         // MN-major A: 64-key atoms 16 KB apart (LBO), 8-query-row groups 1 KB apart (SBO); 16 query rows per MMA
-        const uint64_t ap = cb::umma_smem_desc(cb::smem_u32(sm.pt[bj]), TILE16, 1024);
-        const uint64_t as = cb::umma_smem_desc(cb::smem_u32(sm.ds[bj]), TILE16, 1024);
+        const uint64_t ap = cb::umma_smem_desc(cb::smem_u32(sm.pt[sp]), TILE16, 1024);
+        const uint64_t as = cb::umma_smem_desc(cb::smem_u32(sm.ds), TILE16, 1024);
         const uint64_t bo = cb::umma_smem_desc(cb::smem_u32(sm.dout[bj]), 8192, 1024);
         const uint64_t bq = cb::umma_smem_desc(cb::smem_u32(sm.qu[bj]), 8192, 1024);
 #pragma unroll
         for (int k = 0; k < TM / 16; ++k)
           cb::umma_bf16_ss(tmem + COL_DV, ap + (uint64_t)(k * 128), bo + (uint64_t)(k * 128), idesc_g, (m > 0 || k > 0));
+        cb::umma_commit(&sm.p_empty[sp]);
 #pragma unroll
         for (int k = 0; k < TM / 16; ++k)
           cb::umma_bf16_ss(tmem + COL_DK, as + (uint64_t)(k * 128), bq + (uint64_t)(k * 128), idesc_g, (m > 0 || k > 0));
         cb::umma_commit(&sm.q_empty[bj]);
+        cb::umma_commit(&sm.ds_mma);
       };
       for (int n = 0; n < nq; ++n) {
         const int bi = n & 1;
@@ -218,6 +227,7 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
     const float* del_p = p.delta + (long long)bh * p.T;
     const float* mt_p = p.mt + ((long long)bh * p.nkt + jt) * p.Tpad;
     const float lkeep = DROP ? log2f(p.drop_keep) : 0.f;
+    const uint32_t a_ds = cb::smem_u32(sm.ds) + rowoff;
     float lse_n = 0.f, del_n = 0.f, mt_n = 0.f;
     {
       const int i = it_first * TM + li;
@@ -240,54 +250,52 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
       }
       const int bi = n & 1;
       const uint32_t ph = (n >> 1) & 1;
-      const uint32_t a_pt = cb::smem_u32(sm.pt[bi]) + rowoff;
-      const uint32_t a_ds = cb::smem_u32(sm.ds[bi]) + rowoff;
-      cb::mbar_wait(&sm.q_full[bi], ph);
-      if (n >= 2) cb::mbar_wait(&sm.st_done[bi], ((n - 2) >> 1) & 1);   // the stores of tile n-2 have read ds[bi]
+      const uint32_t a_pt = cb::smem_u32(sm.pt[n % 3]) + rowoff;
+      cb::mbar_wait(&sm.p_full[n % 3], (n / 3) & 1);
+      // this thread's 32 stored probabilities (64 bytes) and its 32 dP columns, all in flight before the first use
+      uint32_t w[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const uint32_t a = a_pt + (((cx + c) ^ sw) << 4);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(w[c * 4]), "=r"(w[c * 4 + 1]), "=r"(w[c * 4 + 2]), "=r"(w[c * 4 + 3]) : "r"(a));
+      }
       cb::mbar_wait(&sm.dp_full[bi], ph);
       cb::tc_fence_after();
+      uint32_t dp[32];
+      cb::tmem_ld_32x32b_x32(lane_addr + COL_DP + bi * TN + g * 32, dp);
+      cb::tmem_ld_wait();
+      cb::tc_fence_before();
+      cb::mbar_arrive(&sm.dp_free[bi]);
+      uint32_t pk[16], dsk[16];
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t w[8];
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t a = a_pt + (((cx + hf * 2 + c) ^ sw) << 4);
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(w[c * 4]), "=r"(w[c * 4 + 1]), "=r"(w[c * 4 + 2]), "=r"(w[c * 4 + 3]) : "r"(a));
+      for (int e = 0; e < 16; ++e) {
+        const uint32_t ww = vis ? w[e] : 0u;
+        const float x0 = cb::bf16_lo(ww) * f, x1 = cb::bf16_hi(ww) * f;     // signed: negative = dropped
+        const float d0 = __uint_as_float(dp[2 * e]), d1 = __uint_as_float(dp[2 * e + 1]);
+        float k0, k1, s0, s1;
+        if (DROP) {
+          k0 = fmaxf(x0, 0.f); k1 = fmaxf(x1, 0.f);
+          s0 = fmaf(k0, d0, fabsf(x0) * ndelta);
+          s1 = fmaf(k1, d1, fabsf(x1) * ndelta);
+        } else {
+          k0 = x0; k1 = x1;
+          s0 = x0 * (d0 + ndelta);
+          s1 = x1 * (d1 + ndelta);
         }
-        uint32_t dp[16];
-        tmem_ld_32x32b_x16(lane_addr + COL_DP + bi * TN + g * 32 + hf * 16, dp);
-        cb::tmem_ld_wait();
-        if (hf == 1) {
-          cb::tc_fence_before();
-          cb::mbar_arrive(&sm.dp_free[bi]);
-        }
-        uint32_t pk[8], dsk[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint32_t ww = vis ? w[e] : 0u;
-          const float x0 = cb::bf16_lo(ww) * f, x1 = cb::bf16_hi(ww) * f;     // signed: negative = dropped
-          const float d0 = __uint_as_float(dp[2 * e]), d1 = __uint_as_float(dp[2 * e + 1]);
-          float k0, k1, s0, s1;
-          if (DROP) {
-            k0 = fmaxf(x0, 0.f); k1 = fmaxf(x1, 0.f);
-            s0 = fmaf(k0, d0, fabsf(x0) * ndelta);
-            s1 = fmaf(k1, d1, fabsf(x1) * ndelta);
-          } else {
-            k0 = x0; k1 = x1;
-            s0 = x0 * (d0 + ndelta);
-            s1 = x1 * (d1 + ndelta);
-          }
-          pk[e] = cb::pack_bf16(k0, k1);
-          dsk[e] = cb::pack_bf16(s0, s1);
-        }
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const uint32_t off = (((cx + hf * 2 + c) ^ sw) << 4);
-          sts_v4(a_pt + off, pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-          sts_v4(a_ds + off, dsk[c * 4], dsk[c * 4 + 1], dsk[c * 4 + 2], dsk[c * 4 + 3]);
-        }
+        pk[e] = cb::pack_bf16(k0, k1);
+        dsk[e] = cb::pack_bf16(s0, s1);
       }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts_v4(a_pt + (((cx + c) ^ sw) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+      if (n >= 1) {   // the single dS tile: the previous tile's dK product and TMA stores are done with it
+        cb::mbar_wait(&sm.ds_mma, (n - 1) & 1);
+        cb::mbar_wait(&sm.ds_st, (n - 1) & 1);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts_v4(a_ds + (((cx + c) ^ sw) << 4), dsk[c * 4], dsk[c * 4 + 1], dsk[c * 4 + 2], dsk[c * 4 + 3]);
       cb::fence_proxy_async();
       cb::mbar_arrive(&sm.pds_full[bi]);
     }

@@ -364,6 +364,126 @@ def gen_generate_case(name):
     print("wrote", name)
 
 
+# ---------------------------------------------------------------------------------------------------
+# A checkpoint WRITTEN BY THE REFERENCE at its code-default model shape (6 layers, 10 heads, d_model 500,
+# d_inner 1000, Dh 50; config_helper.py:7-10) and resumed by the reference.  The file is ~170 MB (weights + Adam
+# moments), far too large for a fixture, so its CONTENT is a pure function of the key names (seeded per key, see
+# keyed_tensor) and only the structure written by torch.save, the synthetic tokens' seed and the reference's
+# continued losses are stored; tests/test_checkpoint_gpu.py rebuilds the identical file from that.
+# ---------------------------------------------------------------------------------------------------
+CKPT_CFG = dict(n_layer=6, n_head=10, d_model=500, d_inner=1000, tgt_len=128, mem_len=1024, same_length=False,
+                clamp_len=-1)
+CKPT_HYPER = dict(lr=0.004, warmup=100, lr_min=1e-4, chunks=2, B=4, train_step=137, n_steps=3, data_seed=77)
+
+
+def keyed_tensor(key, shape, kind):
+    """Deterministic tensor content from the key name alone (same torch CPU generator here and in the test)."""
+    import zlib
+    g = torch.Generator().manual_seed(zlib.crc32(key.encode()) & 0x7FFFFFFF)
+    if kind == "ln_weight":
+        return 1.0 + 0.02 * torch.randn(shape, generator=g)
+    if kind == "exp_avg":
+        return 1e-4 * torch.randn(shape, generator=g)
+    if kind == "exp_avg_sq":
+        return 1e-7 * torch.rand(shape, generator=g) + 1e-9
+    return 0.02 * torch.randn(shape, generator=g)
+
+
+def ckpt_model_state(named_shapes):
+    sd = {}
+    for k, shape in named_shapes:
+        kind = "ln_weight" if k.endswith("layer_norm.weight") else "w"
+        sd[k] = keyed_tensor("model/" + k, shape, kind)
+    return sd
+
+
+def ckpt_batches(n_steps, T, B, seed):
+    rng = np.random.RandomState(seed)
+    out = []
+    for _ in range(n_steps):
+        tok = rng.randint(2, 560, size=(T + 1, B))
+        out.append((torch.from_numpy(tok[:-1]).long(), torch.from_numpy(tok[1:]).long(), torch.from_numpy(rng.rand(B) < 0.25)))
+    return out
+
+
+def gen_checkpoint_case(name):
+    import io
+    import json
+    _stub_modules()
+    from commu.model.dataset import BaseVocab            # the class the reference pickles into its checkpoints
+    from commu.model.model import MemTransformerLM
+    h = CKPT_HYPER
+    torch.manual_seed(0)
+    model = MemTransformerLM(ref_cfg(**CKPT_CFG), Vocab(729))
+    names = [(k, tuple(p.shape)) for k, p in model.named_parameters()]
+    sd0 = ckpt_model_state(names)
+    with torch.no_grad():
+        for k, p in model.named_parameters():
+            p.copy_(sd0[k])
+    model.train()
+
+    def lam(step):
+        if step == 0 and h["warmup"] == 0:
+            return 1.0
+        return max((h["warmup"] ** 0.5) / (step ** 0.5), h["lr_min"] / h["lr"]) if step > h["warmup"] else step / h["warmup"]
+    opt = torch.optim.Adam(model.parameters(), lr=h["lr"], weight_decay=0.0)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lam)
+    # optimizer / scheduler state "after train_step steps": seeded moments, step counters, scheduler epoch
+    osd = opt.state_dict()
+    osd["state"] = {i: {"step": torch.tensor(float(h["train_step"])),
+                        "exp_avg": keyed_tensor("opt/exp_avg/" + k, shp, "exp_avg"),
+                        "exp_avg_sq": keyed_tensor("opt/exp_avg_sq/" + k, shp, "exp_avg_sq")}
+                    for i, (k, shp) in enumerate(names)}
+    opt.load_state_dict(osd)
+    ssd = sched.state_dict()
+    ssd["last_epoch"] = h["train_step"]
+    ssd["_step_count"] = h["train_step"] + 1
+    sched.load_state_dict(ssd)
+    for g_ in opt.param_groups:
+        g_["lr"] = h["lr"] * lam(h["train_step"])
+    # ---- the reference's save_checkpoint dict (train.py:29-54), written and re-read through torch.save ----
+    ckpt = {"model": model.state_dict(), "optimizer": opt.state_dict(), "train_step": h["train_step"],
+            "scheduler": sched.state_dict(), "best_val_loss": 3.21, "vocab": BaseVocab(), "amp": None}
+    buf = io.BytesIO()
+    torch.save(ckpt, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    model.load_state_dict(back["model"], strict=False)            # model_initializer.py:46-47
+    opt.load_state_dict(back["optimizer"])
+    structure = {
+        "model_keys": [[k, list(v.shape), str(v.dtype)] for k, v in back["model"].items()],
+        "optimizer_param_groups": [{k: (v if not isinstance(v, tuple) else list(v)) for k, v in g_.items()}
+                                   for g_ in back["optimizer"]["param_groups"]],
+        "optimizer_state_keys": sorted(next(iter(back["optimizer"]["state"].values())).keys()),
+        "optimizer_n_state": len(back["optimizer"]["state"]),
+        "scheduler_keys": sorted(k for k in back["scheduler"].keys() if k != "lr_lambdas"),
+        "top_level_keys": list(back.keys()),
+        "vocab_class": type(back["vocab"]).__module__ + "." + type(back["vocab"]).__name__,
+        "param_order": [k for k, _ in names],
+        "file_bytes": buf.getbuffer().nbytes,
+    }
+    # ---- the reference continues training from it ----
+    mems = [None] * h["chunks"]
+    losses, lrs, gnorms = [], [], []
+    for data, target, reset in ckpt_batches(h["n_steps"], CKPT_CFG["tgt_len"], h["B"], h["data_seed"]):
+        model.zero_grad()
+        tot = 0.0
+        dc, tc, rc = torch.chunk(data, h["chunks"], 1), torch.chunk(target, h["chunks"], 1), torch.chunk(reset, h["chunks"], 0)
+        for i in range(h["chunks"]):
+            loss, mems[i] = model(dc[i].contiguous(), tc[i].contiguous(), rc[i].contiguous(), mems[i])
+            loss = loss[tc[i] != 0].float().mean() / h["chunks"]
+            tot += loss.item()
+            loss.backward()
+        gnorms.append(float(torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)))
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sched.step()
+        losses.append(tot)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), structure=np.array(json.dumps(structure)),
+                        losses=np.array(losses), lrs=np.array(lrs), gnorms=np.array(gnorms))
+    print("wrote", name, "losses", losses, "lrs", lrs, "file MB", structure["file_bytes"] / 2 ** 20)
+
+
 def main():
     sys.path.insert(0, REF)
     torch.set_num_threads(4)
@@ -382,6 +502,7 @@ def main():
     gen_dataset_case("dataset_batches", seed=16)
     gen_teacher_case("teacher_forcing")
     gen_generate_case("generate_greedy")
+    gen_checkpoint_case("checkpoint_default_shape")
     cfgE = dict(n_layer=2, n_head=2, d_model=32, d_inner=64, tgt_len=10, mem_len=10,
                 same_length=False, clamp_len=-1)
     gen_train_case("train_steps", cfgE, n_token=61, B=4, chunks=2, n_steps=6, seed=15, std=0.05,

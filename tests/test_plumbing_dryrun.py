@@ -147,6 +147,25 @@ def test_trainer_plumbing(stub, monkeypatch):
     assert "commu_clip_adam" in stub.calls and "commu_sumsq" in stub.calls
 
 
+def test_exchange_spans_partition_the_gradient_arena(stub, monkeypatch):
+    """The overlapped gradient exchange sends one span per decoder layer plus the remainder (biases, embedding,
+    logits bias): together they must cover the flat arena exactly once, and a layer's span must hold exactly that
+    layer's parameters (train.py:155, 467-473 of the reference all-reduces every gradient once per step)."""
+    import commu.engine.native_lm as nl
+    from commu.engine.trainer import Trainer
+    monkeypatch.setattr(nl.NativeLM, "__init__", _cpu_init(nl.NativeLM))
+    m = _model(d=64, H=1, Di=128, L=3, same=False)
+    tr = Trainer(m, lr=0.004)
+    total = tr.flat_g.numel()
+    spans = sorted(tr.layer_spans + tr.other_spans)
+    assert spans[0][0] == 0 and spans[-1][1] == total
+    assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+    for l, (lo, hi) in enumerate(tr.layer_spans):
+        inside = [n for n, o in tr.offsets.items() if lo <= o < hi]
+        assert inside and all(n.startswith("layers.%d." % l) for n in inside)
+        assert len(inside) == len([n for n in tr.offsets if n.startswith("layers.%d." % l)])
+
+
 def test_lr_schedule_floor_is_world_independent(stub, monkeypatch):
     """train.py:441-461 of the reference: the optimizer runs at cfg.TRAIN.lr / num_gpus, but the floor of the
     inverse-sqrt schedule is the ratio lr_min / cfg.TRAIN.lr with the UNDIVIDED lr.  At 8 ranks the floor multiplier

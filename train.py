@@ -95,6 +95,21 @@ def save_checkpoint(work_dir, rank, distributed, model, trainer, vocab, train_st
         dist.barrier()
 
 
+def resume_from(path, model, trainer, device):
+    """Continues from a checkpoint written by this script OR by the reference's save_checkpoint (train.py:29-54 of the
+    reference: {"model", "optimizer", "train_step", "scheduler", "best_val_loss", "vocab", "amp"}): weights with
+    strict=False like the reference's loader (model_initializer.py:46-47), torch.optim.Adam's exp_avg / exp_avg_sq /
+    step per parameter index, the step counter that drives the LambdaLR schedule.  Returns (train_step, best_val)."""
+    ckpt = torch.load(path, map_location=device, weights_only=False)      # pickled BaseVocab inside
+    model.load_state_dict(ckpt["model"], strict=False)
+    if ckpt.get("optimizer"):
+        trainer.load_optimizer_state_dict(ckpt["optimizer"])
+    train_step = int(ckpt.get("train_step", 0))
+    trainer.step = train_step
+    trainer.engine.refresh_shadow()
+    return train_step, ckpt.get("best_val_loss")
+
+
 def reduce_scalars(vals, device, distributed):
     t = torch.tensor(vals, dtype=torch.float64, device=device)
     if distributed:
@@ -174,15 +189,9 @@ def main(argv=None):
 
     train_step, best_val = 0, np.inf
     if args.resume:
-        ckpt = torch.load(args.resume, map_location=device, weights_only=False)   # pickled BaseVocab inside
-        model.load_state_dict(ckpt["model"], strict=False)
-        if ckpt.get("optimizer"):
-            trainer.load_optimizer_state_dict(ckpt["optimizer"])
-        train_step = int(ckpt.get("train_step", 0))
-        trainer.step = train_step
-        if ckpt.get("best_val_loss") is not None:
-            best_val = ckpt["best_val_loss"]
-        trainer.engine.refresh_shadow()
+        train_step, bv = resume_from(args.resume, model, trainer, device)
+        if bv is not None:
+            best_val = bv
         logger.info("Resumed from {} at step {}".format(args.resume, train_step))
     log_loss = torch.zeros((), device=device, dtype=torch.float64)
     log_gnorm = torch.zeros((), device=device, dtype=torch.float64)
