@@ -1,19 +1,32 @@
-"""Aggregate an ncu source page (cuda,sass) per CUDA source line: python tools/ncu_lines.py rep kernel_index [top]"""
+"""Aggregate an ncu source page (cuda,sass) per CUDA source line:
+   python tools/ncu_lines.py report.ncu-rep <kernel-name-regex> [top]
+Every SASS row is attributed to the CUDA source line printed above it (needs -lineinfo at compile time)."""
 import csv, subprocess, sys, io
-rep, kid = sys.argv[1], int(sys.argv[2]); top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-id", f":::{kid}"],
+rep, kre = sys.argv[1], sys.argv[2]
+top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--kernel-name", "regex:" + kre],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
-cur_file = None; hdr = None; out = []
+cur_file, cur_line, cur_src, hdr = None, None, "", None
+agg = {}
+first_fn = None
 for r in rows:
-    if len(r) == 2 and r[0] == "File Path": cur_file = r[1].split("/")[-1]; continue
-    if len(r) > 5 and r[0] == "Line No": hdr = r; continue
-    if hdr is None or len(r) < len(hdr) or not r[0]: continue
-    g = lambda k: int(r[hdr.index(k)]) if r[hdr.index(k)].lstrip("-").isdigit() else 0
-    st = {k: g(k) for k in ("stall_barrier", "stall_long_sb", "stall_short_sb", "stall_mio", "stall_sleep", "stall_wait", "stall_math", "stall_not_selected", "stall_selected", "stall_branch_resolving", "stall_no_inst")}
-    out.append((g("Instructions Executed"), g("# Samples"), cur_file, r[0], r[1].strip()[:100], st))
-te = sum(o[0] for o in out); ts = sum(o[1] for o in out)
-print("total inst", te, "samples", ts)
-for o in sorted(out, key=lambda o: -(o[0] / te + o[1] / ts))[:top]:
-    big = ",".join(f"{k[6:]}={v}" for k, v in sorted(o[5].items(), key=lambda kv: -kv[1])[:3] if v)
-    print(f"{100*o[0]/te:5.1f}%exe {100*o[1]/ts:5.1f}%smp {o[2][:18]}:{o[3]:>4} | {o[4][:80]} | {big}")
+    if len(r) == 2 and r[0] == "File Path":
+        cur_file = r[1].split("/")[-1]; continue
+    if len(r) == 2 and r[0] == "Function Name":
+        if first_fn is None: first_fn = r[1]
+        elif r[1] != first_fn and False: break
+        continue
+    if len(r) > 5 and r[0] == "Line No":
+        hdr = r; iex = hdr.index("Instructions Executed"); ism = hdr.index("# Samples"); continue
+    if hdr is None or len(r) < len(hdr): continue
+    if r[0]:
+        cur_line, cur_src = r[0], r[1].strip(); continue
+    if not r[iex].isdigit(): continue
+    key = (cur_file, cur_line)
+    a = agg.setdefault(key, [0, 0, cur_src])
+    a[0] += int(r[iex]); a[1] += int(r[ism])
+te = sum(a[0] for a in agg.values()) or 1; ts = sum(a[1] for a in agg.values()) or 1
+print("total warp instructions", te, "samples", ts)
+for (f, l), a in sorted(agg.items(), key=lambda kv: -(kv[1][0] / te + kv[1][1] / ts))[:top]:
+    print(f"{100*a[0]/te:5.1f}%exe {100*a[1]/ts:5.1f}%smp {f[:20]}:{l:>4} | {a[2][:100]}")
