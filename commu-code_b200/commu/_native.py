@@ -194,6 +194,7 @@ SIGNATURES = {
     "commu_relattn_bwd_dq_tc": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, L, P, P, P],
     "commu_relattn_bwd_dkv_tc": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, P, L, P],
     "commu_decode_linear": [P, L, P, L, I, P, I, P, L, P, L, I, I, I, P],
+    "commu_decode_linear_tiled": [P, L, P, L, I, P, I, P, L, P, L, I, I, I, I, P, P, P],
     "commu_pad_heads": [P, L, I, I, I, I, P, I, L, L, L, P, P],
     "commu_decode_advance": [P, I, I, I, P],
     "commu_decode_attn": [P, P, P, P, I, P, P, I, I, I, I, I, F, P, L, P, P, P],

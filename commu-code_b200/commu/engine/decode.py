@@ -52,6 +52,9 @@ class DecodeState:
 
 
 class DecodeEngine:
+    lin_tiled = True            # fp32 / kernel-per-op linears on the register-tiled GEMM (COMMU_DECODE_LINEAR=simple: old kernel)
+    _lin_scratch = _lin_cnt = None
+
     def __init__(self, model, batch, mem_len, same_length=True, precision="fp32"):
         if batch > 64:
             raise RuntimeError("commu_b200 decode: batch %d > 64 per engine (shard sequences across engines / GPUs)" % batch)
@@ -70,6 +73,7 @@ class DecodeEngine:
             raise RuntimeError("commu_b200: decode needs CUDA (no CPU fallback)")
         nv.lib()
         self.scale = 1.0 / math.sqrt(self.Dh)
+        self.lin_tiled = os.environ.get("COMMU_DECODE_LINEAR", "tiled") == "tiled"
         self._prepare()
 
     # ------------------------------------------------------------------------------------------
@@ -257,6 +261,17 @@ class DecodeEngine:
         nv.dec_linear(self.a_logits)
 
     def _linear(self, x, w, bias, relu, res, out, B, N, K):
+        if self.lin_tiled:
+            # register-tiled SIMT GEMM with K splits (fixed-order split reduction: run-to-run identical results)
+            tiles = (N + 31) // 32
+            need = 2 * 148 * 2048 + tiles * 2048
+            if self._lin_scratch is None or self._lin_scratch.numel() < need or self._lin_cnt.numel() < tiles:
+                self._lin_scratch = torch.empty(max(need, 4 << 20), device=self.dev)
+                self._lin_cnt = torch.zeros(max(tiles, 1024), dtype=torch.int32, device=self.dev)
+            nv.call("commu_decode_linear_tiled", x, x.stride(0), w, w.stride(0), int(w.dtype == torch.bfloat16), bias,
+                    int(relu), res, res.stride(0) if res is not None else 0, out, out.stride(0), B, N, K, 0,
+                    self._lin_scratch, self._lin_cnt)
+            return
         nv.call("commu_decode_linear", x, x.stride(0), w, w.stride(0), int(w.dtype == torch.bfloat16), bias,
                 int(relu), res, res.stride(0) if res is not None else 0, out, out.stride(0), B, N, K)
 

@@ -112,6 +112,130 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) decode_linear_kernel(
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tiled variant for the fp32 engine: out[64, N] = x[64, K] W^T as a register-tiled SIMT GEMM (fp32 FMA, the
+// arithmetic the bit-faithful greedy parity needs).  One CTA = all batch rows x 32 output columns x one K split;
+// thread = 4 rows x 2 columns; x and W chunks of 32 reduction steps are staged in shared memory (x transposed so the
+// 4 rows are one 16-byte read, W rows padded to 36 floats: conflict-free 16-byte reads), the next chunk is fetched
+// into registers while the current one is multiplied.  With K splits the partial sums go to a scratch buffer and
+// the LAST CTA of a column tile (device counter) adds them in split order - a fixed summation order, so repeated
+// runs are bit-identical - and applies bias / ReLU / residual.  The per-column-tile kernel above re-read the whole
+// x for every 4 columns (200 MB of L2 traffic per layer at the benchmark shape).
+// ---------------------------------------------------------------------------------------------
+constexpr int TL_BN = 32, TL_KC = 32, TL_THREADS = 256, TL_WP = TL_KC + 4;
+
+template <typename WT>
+__global__ void __launch_bounds__(TL_THREADS) decode_linear_tiled_kernel(
+    const float* __restrict__ x, long long ldx, const WT* __restrict__ W, long long ldw,
+    const float* __restrict__ bias, int relu, const float* __restrict__ res, long long ldr,
+    float* __restrict__ out, long long ldo, int B, int N, int K, int klen, float* __restrict__ partial,
+    int* __restrict__ counters) {
+  __shared__ __align__(16) float xs[2][TL_KC][64];
+  __shared__ __align__(16) float ws[2][TL_BN][TL_WP];
+  __shared__ int is_last;
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;           // rows 4*ty .. +3, columns tx and tx + 16 of the tile
+  const int n0 = blockIdx.x * TL_BN;
+  const int S = gridDim.y, ks = blockIdx.y;
+  const int k_begin = ks * klen, k_end = min(K, k_begin + klen);
+  const int nchunks = (k_end - k_begin + TL_KC - 1) / TL_KC;
+  // loader roles: x: rows (tid & 63), 16-byte column groups (tid >> 6) and +4; W: column tid >> 3, group tid & 7
+  const int xr = tid & 63, xk = tid >> 6;
+  const int wn = tid >> 3, wk = tid & 7;
+  float4 px[2], pw;
+  auto fetch = [&](int c) {
+    const int k0 = k_begin + c * TL_KC;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int k = k0 + 4 * (xk + 4 * i);
+      px[i] = (xr < B && k < k_end) ? *reinterpret_cast<const float4*>(x + (long long)xr * ldx + k) : make_float4(0, 0, 0, 0);
+    }
+    const int k = k0 + 4 * wk;
+    float w4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (n0 + wn < N && k < k_end) Elem<WT>::load4(W + (long long)(n0 + wn) * ldw + k, w4);
+    pw = make_float4(w4[0], w4[1], w4[2], w4[3]);
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int kk = 4 * (xk + 4 * i);
+      xs[buf][kk][xr] = px[i].x; xs[buf][kk + 1][xr] = px[i].y; xs[buf][kk + 2][xr] = px[i].z; xs[buf][kk + 3][xr] = px[i].w;
+    }
+    *reinterpret_cast<float4*>(&ws[buf][wn][4 * wk]) = pw;
+  };
+  float acc[4][2];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = 0.f;
+  if (nchunks > 0) {
+    fetch(0);
+    stash(0);
+  }
+  __syncthreads();
+  for (int c = 0; c < nchunks; ++c) {
+    const int buf = c & 1;
+    if (c + 1 < nchunks) fetch(c + 1);
+#pragma unroll
+    for (int k4 = 0; k4 < TL_KC / 4; ++k4) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[buf][tx][4 * k4]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[buf][tx + 16][4 * k4]);
+      const float wa[4] = {w0.x, w0.y, w0.z, w0.w}, wb[4] = {w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 xv = *reinterpret_cast<const float4*>(&xs[buf][4 * k4 + e][4 * ty]);
+        acc[0][0] = fmaf(xv.x, wa[e], acc[0][0]); acc[0][1] = fmaf(xv.x, wb[e], acc[0][1]);
+        acc[1][0] = fmaf(xv.y, wa[e], acc[1][0]); acc[1][1] = fmaf(xv.y, wb[e], acc[1][1]);
+        acc[2][0] = fmaf(xv.z, wa[e], acc[2][0]); acc[2][1] = fmaf(xv.z, wb[e], acc[2][1]);
+        acc[3][0] = fmaf(xv.w, wa[e], acc[3][0]); acc[3][1] = fmaf(xv.w, wb[e], acc[3][1]);
+      }
+    }
+    if (c + 1 < nchunks) stash(buf ^ 1);
+    __syncthreads();
+  }
+  auto finish = [&](float v, int b, int n) {
+    if (b < B && n < N) {
+      if (bias) v += bias[n];
+      if (relu) v = fmaxf(v, 0.f);
+      if (res) v += res[(long long)b * ldr + n];
+      out[(long long)b * ldo + n] = v;
+    }
+  };
+  if (S == 1) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      finish(acc[r][0], 4 * ty + r, n0 + tx);
+      finish(acc[r][1], 4 * ty + r, n0 + tx + 16);
+    }
+    return;
+  }
+  // partial[ks][row][tile column]: [S][gridDim.x][64][32]
+  float* mine = partial + (((long long)ks * gridDim.x + blockIdx.x) * 64) * TL_BN;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    mine[(4 * ty + r) * TL_BN + tx] = acc[r][0];
+    mine[(4 * ty + r) * TL_BN + tx + 16] = acc[r][1];
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(counters + blockIdx.x, 1);
+    is_last = prev == S - 1;
+    if (is_last) counters[blockIdx.x] = 0;          // ready for the next launch (launches are stream-ordered)
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+      const int row = 4 * ty + r, col = tx + 16 * cc;
+      float v = 0.f;
+      for (int s2 = 0; s2 < S; ++s2)
+        v += __ldcg(partial + (((long long)s2 * gridDim.x + blockIdx.x) * 64 + row) * TL_BN + col);
+      finish(v, row, n0 + col);
+    }
+}
+
 // src f32 [rows, ld_src] (+ col_off) with H heads of Dh columns -> dst[row*rs + h*hs + off + e],
 // e < 64, zero-padded beyond Dh.  Serves q staging, K/V ring append and the R table.
 template <typename CT>
@@ -134,8 +258,9 @@ __global__ void pad_heads_kernel(const float* __restrict__ src, long long ld_src
 // One CTA per (h, b); 8 lanes share a key (8 dims each), 4 keys per warp iteration.
 // ---------------------------------------------------------------------------------------------
 constexpr int DA_WARPS = 8;
+constexpr int DA_UNROLL = 4;
 template <typename CT>
-__global__ void __launch_bounds__(DA_WARPS * 32) decode_attn_kernel(
+__global__ void __launch_bounds__(DA_WARPS * 32, 2) decode_attn_kernel(
     const float* __restrict__ q, const CT* __restrict__ kc, const CT* __restrict__ vc,
     const CT* __restrict__ rt, const float* __restrict__ u, const float* __restrict__ vb, int H, int C,
     int n_vis, int cur_slot, float scale, float* __restrict__ out, long long ldo, const int* __restrict__ dstate,
@@ -164,39 +289,45 @@ __global__ void __launch_bounds__(DA_WARPS * 32) decode_attn_kernel(
 #pragma unroll
   for (int e = 0; e < 8; ++e) o[e] = 0.f;
   const float sl2 = scale * 1.4426950408889634f;
-  for (int a0 = warp * 4; a0 < n_vis; a0 += DA_WARPS * 4) {
-    const int a = a0 + sub;
-    const bool ok = a < n_vis;
-    float s = -INFINITY;
-    float vv[8];
+  // DA_UNROLL keys per lane group and iteration: every load of the batch is issued before the first use, so one
+  // thread keeps 3 * DA_UNROLL 32-byte reads in flight (the stream is HBM-latency bound otherwise: 52 % -> of peak)
+  for (int a0 = warp * 4; a0 < n_vis; a0 += DA_WARPS * 4 * DA_UNROLL) {
+    float kk[DA_UNROLL][8], rr[DA_UNROLL][8], vv[DA_UNROLL][8];
+    bool ok[DA_UNROLL];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) vv[e] = 0.f;
-    if (ok) {
-      int slot = cur_slot - a;
-      if (slot < 0) slot += C;
-      float kk[8], rr[8];
-      Elem<CT>::load8(kbase + (long long)slot * 64, kk);
-      Elem<CT>::load8(rbase + (long long)a * H * 64, rr);
-      Elem<CT>::load8(vbase + (long long)slot * 64, vv);
+    for (int uu = 0; uu < DA_UNROLL; ++uu) {
+      const int a = a0 + uu * DA_WARPS * 4 + sub;
+      ok[uu] = a < n_vis;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) kk[uu][e] = rr[uu][e] = vv[uu][e] = 0.f;
+      if (ok[uu]) {
+        int slot = cur_slot - a;
+        if (slot < 0) slot += C;
+        Elem<CT>::load8(kbase + (long long)slot * 64, kk[uu]);
+        Elem<CT>::load8(rbase + (long long)a * H * 64, rr[uu]);
+        Elem<CT>::load8(vbase + (long long)slot * 64, vv[uu]);
+      }
+    }
+#pragma unroll
+    for (int uu = 0; uu < DA_UNROLL; ++uu) {
       float d = 0.f;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) d = fmaf(qu[e], kk[e], fmaf(qv[e], rr[e], d));
-      s = d;
-    }
-    // reduce the partial dot over the 8 lanes of the key (inactive keys carry -inf -> stay -inf)
-    float t = ok ? s : 0.f;
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    t += __shfl_xor_sync(0xffffffffu, t, 4);
-    s = ok ? t * sl2 : -INFINITY;
-    const float mn = fmaxf(m, s);
-    const float msafe = mn == -INFINITY ? 0.f : mn;
-    const float corr = exp2f(m - msafe);
-    const float p = exp2f(s - msafe);
-    l = l * corr + p;
+      for (int e = 0; e < 8; ++e) d = fmaf(qu[e], kk[uu][e], fmaf(qv[e], rr[uu][e], d));
+      // reduce the partial dot over the 8 lanes of the key (inactive keys carry -inf)
+      float t = ok[uu] ? d : 0.f;
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 4);
+      const float s = ok[uu] ? t * sl2 : -INFINITY;
+      const float mn = fmaxf(m, s);
+      const float msafe = mn == -INFINITY ? 0.f : mn;
+      const float corr = exp2f(m - msafe);
+      const float p = exp2f(s - msafe);
+      l = l * corr + p;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = fmaf(p, vv[e], o[e] * corr);
-    m = mn;
+      for (int e = 0; e < 8; ++e) o[e] = fmaf(p, vv[uu][e], o[e] * corr);
+      m = mn;
+    }
   }
   // combine the 4 key sub-groups of the warp
 #pragma unroll
@@ -420,6 +551,39 @@ int commu_decode_linear(const float* x, int64_t ldx, const void* w, int64_t ldw,
     decode_linear_kernel<bf16><<<grid, LIN_WARPS * 32, 0, s>>>(x, ldx, (const bf16*)w, ldw, bias, relu, res, ldr, out, ldo, B, N, K);
   else
     decode_linear_kernel<float><<<grid, LIN_WARPS * 32, 0, s>>>(x, ldx, (const float*)w, ldw, bias, relu, res, ldr, out, ldo, B, N, K);
+  cb_host::count_launch();
+  CB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Same contract on the register-tiled kernel (fp32 engine).  splits >= 1 K splits (0 = chosen here so that the grid
+// fills the SMs); scratch: fp32 [splits * ceil(N / 32) * 64 * 32], counters: int32 [ceil(N / 32)] zero-initialised
+// once (both may be NULL when splits == 1).
+int commu_decode_linear_tiled(const float* x, int64_t ldx, const void* w, int64_t ldw, int w_bf16, const float* bias,
+                              int relu, const float* res, int64_t ldr, float* out, int64_t ldo, int B, int N, int K,
+                              int splits, float* scratch, int* counters, void* stream) {
+  CB_REQUIRE(x && w && out && B >= 1 && B <= 64 && N > 0 && K > 0, "decode_linear_tiled: bad args (B=%d must be <= 64)", B);
+  CB_REQUIRE(K % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0, "decode_linear_tiled: K, ldx, ldw must be multiples of 4");
+  const int tiles = cb_host::ceil_div(N, TL_BN);
+  int S = splits;
+  if (S <= 0) {
+    S = cb_host::ceil_div(2 * cb_host::num_sms(), tiles);
+    if (!scratch || !counters) S = 1;
+  }
+  const int kchunks = cb_host::ceil_div(K, TL_KC);
+  if (S > kchunks) S = kchunks;
+  if (S < 1) S = 1;
+  const int klen = cb_host::ceil_div(kchunks, S) * TL_KC;
+  S = cb_host::ceil_div(K, klen);
+  CB_REQUIRE(S == 1 || (scratch && counters), "decode_linear_tiled: K splits need scratch and counters");
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(tiles, S);
+  if (w_bf16)
+    decode_linear_tiled_kernel<bf16><<<grid, TL_THREADS, 0, s>>>(x, ldx, (const bf16*)w, ldw, bias, relu, res, ldr, out, ldo,
+                                                                 B, N, K, klen, scratch, counters);
+  else
+    decode_linear_tiled_kernel<float><<<grid, TL_THREADS, 0, s>>>(x, ldx, (const float*)w, ldw, bias, relu, res, ldr, out,
+                                                                  ldo, B, N, K, klen, scratch, counters);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

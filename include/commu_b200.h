@@ -259,6 +259,12 @@ int commu_comm_destroy(void);
 int commu_decode_linear(const float* x, int64_t ldx, const void* w, int64_t ldw, int w_bf16, const float* bias,
                         int relu, const float* res, int64_t ldr, float* out, int64_t ldo, int B, int N, int K,
                         void* stream);
+/* Same contract on a register-tiled fp32 SIMT GEMM (one CTA = all rows x 32 columns x one K split; partial sums of the
+ * splits are added in a fixed order by the last CTA of a column tile, so results are run-to-run identical).  splits
+ * = 0 lets the library pick; scratch: fp32 [splits * ceil(N/32) * 2048], counters: int32 [ceil(N/32)] zeroed once. */
+int commu_decode_linear_tiled(const float* x, int64_t ldx, const void* w, int64_t ldw, int w_bf16, const float* bias,
+                              int relu, const float* res, int64_t ldr, float* out, int64_t ldo, int B, int N, int K,
+                              int splits, float* scratch, int* counters, void* stream);
 /* dst[row*row_stride + h*head_stride + offset + e] = src[row, col_off + h*Dh + e], e < 64 (zero padded):
  * stages q, appends K / V to the ring cache slot, builds the R-by-distance table. */
 int commu_pad_heads(const float* src, int64_t ld_src, int col_off, int rows, int H, int Dh, void* dst,

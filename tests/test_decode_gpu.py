@@ -325,3 +325,35 @@ def test_decode_greedy_512_tokens_at_bench_shape(precision):
     with open(os.path.join(ROOT, "gpurun_out", "decode_parity_%s.json" % precision), "w") as f:
         json.dump({"precision": precision, "steps": 512, "batch": B, "identical_tokens": same, "thin_margin_steps": thin,
                    "wrong_with_margin": wrong, "worst_logit_err": worst, "logit_scale": scale}, f)
+
+
+@pytest.mark.parametrize("B,N,K", [(64, 1536, 512), (64, 512, 2048), (5, 729, 512), (1, 500, 100), (33, 2048, 512), (64, 40, 36)])
+@pytest.mark.parametrize("wdtype", [torch.float32, torch.bfloat16])
+def test_decode_linear_tiled_matches_matmul(B, N, K, wdtype):
+    """fp32-engine linear layers (register-tiled SIMT GEMM with K splits): fp32 FMA results against torch's fp32
+    matmul (summation-order noise only), bias / ReLU / residual epilogue, and bit-identical repeated runs (the K
+    splits are added in a fixed order by the last CTA of a tile)."""
+    from commu import _native as nv
+    torch.manual_seed(B * 7 + N + K)
+    dev = "cuda"
+    x = torch.randn(B, K, device=dev)
+    w = (torch.randn(N, K, device=dev) * 0.1).to(wdtype)
+    bias = torch.randn(N, device=dev)
+    res = torch.randn(B, N, device=dev)
+    scratch = torch.empty(4 << 20, device=dev)
+    cnt = torch.zeros(1024, dtype=torch.int32, device=dev)
+    outs = []
+    for splits in (0, 0, 1, 3):
+        out = torch.full((B, N), float("nan"), device=dev)
+        nv.call("commu_decode_linear_tiled", x, K, w, K, int(wdtype == torch.bfloat16), bias, 1, res, N, out, N, B, N, K,
+                splits, scratch, cnt)
+        outs.append(out)
+    ref = torch.relu(x.double() @ w.double().t() + bias.double()) + res.double()
+    for o in outs:
+        assert (o.double() - ref).abs().max() < 2e-5 * max(1.0, float(ref.abs().max())), (B, N, K)
+    assert torch.equal(outs[0], outs[1])
+    assert int(cnt.abs().sum()) == 0                      # every tile counter is back at zero
+    plain = torch.empty(B, N, device=dev)
+    nv.call("commu_decode_linear_tiled", x, K, w, K, int(wdtype == torch.bfloat16), None, 0, None, 0, plain, N, B, N, K,
+            0, scratch, cnt)
+    assert (plain.double() - x.double() @ w.double().t()).abs().max() < 2e-5 * max(1.0, float(ref.abs().max()))
