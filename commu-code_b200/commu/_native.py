@@ -195,6 +195,7 @@ SIGNATURES = {
     "commu_relattn_bwd_dkv_tc": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, P, L, P, P, P, L, P],
     "commu_decode_linear": [P, L, P, L, I, P, I, P, L, P, L, I, I, I, P],
     "commu_decode_linear_tiled": [P, L, P, L, I, P, I, P, L, P, L, I, I, I, I, P, P, P],
+    "commu_decode_qkv_tiled": [P, L, P, L, I, I, I, I, P, P, P, I, I, P, P, P, P],
     "commu_pad_heads": [P, L, I, I, I, I, P, I, L, L, L, P, P],
     "commu_decode_advance": [P, I, I, I, P],
     "commu_decode_attn": [P, P, P, P, I, P, P, I, I, I, I, I, F, P, L, P, P, P],
@@ -217,7 +218,7 @@ SIGNATURES = {
     "commu_cast_pad": [P, L, I, I, I, I, I, I, P, L, I, P],
     "commu_unpad_accum": [P, L, I, I, I, I, I, I, P, L, F, P],
     "commu_sumsq": [P, L, P, P],
-    "commu_clip_adam": [P, P, P, P, L, F, F, F, F, I, P, F, F, F, P, P],
+    "commu_clip_adam": [P, P, P, P, L, F, F, F, F, I, P, F, F, F, P, P, P],
     "commu_relattn_fwd": [P, L, P, P, L, P, L, I, P, P, P, I, I, I, I, I, I, F, P, L, P, P, P, P],
     "commu_relattn_fwd_tc": [P, L, P, P, L, P, L, I, P, P, P, I, I, I, I, I, I, F, P, L, P, P, P, P, P, P],
     "commu_relattn_bwd": [P, P, L, P, P, L, P, L, I, P, I, I, I, I, I, I, F, P, L, P, P, L, P, P, L,

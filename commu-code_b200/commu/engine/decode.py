@@ -127,7 +127,7 @@ class DecodeEngine:
         self.lbias = sd["crit.out_layers.0.bias"].detach()
         # step workspaces
         f = lambda *s: torch.empty(*s, device=dev)
-        self.ws = dict(x=f(B, d), qkv=f(B, 3 * H * Dh), q=f(B, H, 64), att=f(B, H * 64), z=f(B, d), y=f(B, d),
+        self.ws = dict(x=f(B, d), qkv=f(B, 3 * H * Dh), q=torch.zeros(B, H, 64, device=dev), att=f(B, H * 64), z=f(B, d), y=f(B, d),
                        h=f(B, self.Di), logits=f(B, self.V))
         # bf16 throughput mode: the linear layers run on the tcgen05 GEMM (weights streamed once per step,
         # the 64 batch rows are one half-filled 128-row MMA tile), so activations also exist as bf16 operands
@@ -260,14 +260,18 @@ class DecodeEngine:
             nv.dec_linear(a_f2)
         nv.dec_linear(self.a_logits)
 
+    def _lin_buffers(self, N):
+        """Scratch of the K-split partial sums and the per-tile counters of the tiled linear kernel."""
+        tiles = (N + 31) // 32
+        need = 2 * 148 * 2048 + tiles * 2048
+        if self._lin_scratch is None or self._lin_scratch.numel() < need or self._lin_cnt.numel() < tiles:
+            self._lin_scratch = torch.empty(max(need, 4 << 20), device=self.dev)
+            self._lin_cnt = torch.zeros(max(tiles, 1024), dtype=torch.int32, device=self.dev)
+
     def _linear(self, x, w, bias, relu, res, out, B, N, K):
         if self.lin_tiled:
             # register-tiled SIMT GEMM with K splits (fixed-order split reduction: run-to-run identical results)
-            tiles = (N + 31) // 32
-            need = 2 * 148 * 2048 + tiles * 2048
-            if self._lin_scratch is None or self._lin_scratch.numel() < need or self._lin_cnt.numel() < tiles:
-                self._lin_scratch = torch.empty(max(need, 4 << 20), device=self.dev)
-                self._lin_cnt = torch.zeros(max(tiles, 1024), dtype=torch.int32, device=self.dev)
+            self._lin_buffers(N)
             nv.call("commu_decode_linear_tiled", x, x.stride(0), w, w.stride(0), int(w.dtype == torch.bfloat16), bias,
                     int(relu), res, res.stride(0) if res is not None else 0, out, out.stride(0), B, N, K, 0,
                     self._lin_scratch, self._lin_cnt)
@@ -305,13 +309,19 @@ class DecodeEngine:
             w = self.W[l]
             if tc:
                 nv.gemm(wb["x"], w["qkv"], m=B, n=3 * H * Dh, k=d, out_f32=ws["qkv"])
+            elif self.lin_tiled and not self.bf16:
+                # fp32 engine: the qkv projection scatters q / k / v into the padded head layouts from its epilogue
+                self._lin_buffers(3 * H * Dh)
+                nv.call("commu_decode_qkv_tiled", x, x.stride(0), w["qkv"], w["qkv"].stride(0), B, H, Dh, d, ws["q"],
+                        self.kc[l], self.vc[l], C, slot, dstate, self._lin_scratch, self._lin_cnt)
             else:
                 self._linear(x, w["qkv"], None, False, None, ws["qkv"], B, 3 * H * Dh, d)
-            nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 0, B, H, Dh, ws["q"], 0, H * 64, 64, 0, None)
-            nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, H * Dh, B, H, Dh, self.kc[l], cb, H * C * 64, C * 64,
-                    slot * 64, dstate)
-            nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 2 * H * Dh, B, H, Dh, self.vc[l], cb, H * C * 64, C * 64,
-                    slot * 64, dstate)
+            if tc or self.bf16 or not self.lin_tiled:
+                nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 0, B, H, Dh, ws["q"], 0, H * 64, 64, 0, None)
+                nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, H * Dh, B, H, Dh, self.kc[l], cb, H * C * 64, C * 64,
+                        slot * 64, dstate)
+                nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 2 * H * Dh, B, H, Dh, self.vc[l], cb, H * C * 64, C * 64,
+                        slot * 64, dstate)
             nv.call("commu_decode_attn", ws["q"], self.kc[l], self.vc[l], self.rt[l], cb, self.u, self.vb, B, H, C,
                     n_vis, slot, self.scale, ws["att"], H * 64, dstate, wb["att"] if tc else None)
             if tc:

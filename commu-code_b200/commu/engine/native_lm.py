@@ -136,8 +136,47 @@ class NativeLM:
         return S
 
     @torch.no_grad()
-    def refresh_shadow(self):
+    def adopt_shadow(self, flat_bf16, flat_f32, offsets):
+        """Aligned shapes only (Dh = 64, d and d_inner multiples of 64): the operand shadows become VIEWS of a flat bf16
+        arena that mirrors the trainer's flat fp32 master arena (same offsets), so the Adam kernel can emit them
+        (commu_clip_adam p_bf16) and the 85 cast launches after every optimizer step disappear."""
+        assert self.aligned
+        H, d, Di, V = self.H, self.d, self.Di, self.V
+        view = lambda name, rows, cols, skip=0: flat_bf16[offsets[name] + skip: offsets[name] + skip + rows * cols].view(rows, cols)
+        S = {"layers": []}
+        for l in range(self.L):
+            pre = "layers.%d." % l
+            S["layers"].append(dict(
+                wq=view(pre + "dec_attn.qkv_net.weight", self.hd, d),
+                wkv=view(pre + "dec_attn.qkv_net.weight", 2 * self.hd, d, skip=self.hd * d),
+                wr=view(pre + "dec_attn.r_net.weight", self.hd, d),
+                wo=view(pre + "dec_attn.o_net.weight", d, self.hd),
+                w1=view(pre + "pos_ff.CoreNet.0.weight", Di, d),
+                w2=view(pre + "pos_ff.CoreNet.3.weight", d, Di),
+                b1=self.P[pre + "pos_ff.CoreNet.0.bias"], b2=self.P[pre + "pos_ff.CoreNet.3.bias"]))   # fp32 masters themselves
+        S["emb"] = view("word_emb.emb_layers.0.weight", V, d)
+        S["u"], S["vb"] = self.P["r_w_bias"], self.P["r_r_bias"]
+        S["lbias"] = torch.zeros(self.vp, device=self.dev)
+        self._shadow = S
+        self._ext = (flat_bf16, flat_f32)
+        self._shadow_version = None
+
+    @torch.no_grad()
+    def refresh_shadow(self, after_update=False):
         """fp32 masters -> bf16 operand shadows (padded).  Call after every optimizer step."""
+        if getattr(self, "_ext", None) is not None:
+            # adopted arena: after an optimizer step the Adam kernel has already written the bf16 copy; any other
+            # change of the masters (load_state_dict, manual edits) is caught by the version check -> one flat cast
+            S, P = self._shadow, self.P
+            if S["layers"][0]["b1"] is not P["layers.0.pos_ff.CoreNet.0.bias"]:   # parameters re-materialised
+                self._ext = None
+                self._shadow = None
+                return self.refresh_shadow()
+            if not after_update:
+                self._ext[0].copy_(self._ext[1])
+            S["lbias"][:self.V].copy_(P["crit.out_layers.0.bias"])
+            self._shadow_version = self._param_version()
+            return
         if self._shadow is None:
             self._shadow = self._alloc_shadow()
         S, P = self._shadow, self.P

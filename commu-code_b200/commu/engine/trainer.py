@@ -119,6 +119,12 @@ class Trainer:
         self.gnorm_sq = torch.zeros(1, device=dev)
         self.gnorm = torch.zeros(1, device=dev)
         self.engine = self.model._engine()
+        # aligned shapes: the bf16 GEMM operands are views of ONE flat bf16 arena with the layout of flat_p, written by
+        # the Adam kernel itself (no cast pass after the optimizer step)
+        self.flat_pb = None
+        if getattr(self.engine, "aligned", False) and dev.type == "cuda":
+            self.flat_pb = self.flat_p.to(torch.bfloat16)
+            self.engine.adopt_shadow(self.flat_pb, self.flat_p, self.offsets)
         self.engine.refresh_shadow()
 
     def current_lr(self):
@@ -175,8 +181,8 @@ class Trainer:
         nv.call("commu_sumsq", self.flat_g, self.flat_g.numel(), self.gnorm_sq)
         nv.call("commu_clip_adam", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_p.numel(),
                 lr, self.betas[0], self.betas[1], self.eps, self.step, self.gnorm_sq, self.clip,
-                1.0 / self.world, self.weight_decay, self.gnorm)
-        self.engine.refresh_shadow()
+                1.0 / self.world, self.weight_decay, self.gnorm, self.flat_pb)
+        self.engine.refresh_shadow(after_update=self.flat_pb is not None)
         return self.gnorm[0].clone()
 
     # ---- gradient exchange overlapped with the backward (one NCCL sum all-reduce per layer span, side stream) ----

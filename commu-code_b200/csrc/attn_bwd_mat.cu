@@ -44,6 +44,7 @@ constexpr float LOG2E = 1.4426950408889634f;
 struct MatParams {
   int T, M, B, H, Tpad, Kp, P, X, nkt, kr;
   int same_length, shift;
+  int ds4d;             // 1: the dS tile moves as one 4-D TMA box per key half (group stride 8P - 8), 0: 16 eight-row boxes
   const unsigned char* reset;
   float scale, drop_keep;
   const float* lse;     // [B,H,T]
@@ -81,7 +82,8 @@ template <bool DROP>
 __global__ void __launch_bounds__(P1_THREADS, 1)
 relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_qu,
                       const __grid_constant__ CUtensorMap tm_do, const __grid_constant__ CUtensorMap tm_p,
-                      const __grid_constant__ CUtensorMap tm_ds, const MatParams p) {
+                      const __grid_constant__ CUtensorMap tm_ds, const __grid_constant__ CUtensorMap tm_ds4,
+                      const MatParams p) {
   extern __shared__ uint8_t smem_raw[];
   P1Smem& sm = *reinterpret_cast<P1Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -154,13 +156,19 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
         if (n + 6 < nq) prefetch_p(n + 6);
         const int i0 = (it_first + n) * TM;
         cb::mbar_wait(&sm.pds_full[n & 1], (n >> 1) & 1);
-        // coarse-sheared store: the 8-row group g of the tile goes to column j0 + X - (i0 + 8g)
+        // coarse-sheared store: the 8-row group g of the tile goes to column j0 + X - (i0 + 8g) - as ONE 4-D box per
+        // key half when the driver accepted the group stride 8P - 8 (36 -> 6 TMA operations per tile), else 16 boxes
+        if (p.ds4d) {
+          cb::tma_store_4d(&tm_ds4, sm.ds, j0 + p.X, 0, i0 >> 3, bh);
+          cb::tma_store_4d(&tm_ds4, sm.ds + TILE16, j0 + 64 + p.X, 0, i0 >> 3, bh);
+        } else {
 #pragma unroll 1
-        for (int half = 0; half < 2; ++half)
+          for (int half = 0; half < 2; ++half)
 #pragma unroll 4
-          for (int g = 0; g < 16; ++g)
-            cb::tma_store_2d(&tm_ds, sm.ds + half * TILE16 + g * 1024, j0 + 64 * half + p.X - (i0 + 8 * g),
-                             bh * p.Tpad + i0 + 8 * g);
+            for (int g = 0; g < 16; ++g)
+              cb::tma_store_2d(&tm_ds, sm.ds + half * TILE16 + g * 1024, j0 + 64 * half + p.X - (i0 + 8 * g),
+                               bh * p.Tpad + i0 + 8 * g);
+        }
         cb::tma_store_commit();
         cb::tma_store_wait_read<0>();       // the single dS tile may be rewritten (the next tile needs it ~1000 cycles later)
         cb::mbar_arrive(&sm.ds_st);
@@ -228,10 +236,13 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
     const float* mt_p = p.mt + ((long long)bh * p.nkt + jt) * p.Tpad;
     const float lkeep = DROP ? log2f(p.drop_keep) : 0.f;
     const uint32_t a_ds = cb::smem_u32(sm.ds) + rowoff;
-    float lse_n = 0.f, del_n = 0.f, mt_n = 0.f;
-    {
-      const int i = it_first * TM + li;
-      if (i < p.T) { lse_n = lse_p[i]; del_n = del_p[i]; mt_n = mt_p[i]; }
+    // per-row constants of the NEXT TWO tiles are always in flight: under the bulk traffic of this kernel a plain
+    // global load takes longer than one tile (ncu: 19 % of the stall samples sat on the first use with a one-tile lead)
+    float lse_q[2] = {0.f, 0.f}, del_q[2] = {0.f, 0.f}, mt_q[2] = {0.f, 0.f};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = (it_first + u) * TM + li;
+      if (u < nq && i < p.T) { lse_q[u] = lse_p[i]; del_q[u] = del_p[i]; mt_q[u] = mt_p[i]; }
     }
     for (int n = 0; n < nq; ++n) {
       const int i0 = (it_first + n) * TM;
@@ -241,12 +252,15 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
       // (a tile in which this row saw no visible key yet was taken at m_tile = 0 with P~ = 0: clamp, so that a very
       // negative LSE cannot turn 0 * exp2(-LSE) into NaN; tiles the forward skipped carry no m_tile at all)
       const bool vis = jt >= key_lo(i0, p.M, p.same_length, p.shift, reset) / TN;   // did the forward visit this tile?
+      const float lse_n = (n & 1) ? lse_q[1] : lse_q[0], del_n = (n & 1) ? del_q[1] : del_q[0];
+      const float mt_n = (n & 1) ? mt_q[1] : mt_q[0];
       const float f = vis ? ex2(fminf(mt_n - lse_n * LOG2E, 0.f) - lkeep) : 0.f;
       const float ndelta = -(DROP ? del_n * p.drop_keep : del_n);
       {
-        const int inext = i + TM;
-        lse_n = 0.f; del_n = 0.f; mt_n = 0.f;
-        if (n + 1 < nq && inext < p.T) { lse_n = lse_p[inext]; del_n = del_p[inext]; mt_n = mt_p[inext]; }
+        const int i2 = i + 2 * TM;
+        float a = 0.f, bq = 0.f, c = 0.f;
+        if (n + 2 < nq && i2 < p.T) { a = lse_p[i2]; bq = del_p[i2]; c = mt_p[i2]; }
+        if (n & 1) { lse_q[1] = a; del_q[1] = bq; mt_q[1] = c; } else { lse_q[0] = a; del_q[0] = bq; mt_q[0] = c; }
       }
       const int bi = n & 1;
       const uint32_t ph = (n >> 1) & 1;
@@ -267,35 +281,44 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
       cb::tmem_ld_wait();
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.dp_free[bi]);
-      uint32_t pk[16], dsk[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const uint32_t ww = vis ? w[e] : 0u;
-        const float x0 = cb::bf16_lo(ww) * f, x1 = cb::bf16_hi(ww) * f;     // signed: negative = dropped
-        const float d0 = __uint_as_float(dp[2 * e]), d1 = __uint_as_float(dp[2 * e + 1]);
-        float k0, k1, s0, s1;
-        if (DROP) {
-          k0 = fmaxf(x0, 0.f); k1 = fmaxf(x1, 0.f);
-          s0 = fmaf(k0, d0, fabsf(x0) * ndelta);
-          s1 = fmaf(k1, d1, fabsf(x1) * ndelta);
-        } else {
-          k0 = x0; k1 = x1;
-          s0 = x0 * (d0 + ndelta);
-          s1 = x1 * (d1 + ndelta);
-        }
-        pk[e] = cb::pack_bf16(k0, k1);
-        dsk[e] = cb::pack_bf16(s0, s1);
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-        sts_v4(a_pt + (((cx + c) ^ sw) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
-      if (n >= 1) {   // the single dS tile: the previous tile's dK product and TMA stores are done with it
-        cb::mbar_wait(&sm.ds_mma, (n - 1) & 1);
+      if (n >= 1) {   // the single dS tile: the previous tile's dK product and TMA stores are done with it (both
+        cb::mbar_wait(&sm.ds_mma, (n - 1) & 1);   // completed about a tile ago in steady state)
         cb::mbar_wait(&sm.ds_st, (n - 1) & 1);
       }
+      if (vis) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
-        sts_v4(a_ds + (((cx + c) ^ sw) << 4), dsk[c * 4], dsk[c * 4 + 1], dsk[c * 4 + 2], dsk[c * 4 + 3]);
+        for (int c = 0; c < 4; ++c) {      // 8 keys = one 16-byte chunk of P and of dS, stored as soon as it is formed
+          uint32_t pk[4], dsk[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int e = 4 * c + q;
+            const float x0 = cb::bf16_lo(w[e]) * f, x1 = cb::bf16_hi(w[e]) * f;     // signed: negative = dropped
+            const float d0 = __uint_as_float(dp[2 * e]), d1 = __uint_as_float(dp[2 * e + 1]);
+            float k0, k1, s0, s1;
+            if (DROP) {
+              k0 = fmaxf(x0, 0.f); k1 = fmaxf(x1, 0.f);
+              s0 = fmaf(k0, d0, fabsf(x0) * ndelta);
+              s1 = fmaf(k1, d1, fabsf(x1) * ndelta);
+            } else {
+              k0 = x0; k1 = x1;
+              s0 = x0 * (d0 + ndelta);
+              s1 = x1 * (d1 + ndelta);
+            }
+            pk[q] = cb::pack_bf16(k0, k1);
+            dsk[q] = cb::pack_bf16(s0, s1);
+          }
+          const uint32_t off = (((cx + c) ^ sw) << 4);
+          sts_v4(a_pt + off, pk[0], pk[1], pk[2], pk[3]);
+          sts_v4(a_ds + off, dsk[0], dsk[1], dsk[2], dsk[3]);
+        }
+      } else {       // a tile the forward skipped (reset / same_length): P = dS = 0, the stored bits are never used
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t off = (((cx + c) ^ sw) << 4);
+          sts_v4(a_pt + off, 0u, 0u, 0u, 0u);
+          sts_v4(a_ds + off, 0u, 0u, 0u, 0u);
+        }
+      }
       cb::fence_proxy_async();
       cb::mbar_arrive(&sm.pds_full[bi]);
     }
@@ -359,6 +382,7 @@ __host__ __device__ inline int a_blocks(int Tpad) { return (Tpad / 8 + 127) / 12
 template <int MODE>
 __global__ void __launch_bounds__(G_THREADS, 1)
 relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a,    // MODE_A: 2-D dS view, box {64, 8}; else the residue view, box {64,1,128,1}
+                        const __grid_constant__ CUtensorMap tm_a4,   // MODE_A with p.ds4d: 4-D dS view, box {64, 8, 16, 1}
                         const __grid_constant__ CUtensorMap tm_b,    // MODE_A: K rows3d; MODE_C: Rrev 2-D; MODE_R: unused
                         const __grid_constant__ Maps8 tm_qv,         // MODE_R: (q+v) rows of residue r, one map per r
                         const MatParams p) {
@@ -415,12 +439,17 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a,    // MODE_A: 
         cb::mbar_arrive_expect_tx(&sm.full[st], TILE32 + TILE16);
         if (MODE == MODE_A) {
           const int j0 = s * TN;
+          if (p.ds4d) {
+            cb::tma_load_4d(sm.a[st], &tm_a4, &sm.full[st], j0 + p.X, 0, i0 >> 3, bh);
+            cb::tma_load_4d(sm.a[st] + TILE16, &tm_a4, &sm.full[st], j0 + 64 + p.X, 0, i0 >> 3, bh);
+          } else {
 #pragma unroll 1
-          for (int half = 0; half < 2; ++half)
+            for (int half = 0; half < 2; ++half)
 #pragma unroll 4
-            for (int g = 0; g < 16; ++g)
-              cb::tma_load_2d(sm.a[st] + half * TILE16 + g * 1024, &tm_a, &sm.full[st],
-                              j0 + 64 * half + p.X - (i0 + 8 * g), bh * p.Tpad + i0 + 8 * g);
+              for (int g = 0; g < 16; ++g)
+                cb::tma_load_2d(sm.a[st] + half * TILE16 + g * 1024, &tm_a, &sm.full[st],
+                                j0 + 64 * half + p.X - (i0 + 8 * g), bh * p.Tpad + i0 + 8 * g);
+          }
           cb::tma_load_3d(sm.b[st], &tm_b, &sm.full[st], h * DH, b, j0);
         } else if (MODE == MODE_C) {
           const int cc = (s_first + s) * 128;
@@ -676,6 +705,19 @@ extern "C" int commu_relattn_bwd_mat(const void* qu, const void* qv, int64_t ldq
     const uint32_t box[2] = {64, 8};
     if ((rc = make_tmap(&tds2, ds, 2, dims, str, box))) return rc;
   }
+  CUtensorMap tds4 = tds2;
+  {   // key-indexed view as one box per key half: {column, row in group, 8-row group (stride 8P - 8: the coarse shear), (b,h)}
+    const uint64_t dims[4] = {(uint64_t)g.P, 8, (uint64_t)g.Tpad / 8, (uint64_t)BH};
+    const uint64_t str[3] = {(uint64_t)g.P * 2, (uint64_t)(8 * g.P - 8) * 2, (uint64_t)g.Tpad * g.P * 2};
+    const uint32_t box[4] = {64, 8, 16, 1};
+    static int use4d = -1;        // COMMU_ATTN_DS4D=0 forces the 16-box path
+    if (use4d < 0) {
+      const char* e = getenv("COMMU_ATTN_DS4D");
+      use4d = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.ds4d = use4d && make_tmap(&tds4, ds, 4, dims, str, box) == 0;
+    if (!p.ds4d) tds4 = tds2;     // (a driver that rejects the overlapping group stride: keep the 2-D boxes)
+  }
   {   // residue view: {column, residue r, row block a, (b,h)}
     const uint64_t dims[4] = {(uint64_t)g.P, 8, (uint64_t)g.Tpad / 8, (uint64_t)BH};
     const uint64_t str[3] = {(uint64_t)g.P * 2, (uint64_t)g.P * 16, (uint64_t)g.Tpad * g.P * 2};
@@ -714,14 +756,14 @@ extern "C" int commu_relattn_bwd_mat(const void* qu, const void* qv, int64_t ldq
   }
   {
     dim3 grid(cb_host::ceil_div(Ktot, TN), H, B);
-    if (thr) relattn_bwd_p1_kernel<true><<<grid, P1_THREADS, p1_smem, stream>>>(tv, tqu, tdo, tp, tds2, p);
-    else relattn_bwd_p1_kernel<false><<<grid, P1_THREADS, p1_smem, stream>>>(tv, tqu, tdo, tp, tds2, p);
+    if (thr) relattn_bwd_p1_kernel<true><<<grid, P1_THREADS, p1_smem, stream>>>(tv, tqu, tdo, tp, tds2, tds4, p);
+    else relattn_bwd_p1_kernel<false><<<grid, P1_THREADS, p1_smem, stream>>>(tv, tqu, tdo, tp, tds2, tds4, p);
   }
   const int nab = a_blocks(g.Tpad);
-  relattn_bwd_band_kernel<MODE_A><<<dim3(cb_host::ceil_div(T, TM), H, B), G_THREADS, g_smem, stream>>>(tds2, tk, tqv, p);
-  relattn_bwd_band_kernel<MODE_C><<<dim3(nab * 8, H, B), G_THREADS, g_smem, stream>>>(tdsg, trr, tqv, p);
+  relattn_bwd_band_kernel<MODE_A><<<dim3(cb_host::ceil_div(T, TM), H, B), G_THREADS, g_smem, stream>>>(tds2, tds4, tk, tqv, p);
+  relattn_bwd_band_kernel<MODE_C><<<dim3(nab * 8, H, B), G_THREADS, g_smem, stream>>>(tdsg, tds4, trr, tqv, p);
   const int ncb = (g.X + M + 7) / 128 + 1;
-  relattn_bwd_band_kernel<MODE_R><<<dim3(ncb * 8, H, 1), G_THREADS, g_smem, stream>>>(tdsg, trr, tqv, p);
+  relattn_bwd_band_kernel<MODE_R><<<dim3(ncb * 8, H, 1), G_THREADS, g_smem, stream>>>(tdsg, tds4, trr, tqv, p);
   cb_host::count_launch(5);
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

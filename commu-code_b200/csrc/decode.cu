@@ -123,13 +123,20 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) decode_linear_kernel(
 // x for every 4 columns (200 MB of L2 traffic per layer at the benchmark shape).
 // ---------------------------------------------------------------------------------------------
 constexpr int TL_BN = 32, TL_KC = 32, TL_THREADS = 256, TL_WP = TL_KC + 4;
+struct QkvDest {      // optional epilogue of the qkv projection (fp32 engine): scatter into the padded head layouts
+  float* q;
+  float* k;
+  float* v;
+  int H, Dh, C, slot;
+  const int* dstate;
+};
 
 template <typename WT>
 __global__ void __launch_bounds__(TL_THREADS) decode_linear_tiled_kernel(
     const float* __restrict__ x, long long ldx, const WT* __restrict__ W, long long ldw,
     const float* __restrict__ bias, int relu, const float* __restrict__ res, long long ldr,
     float* __restrict__ out, long long ldo, int B, int N, int K, int klen, float* __restrict__ partial,
-    int* __restrict__ counters) {
+    int* __restrict__ counters, QkvDest qd) {
   __shared__ __align__(16) float xs[2][TL_KC][64];
   __shared__ __align__(16) float ws[2][TL_BN][TL_WP];
   __shared__ int is_last;
@@ -191,12 +198,20 @@ __global__ void __launch_bounds__(TL_THREADS) decode_linear_tiled_kernel(
     if (c + 1 < nchunks) stash(buf ^ 1);
     __syncthreads();
   }
+  const int slot = qd.q ? (qd.dstate ? qd.dstate[0] : qd.slot) : 0;
   auto finish = [&](float v, int b, int n) {
     if (b < B && n < N) {
       if (bias) v += bias[n];
       if (relu) v = fmaxf(v, 0.f);
       if (res) v += res[(long long)b * ldr + n];
-      out[(long long)b * ldo + n] = v;
+      if (qd.q) {   // qkv_net: q -> staged query [B,H,64], k / v -> ring slot of the caches [B,H,C,64] (head dim padded to 64)
+        const int hd = qd.H * qd.Dh;
+        const int which = n / hd, hh = (n % hd) / qd.Dh, e = n % qd.Dh;
+        if (which == 0) qd.q[((long long)b * qd.H + hh) * 64 + e] = v;
+        else (which == 1 ? qd.k : qd.v)[(((long long)b * qd.H + hh) * qd.C + slot) * 64 + e] = v;
+      } else {
+        out[(long long)b * ldo + n] = v;
+      }
     }
   };
   if (S == 1) {
@@ -578,12 +593,39 @@ int commu_decode_linear_tiled(const float* x, int64_t ldx, const void* w, int64_
   CB_REQUIRE(S == 1 || (scratch && counters), "decode_linear_tiled: K splits need scratch and counters");
   cudaStream_t s = (cudaStream_t)stream;
   dim3 grid(tiles, S);
+  QkvDest qd = {};
   if (w_bf16)
     decode_linear_tiled_kernel<bf16><<<grid, TL_THREADS, 0, s>>>(x, ldx, (const bf16*)w, ldw, bias, relu, res, ldr, out, ldo,
-                                                                 B, N, K, klen, scratch, counters);
+                                                                 B, N, K, klen, scratch, counters, qd);
   else
     decode_linear_tiled_kernel<float><<<grid, TL_THREADS, 0, s>>>(x, ldx, (const float*)w, ldw, bias, relu, res, ldr, out,
-                                                                  ldo, B, N, K, klen, scratch, counters);
+                                                                  ldo, B, N, K, klen, scratch, counters, qd);
+  cb_host::count_launch();
+  CB_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// qkv_net of the fp32 engine on the same kernel: [q | k | v] = x W^T (W fp32 [3*H*Dh, K], model.py:283-310 at T = 1) with
+// the results scattered by the epilogue - q to the staged query [B,H,64], k / v into ring slot `slot` (or dev_state[0])
+// of the fp32 caches [B,H,C,64]; the padding columns Dh..63 of all three are never written (they stay zero).
+int commu_decode_qkv_tiled(const float* x, int64_t ldx, const float* w, int64_t ldw, int B, int H, int Dh, int K, float* q_out,
+                           float* k_cache, float* v_cache, int C, int slot, const int* dev_state, float* scratch,
+                           int* counters, void* stream) {
+  CB_REQUIRE(x && w && q_out && k_cache && v_cache && B >= 1 && B <= 64 && H > 0 && Dh > 0 && Dh <= 64 && K > 0,
+             "decode_qkv_tiled: bad args");
+  CB_REQUIRE(K % 4 == 0 && ldx % 4 == 0 && ldw % 4 == 0, "decode_qkv_tiled: K, ldx, ldw must be multiples of 4");
+  CB_REQUIRE(dev_state || (slot >= 0 && slot < C), "decode_qkv_tiled: bad slot");
+  const int N = 3 * H * Dh;
+  const int tiles = cb_host::ceil_div(N, TL_BN);
+  int S = (scratch && counters) ? cb_host::ceil_div(2 * cb_host::num_sms(), tiles) : 1;
+  const int kchunks = cb_host::ceil_div(K, TL_KC);
+  if (S > kchunks) S = kchunks;
+  if (S < 1) S = 1;
+  const int klen = cb_host::ceil_div(kchunks, S) * TL_KC;
+  S = cb_host::ceil_div(K, klen);
+  QkvDest qd = {q_out, k_cache, v_cache, H, Dh, C, slot, dev_state};
+  decode_linear_tiled_kernel<float><<<dim3(tiles, S), TL_THREADS, 0, (cudaStream_t)stream>>>(
+      x, ldx, w, ldw, nullptr, 0, nullptr, 0, nullptr, 0, B, N, K, klen, scratch, counters, qd);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -488,7 +488,8 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
                             float bc1, float bc2, const float* __restrict__ gnorm_sq, float clip,
-                            float grad_scale, float weight_decay, float* __restrict__ gnorm_out) {
+                            float grad_scale, float weight_decay, float* __restrict__ gnorm_out,
+                            bf16* __restrict__ p_bf16) {
   float coef = grad_scale;
   const float norm = sqrtf(*gnorm_sq) * grad_scale;
   if (clip > 0.f) coef *= fminf(1.f, clip / (norm + 1e-6f));
@@ -502,7 +503,9 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
     m[i] = mi;
     v[i] = vi;
-    p[i] -= step * mi / (sqrtf(vi) * rsq_bc2 + eps);
+    const float pn = p[i] - step * mi / (sqrtf(vi) * rsq_bc2 + eps);
+    p[i] = pn;
+    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pn);   // bf16 operand shadow of the updated master, same flat layout
   }
 }
 
@@ -687,12 +690,12 @@ int commu_sumsq(const float* g, int64_t n, float* out_accum, void* stream) {
 
 int commu_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                     float beta2, float eps, int step, const float* gnorm_sq, float clip, float grad_scale,
-                    float weight_decay, float* gnorm_out, void* stream) {
+                    float weight_decay, float* gnorm_out, void* p_bf16, void* stream) {
   CB_REQUIRE(p && g && m && v && gnorm_sq && n > 0 && step >= 1, "clip_adam: bad args");
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2 = (float)(1.0 - pow((double)beta2, (double)step));
   adam_kernel<<<cb_host::num_sms() * 8, THREADS, 0, (cudaStream_t)stream>>>(
-      p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, gnorm_sq, clip, grad_scale, weight_decay, gnorm_out);
+      p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2, gnorm_sq, clip, grad_scale, weight_decay, gnorm_out, (bf16*)p_bf16);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -136,11 +136,12 @@ int commu_unpad_accum(const float* src, int64_t ld_src, int R, int C, int rseg, 
 /* Optimizer tail (train.py:159-169): out_accum += sum(g^2); then
  * g' = g * grad_scale * min(1, clip / (||g * grad_scale|| + 1e-6)) (clip_grad_norm_) followed by Adam
  * (torch.optim.Adam, no amsgrad; weight_decay is its L2 term g' += weight_decay * p, train.py:442-443) on flat
- * fp32 arenas.  step >= 1. */
+ * fp32 arenas.  step >= 1.  p_bf16 (optional): bf16 copy of the updated parameters in the same flat layout - the GEMM
+ * operand shadows, so that no separate cast pass runs after the optimizer step. */
 int commu_sumsq(const float* g, int64_t n, float* out_accum, void* stream);
 int commu_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                     float beta2, float eps, int step, const float* gnorm_sq, float clip, float grad_scale,
-                    float weight_decay, float* gnorm_out, void* stream);
+                    float weight_decay, float* gnorm_out, void* p_bf16, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused relative-position attention (RelPartialLearnableMultiHeadAttn.forward, model.py:312-345,
@@ -265,6 +266,12 @@ int commu_decode_linear(const float* x, int64_t ldx, const void* w, int64_t ldw,
 int commu_decode_linear_tiled(const float* x, int64_t ldx, const void* w, int64_t ldw, int w_bf16, const float* bias,
                               int relu, const float* res, int64_t ldr, float* out, int64_t ldo, int B, int N, int K,
                               int splits, float* scratch, int* counters, void* stream);
+/* qkv_net of the fp32 engine on the tiled kernel ([q|k|v] = x W^T, W fp32 [3*H*Dh, K]; model.py:283-310 at T = 1): the
+ * epilogue scatters q to the staged query [B,H,64] and k / v into ring slot `slot` (or dev_state[0]) of the fp32 caches
+ * [B,H,C,64]; padding columns Dh..63 are never written (the buffers are zero-initialised once). */
+int commu_decode_qkv_tiled(const float* x, int64_t ldx, const float* w, int64_t ldw, int B, int H, int Dh, int K,
+                           float* q_out, float* k_cache, float* v_cache, int C, int slot, const int* dev_state,
+                           float* scratch, int* counters, void* stream);
 /* dst[row*row_stride + h*head_stride + offset + e] = src[row, col_off + h*Dh + e], e < 64 (zero padded):
  * stages q, appends K / V to the ring cache slot, builds the R-by-distance table. */
 int commu_pad_heads(const float* src, int64_t ld_src, int col_off, int rows, int H, int Dh, void* dst,

@@ -372,6 +372,8 @@ def test_cast_colsum_adam():
         gb = gbuf * step
         gn.zero_()
         nv.call("commu_sumsq", gb, n_al, gn)
-        nv.call("commu_clip_adam", p, gb, m, v, n_al, 0.004, 0.9, 0.999, 1e-8, step, gn, 1.0, 1.0, wd, gout)
+        pb = torch.empty(n_al, device=dev, dtype=torch.bfloat16)
+        nv.call("commu_clip_adam", p, gb, m, v, n_al, 0.004, 0.9, 0.999, 1e-8, step, gn, 1.0, 1.0, wd, gout, pb)
+        assert torch.equal(pb, p.bfloat16())
         assert abs(gout.item() - tn.item()) / tn.item() < 1e-4
         assert (p[:n] - ref_p.data).abs().max() < 2e-6
