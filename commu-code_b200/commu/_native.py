@@ -198,7 +198,7 @@ SIGNATURES = {
     "commu_decode_qkv_tiled": [P, L, P, L, I, I, I, I, P, P, P, I, I, P, P, P, P],
     "commu_pad_heads": [P, L, I, I, I, I, P, I, L, L, L, P, P],
     "commu_decode_advance": [P, I, I, I, P],
-    "commu_decode_attn": [P, P, P, P, I, P, P, I, I, I, I, I, F, P, L, P, P, P],
+    "commu_decode_attn": [P, P, P, P, I, P, P, I, I, I, I, I, F, P, L, P, P, I, P, P, P],
     "commu_decode_fused_linear": [P, P],
     "commu_decode_attn_split": [P, P, P, P, P, P, I, I, I, I, I, F, I, P, P, P, P, L, P, I, I, P],
     "commu_sample": [P, L, I, I, F, I, F, P, ctypes.c_uint64, ctypes.c_uint64, P, P, L, P, P],

@@ -54,6 +54,7 @@ class DecodeState:
 class DecodeEngine:
     lin_tiled = True            # fp32 / kernel-per-op linears on the register-tiled GEMM (COMMU_DECODE_LINEAR=simple: old kernel)
     _lin_scratch = _lin_cnt = None
+    attn_splits, _att_part, _att_cnt = 1, None, None
 
     def __init__(self, model, batch, mem_len, same_length=True, precision="fp32"):
         if batch > 64:
@@ -74,6 +75,11 @@ class DecodeEngine:
         nv.lib()
         self.scale = 1.0 / math.sqrt(self.Dh)
         self.lin_tiled = os.environ.get("COMMU_DECODE_LINEAR", "tiled") == "tiled"
+        # key splits of the streaming attention of the kernel-per-op engines: B*H*splits CTAs should be a near-integer
+        # number of waves of the 2 x SM-count resident slots
+        self.attn_splits = int(os.environ.get("COMMU_DECODE_ATTN_SPLITS", "0")) or self._pick_attn_splits()
+        self._att_part = torch.empty(batch * self.H * self.attn_splits * 66, device=self.dev)
+        self._att_cnt = torch.zeros(batch * self.H, dtype=torch.int32, device=self.dev)
         self._prepare()
 
     # ------------------------------------------------------------------------------------------
@@ -260,6 +266,19 @@ class DecodeEngine:
             nv.dec_linear(a_f2)
         nv.dec_linear(self.a_logits)
 
+    def _pick_attn_splits(self):
+        sms = torch.cuda.get_device_properties(self.dev).multi_processor_count if self.dev.type == "cuda" else 148
+        slots, work = 2 * sms, self.B * self.H
+        best, best_eff = 1, 0.0
+        for s_ in range(1, 9):
+            if s_ > 1 and self.mem_len // s_ < 256:
+                break
+            waves = work * s_ / slots
+            eff = waves / math.ceil(waves)
+            if eff > best_eff + 0.03:
+                best, best_eff = s_, eff
+        return best
+
     def _lin_buffers(self, N):
         """Scratch of the K-split partial sums and the per-tile counters of the tiled linear kernel."""
         tiles = (N + 31) // 32
@@ -323,7 +342,8 @@ class DecodeEngine:
                 nv.call("commu_pad_heads", ws["qkv"], 3 * H * Dh, 2 * H * Dh, B, H, Dh, self.vc[l], cb, H * C * 64, C * 64,
                         slot * 64, dstate)
             nv.call("commu_decode_attn", ws["q"], self.kc[l], self.vc[l], self.rt[l], cb, self.u, self.vb, B, H, C,
-                    n_vis, slot, self.scale, ws["att"], H * 64, dstate, wb["att"] if tc else None)
+                    n_vis, slot, self.scale, ws["att"], H * 64, dstate, wb["att"] if tc else None,
+                    self.attn_splits, self._att_part, self._att_cnt)
             if tc:
                 nv.gemm(wb["att"], w["o"], m=B, n=d, k=H * 64, add_f32=x, out_f32=ws["z"])
                 nv.call("commu_layernorm_fwd", ws["z"], d, w["g1"], w["be1"], d, d, 1e-5, B, ws["y"], d, wb["y"], d,

@@ -281,44 +281,35 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
       cb::tmem_ld_wait();
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.dp_free[bi]);
-      if (n >= 1) {   // the single dS tile: the previous tile's dK product and TMA stores are done with it (both
-        cb::mbar_wait(&sm.ds_mma, (n - 1) & 1);   // completed about a tile ago in steady state)
+      uint32_t pk[16], dsk[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const uint32_t ww = vis ? w[e] : 0u;       // a tile the forward skipped (reset / same_length): P = dS = 0
+        const float x0 = cb::bf16_lo(ww) * f, x1 = cb::bf16_hi(ww) * f;     // signed: negative = dropped
+        const float d0 = __uint_as_float(dp[2 * e]), d1 = __uint_as_float(dp[2 * e + 1]);
+        float k0, k1, s0, s1;
+        if (DROP) {
+          k0 = fmaxf(x0, 0.f); k1 = fmaxf(x1, 0.f);
+          s0 = fmaf(k0, d0, fabsf(x0) * ndelta);
+          s1 = fmaf(k1, d1, fabsf(x1) * ndelta);
+        } else {
+          k0 = x0; k1 = x1;
+          s0 = x0 * (d0 + ndelta);
+          s1 = x1 * (d1 + ndelta);
+        }
+        pk[e] = cb::pack_bf16(k0, k1);
+        dsk[e] = cb::pack_bf16(s0, s1);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        sts_v4(a_pt + (((cx + c) ^ sw) << 4), pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+      if (n >= 1) {   // the single dS tile: the previous tile's dK product and TMA stores are done with it
+        cb::mbar_wait(&sm.ds_mma, (n - 1) & 1);
         cb::mbar_wait(&sm.ds_st, (n - 1) & 1);
       }
-      if (vis) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {      // 8 keys = one 16-byte chunk of P and of dS, stored as soon as it is formed
-          uint32_t pk[4], dsk[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int e = 4 * c + q;
-            const float x0 = cb::bf16_lo(w[e]) * f, x1 = cb::bf16_hi(w[e]) * f;     // signed: negative = dropped
-            const float d0 = __uint_as_float(dp[2 * e]), d1 = __uint_as_float(dp[2 * e + 1]);
-            float k0, k1, s0, s1;
-            if (DROP) {
-              k0 = fmaxf(x0, 0.f); k1 = fmaxf(x1, 0.f);
-              s0 = fmaf(k0, d0, fabsf(x0) * ndelta);
-              s1 = fmaf(k1, d1, fabsf(x1) * ndelta);
-            } else {
-              k0 = x0; k1 = x1;
-              s0 = x0 * (d0 + ndelta);
-              s1 = x1 * (d1 + ndelta);
-            }
-            pk[q] = cb::pack_bf16(k0, k1);
-            dsk[q] = cb::pack_bf16(s0, s1);
-          }
-          const uint32_t off = (((cx + c) ^ sw) << 4);
-          sts_v4(a_pt + off, pk[0], pk[1], pk[2], pk[3]);
-          sts_v4(a_ds + off, dsk[0], dsk[1], dsk[2], dsk[3]);
-        }
-      } else {       // a tile the forward skipped (reset / same_length): P = dS = 0, the stored bits are never used
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t off = (((cx + c) ^ sw) << 4);
-          sts_v4(a_pt + off, 0u, 0u, 0u, 0u);
-          sts_v4(a_ds + off, 0u, 0u, 0u, 0u);
-        }
-      }
+      for (int c = 0; c < 4; ++c)
+        sts_v4(a_ds + (((cx + c) ^ sw) << 4), dsk[c * 4], dsk[c * 4 + 1], dsk[c * 4 + 2], dsk[c * 4 + 3]);
       cb::fence_proxy_async();
       cb::mbar_arrive(&sm.pds_full[bi]);
     }

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(LIN_WARPS * 32) decode_linear_kernel(
 // runs are bit-identical - and applies bias / ReLU / residual.  The per-column-tile kernel above re-read the whole
 // x for every 4 columns (200 MB of L2 traffic per layer at the benchmark shape).
 // ---------------------------------------------------------------------------------------------
-constexpr int TL_BN = 32, TL_KC = 32, TL_THREADS = 256, TL_WP = TL_KC + 4;
+constexpr int TL_BN = 32, TL_KC = 32, TL_THREADS = 256, TL_WP = TL_KC + 4, TL_MAXS = 8;
 struct QkvDest {      // optional epilogue of the qkv projection (fp32 engine): scatter into the padded head layouts
   float* q;
   float* k;
@@ -244,9 +244,15 @@ __global__ void __launch_bounds__(TL_THREADS) decode_linear_tiled_kernel(
 #pragma unroll
     for (int cc = 0; cc < 2; ++cc) {
       const int row = 4 * ty + r, col = tx + 16 * cc;
+      // all partials of this output are requested before the first add (one L2 round trip instead of S), then added
+      // in split order
+      float pv[TL_MAXS];
+#pragma unroll
+      for (int s2 = 0; s2 < TL_MAXS; ++s2)
+        pv[s2] = s2 < S ? __ldcg(partial + (((long long)s2 * gridDim.x + blockIdx.x) * 64 + row) * TL_BN + col) : 0.f;
       float v = 0.f;
-      for (int s2 = 0; s2 < S; ++s2)
-        v += __ldcg(partial + (((long long)s2 * gridDim.x + blockIdx.x) * 64 + row) * TL_BN + col);
+#pragma unroll
+      for (int s2 = 0; s2 < TL_MAXS; ++s2) v += pv[s2];
       finish(v, row, n0 + col);
     }
 }
@@ -279,13 +285,19 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 2) decode_attn_kernel(
     const float* __restrict__ q, const CT* __restrict__ kc, const CT* __restrict__ vc,
     const CT* __restrict__ rt, const float* __restrict__ u, const float* __restrict__ vb, int H, int C,
     int n_vis, int cur_slot, float scale, float* __restrict__ out, long long ldo, const int* __restrict__ dstate,
-    bf16* __restrict__ out_bf16) {
+    bf16* __restrict__ out_bf16, float* __restrict__ partial, int* __restrict__ counters) {
   __shared__ float sh_m[DA_WARPS], sh_l[DA_WARPS], sh_o[DA_WARPS][64];
+  __shared__ int is_last;
   if (dstate) {
     cur_slot = dstate[0];
     n_vis = dstate[1];
   }
   const int h = blockIdx.x, b = blockIdx.y;
+  // key splits (gridDim.z): B*H CTAs do not fill the 2 x 148 resident slots evenly (512 = 1.73 waves); with 4 splits
+  // the grid is 6.9 waves.  The partial (max, sum, out) triples are merged in split order by the last CTA of a (b, h).
+  const int nsplit = gridDim.z, zi = blockIdx.z;
+  const int chunk = ((n_vis + nsplit - 1) / nsplit + 31) & ~31;
+  const int a_begin = zi * chunk, a_end = min(n_vis, a_begin + chunk);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane >> 3, part = lane & 7;
   float qu[8], qv[8];
@@ -306,13 +318,13 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 2) decode_attn_kernel(
   const float sl2 = scale * 1.4426950408889634f;
   // DA_UNROLL keys per lane group and iteration: every load of the batch is issued before the first use, so one
   // thread keeps 3 * DA_UNROLL 32-byte reads in flight (the stream is HBM-latency bound otherwise: 52 % -> of peak)
-  for (int a0 = warp * 4; a0 < n_vis; a0 += DA_WARPS * 4 * DA_UNROLL) {
+  for (int a0 = a_begin + warp * 4; a0 < a_end; a0 += DA_WARPS * 4 * DA_UNROLL) {
     float kk[DA_UNROLL][8], rr[DA_UNROLL][8], vv[DA_UNROLL][8];
     bool ok[DA_UNROLL];
 #pragma unroll
     for (int uu = 0; uu < DA_UNROLL; ++uu) {
       const int a = a0 + uu * DA_WARPS * 4 + sub;
-      ok[uu] = a < n_vis;
+      ok[uu] = a < a_end;
 #pragma unroll
       for (int e = 0; e < 8; ++e) kk[uu][e] = rr[uu][e] = vv[uu][e] = 0.f;
       if (ok[uu]) {
@@ -369,20 +381,53 @@ __global__ void __launch_bounds__(DA_WARPS * 32, 2) decode_attn_kernel(
     for (int e = 0; e < 8; ++e) sh_o[warp][part * 8 + e] = o[e];
   }
   __syncthreads();
+  float mm = -INFINITY, ll = 0.f, oo = 0.f;
   if (threadIdx.x < 64) {
-    float mm = -INFINITY;
 #pragma unroll
     for (int w = 0; w < DA_WARPS; ++w) mm = fmaxf(mm, sh_m[w]);
-    float ll = 0.f, oo = 0.f;
 #pragma unroll
     for (int w = 0; w < DA_WARPS; ++w) {
       const float c = sh_m[w] == -INFINITY ? 0.f : exp2f(sh_m[w] - mm);
       ll += sh_l[w] * c;
       oo += sh_o[w][threadIdx.x] * c;
     }
-    out[(long long)b * ldo + h * 64 + threadIdx.x] = oo / ll;
-    if (out_bf16) out_bf16[(long long)b * ldo + h * 64 + threadIdx.x] = __float2bfloat16_rn(oo / ll);
   }
+  const long long orow = (long long)b * ldo + h * 64 + threadIdx.x;
+  if (nsplit == 1) {
+    if (threadIdx.x < 64) {
+      out[orow] = oo / ll;
+      if (out_bf16) out_bf16[orow] = __float2bfloat16_rn(oo / ll);
+    }
+    return;
+  }
+  const int bh = b * H + h;
+  float* mine = partial + ((long long)bh * nsplit + zi) * 66;
+  if (threadIdx.x < 64) {
+    mine[threadIdx.x] = oo;
+    if (threadIdx.x == 0) { mine[64] = mm; mine[65] = ll; }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(counters + bh, 1);
+    is_last = prev == nsplit - 1;
+    if (is_last) counters[bh] = 0;
+  }
+  __syncthreads();
+  if (!is_last || threadIdx.x >= 64) return;
+  __threadfence();
+  float m_all = -INFINITY;
+  for (int z = 0; z < nsplit; ++z) m_all = fmaxf(m_all, __ldcg(partial + ((long long)bh * nsplit + z) * 66 + 64));
+  float l_all = 0.f, o_all = 0.f;
+  for (int z = 0; z < nsplit; ++z) {
+    const float* pz = partial + ((long long)bh * nsplit + z) * 66;
+    const float mz = __ldcg(pz + 64);
+    const float c = mz == -INFINITY ? 0.f : exp2f(mz - m_all);
+    l_all += __ldcg(pz + 65) * c;
+    o_all += __ldcg(pz + threadIdx.x) * c;
+  }
+  out[orow] = o_all / l_all;
+  if (out_bf16) out_bf16[orow] = __float2bfloat16_rn(o_all / l_all);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -587,6 +632,7 @@ int commu_decode_linear_tiled(const float* x, int64_t ldx, const void* w, int64_
   }
   const int kchunks = cb_host::ceil_div(K, TL_KC);
   if (S > kchunks) S = kchunks;
+  if (S > TL_MAXS) S = TL_MAXS;
   if (S < 1) S = 1;
   const int klen = cb_host::ceil_div(kchunks, S) * TL_KC;
   S = cb_host::ceil_div(K, klen);
@@ -620,6 +666,7 @@ int commu_decode_qkv_tiled(const float* x, int64_t ldx, const float* w, int64_t 
   int S = (scratch && counters) ? cb_host::ceil_div(2 * cb_host::num_sms(), tiles) : 1;
   const int kchunks = cb_host::ceil_div(K, TL_KC);
   if (S > kchunks) S = kchunks;
+  if (S > TL_MAXS) S = TL_MAXS;
   if (S < 1) S = 1;
   const int klen = cb_host::ceil_div(kchunks, S) * TL_KC;
   S = cb_host::ceil_div(K, klen);
@@ -653,19 +700,24 @@ int commu_pad_heads(const float* src, int64_t ld_src, int col_off, int rows, int
 // The n_vis most recent ring entries (ages 0..n_vis-1, age 0 at slot cur_slot) are attended.
 int commu_decode_attn(const float* q, const void* kcache, const void* vcache, const void* rtab, int cache_bf16,
                       const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
-                      float scale, float* out, int64_t ldo, const int* dev_state, void* out_bf16, void* stream) {
+                      float scale, float* out, int64_t ldo, const int* dev_state, void* out_bf16, int splits,
+                      float* partial, int* counters, void* stream) {
   CB_REQUIRE(q && kcache && vcache && rtab && out, "decode_attn: null arg");
   CB_REQUIRE(dev_state || (n_vis >= 1 && n_vis <= C && cur_slot >= 0 && cur_slot < C),
              "decode_attn: bad args (n_vis=%d C=%d slot=%d)", n_vis, C, cur_slot);
   cudaStream_t s = (cudaStream_t)stream;
   cb_host::ProfScope prof(cb_host::PROF_DECODE_ATTN, s);
-  dim3 grid(H, B);
+  if (splits < 1 || !partial || !counters) splits = 1;
+  CB_REQUIRE(splits <= 16, "decode_attn: at most 16 key splits");
+  dim3 grid(H, B, splits);
   if (cache_bf16)
     decode_attn_kernel<bf16><<<grid, DA_WARPS * 32, 0, s>>>(q, (const bf16*)kcache, (const bf16*)vcache, (const bf16*)rtab,
-                                                            r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo, dev_state, (bf16*)out_bf16);
+                                                            r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo, dev_state,
+                                                            (bf16*)out_bf16, partial, counters);
   else
     decode_attn_kernel<float><<<grid, DA_WARPS * 32, 0, s>>>(q, (const float*)kcache, (const float*)vcache, (const float*)rtab,
-                                                             r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo, dev_state, (bf16*)out_bf16);
+                                                             r_w_bias, r_r_bias, H, C, n_vis, cur_slot, scale, out, ldo, dev_state,
+                                                             (bf16*)out_bf16, partial, counters);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;

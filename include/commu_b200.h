@@ -287,7 +287,11 @@ int commu_decode_advance(int* state, int C, int mem_len, int extra_visible, void
  * out_bf16 (optional, same leading dim) receives a bf16 copy: the operand of the o_net GEMM. */
 int commu_decode_attn(const float* q, const void* kcache, const void* vcache, const void* rtab, int cache_bf16,
                       const float* r_w_bias, const float* r_r_bias, int B, int H, int C, int n_vis, int cur_slot,
-                      float scale, float* out, int64_t ldo, const int* dev_state, void* out_bf16, void* stream);
+                      float scale, float* out, int64_t ldo, const int* dev_state, void* out_bf16, int splits,
+                      float* partial, int* counters, void* stream);
+/* (splits > 1: the visible keys of every (sequence, head) are cut into `splits` ranges handled by different CTAs so
+ * that the grid fills the SMs evenly; partial: fp32 [B*H*splits*66], counters: int32 [B*H] zero-initialised once; the
+ * last CTA of a (sequence, head) merges the ranges in order - run-to-run identical.) */
 /* ---- fused token-step kernels of the bf16 decode engine (one decoder layer = 5 launches) ----
  * commu_decode_fused_linear: out[b, n0..n0+15] per CTA = epilogue( prologue(input)[b, :K] . W[n, :K] ), B <= 64
  * rows as the M side of warp-level bf16 MMAs, fp32 accumulation, weights streamed once per call.
