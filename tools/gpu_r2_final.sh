@@ -1,0 +1,26 @@
+#!/bin/bash
+# round 2, evidence run on one B200: GPU test suite, smoke, reference arm, default bench line, launch list + ncu summary
+set +e
+mkdir -p gpurun_out
+timeout 1800 python -m pytest tests -q -m gpu --deselect tests/test_gemm_gpu.py::test_gemm_perf 2>&1 | tail -12 > gpurun_out/r02_gpu_tests.log; tail -4 gpurun_out/r02_gpu_tests.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_bench_reference_arm.err; cut -c1-400 gpurun_out/r02_bench_reference_arm.json
+timeout 1500 python bench.py > gpurun_out/r02_bench_default_final.json 2> gpurun_out/r02_bench_default_final.err
+python - <<'PY'
+import json
+try:
+    j=json.load(open('gpurun_out/r02_bench_default_final.json')); print({k:j.get(k) for k in ("value","ms_per_step","e2e","kernel_time_ms_per_step","roofline","cpu_baseline","clocks","gpu_launches","vs_reference_gpu","final_loss")}); print(j.get("decode"))
+except Exception as e: print("bench parse failed", e)
+PY
+tail -3 gpurun_out/r02_bench_default_final.err
+timeout 600 python bench.py --batch-chunk 4 --no-decode --no-cpu-baseline --no-reference-gpu > gpurun_out/r02_bench_batch_chunk4.json 2>/dev/null; cut -c1-300 gpurun_out/r02_bench_batch_chunk4.json
+COMMU_BENCH_PROFILE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_ncu_launches_bench.csv python bench.py --steps 1 --warmup 2 --no-decode --no-cpu-baseline --no-reference-gpu > gpurun_out/r02_bench_under_ncu.log 2>&1
+python - <<'PY'
+import csv, subprocess
+rows = list(csv.reader(open('gpurun_out/r02_ncu_launches_bench.csv')))
+hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+n = max(int(r[0]) for r in rows[hi+1:] if r and r[0].isdigit()) + 1
+per = n // 4
+print(subprocess.run(["python", "tools/launch_summary.py", "gpurun_out/r02_ncu_launches_bench.csv", "gpurun_out/r02_launch_shares_bench.md", str(2*per), str(3*per)], capture_output=True, text=True).stdout)
+PY
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"relattn_bwd_p1|relattn_bwd_band|relattn_fwd_tc" -s 5 -c 5 -o gpurun_out/r02_prof_attn_mat -f python tools/prof_bwd.py 16 > gpurun_out/r02_ncu.log 2>&1; tail -1 gpurun_out/r02_ncu.log
