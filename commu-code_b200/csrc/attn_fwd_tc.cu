@@ -68,7 +68,7 @@ struct Smem {
   float xsum[4][TM];  // per-row partial sums (end of kernel)
   uint64_t q_ready;
   uint64_t k_full[2], k_empty[2], v_full, v_empty, r_full[2], r_empty[2];
-  uint64_t s_full[2], s_empty[2], bd_full, bd_empty, p_full, o_full, o_empty, pst_full, pst_free;
+  uint64_t s_full[2], s_empty[2], bd_full, bd_empty, p_full, o_full, pst_full, pst_free;
   uint32_t tmem_base;
 };
 
@@ -107,7 +107,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
     cb::mbar_init(&sm.pst_full, SOFT); cb::mbar_init(&sm.pst_free, 1);
     cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
     cb::mbar_init(&sm.p_full, SOFT);
-    cb::mbar_init(&sm.o_full, 1); cb::mbar_init(&sm.o_empty, SOFT);
+    cb::mbar_init(&sm.o_full, 1);
     cb::fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -159,7 +159,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       const uint32_t idesc_s = cb::umma_idesc_bf16(TM, TN, 0, 0);   // S, BD: both operands K-major
       const uint32_t idesc_o = cb::umma_idesc_bf16(TM, DH, 0, 1);   // PV: A in TMEM, B = V (MN-major)
       Ring rk, rr, rs;
-      uint32_t bd_phase = 0, p_phase = 0, o_phase = 0;
+      uint32_t bd_phase = 0, p_phase = 0;
       const uint32_t a_qu = cb::smem_u32(sm.qu), a_qv = cb::smem_u32(sm.qv);
       cb::mbar_wait(&sm.q_ready, 0);
       cb::tc_fence_after();
@@ -199,18 +199,16 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
           issue_s();   // S(t+1)
           issue_bd();  // beta = t+2
         }
-        cb::mbar_wait(&sm.p_full, p_phase);
+        cb::mbar_wait(&sm.p_full, p_phase);     // (every row's O has been rescaled by then, where its maximum moved)
         cb::mbar_wait(&sm.v_full, t & 1);
-        cb::mbar_wait(&sm.o_empty, o_phase ^ 1);
         cb::tc_fence_after();
         const uint64_t vd = cb::umma_smem_desc(cb::smem_u32(sm.v), 8192, 1024);
 #pragma unroll
-        for (int k = 0; k < TN / 16; ++k)
-          umma_bf16_ts(tmem + COL_O, tmem + COL_P + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, k > 0);
+        for (int k = 0; k < TN / 16; ++k)   // O accumulates in TMEM over the key tiles
+          umma_bf16_ts(tmem + COL_O, tmem + COL_P + 8 * k, vd + (uint64_t)(k * (2048 >> 4)), idesc_o, (t > 0 || k > 0));
         cb::umma_commit(&sm.v_empty);
         cb::umma_commit(&sm.o_full);
         p_phase ^= 1;
-        o_phase ^= 1;
       }
     }
   } else if (warp == 3) {
@@ -261,7 +259,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       cb::fence_proxy_async();
     }
     cb::mbar_arrive(&sm.q_ready);
-    uint32_t bd_phase = 0, o_phase = 0;
+    uint32_t bd_phase = 0;
     Ring rs;
     const uint32_t my_row = cb::smem_u32(sm.bd) + li * STAGE_ROW;
     // copy this thread's 32 columns of the BD block in TMEM into half `half` of its row's fp16 staging
@@ -282,9 +280,6 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
                pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
                pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
     };
-    float o[OPT];
-#pragma unroll
-    for (int e = 0; e < OPT; ++e) o[e] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     const float sl2 = p.scale * 1.4426950408889634f;
     const drop::Keys dkeys = drop::row_keys(p.drop_ka, p.drop_kb, (uint32_t)((b * p.H + h) * p.T + i));
@@ -336,10 +331,16 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       sm.xch[g][li] = mx;
       named_bar(2 + wq, NWG * 32);
       mx = fmaxf(fmaxf(sm.xch[0][li], sm.xch[1][li]), fmaxf(sm.xch[2][li], sm.xch[3][li]));
+      // LAZY running maximum: the reference point of the exponentials only moves when the row's maximum grew by more
+      // than 2^8 (or when the row sees its first visible key); otherwise P~ = exp2(s - m_run) may reach 256, which bf16 /
+      // fp32 hold without loss, the normaliser and the stored (P~, m_tile) pairs stay consistent, and O - which
+      // accumulates in TMEM across the key tiles - needs no rescale.  The four threads of a row take the same decision.
       mx = fmaxf(mx * sl2, m_run);
-      const float msafe = mx == -INFINITY ? 0.f : mx;
-      const float corr = ex2(m_run - msafe);
-      m_run = mx;
+      const bool raise = mx > m_run + 8.f;            // (-inf + 8 = -inf: the first finite maximum raises)
+      const float m_use = raise ? mx : m_run;
+      const float msafe = m_use == -INFINITY ? 0.f : m_use;
+      const float corr = raise ? ex2(m_run - msafe) : 1.f;
+      m_run = m_use;
       float rsum = 0.f;
       uint32_t pk[CPT / 2];
       uint32_t a_pst = 0;
@@ -376,18 +377,16 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
         cb::mbar_arrive(&sm.pst_full);
       }
       l_run = l_run * corr + rsum;
-      // ---- fold the previous tile's partial O (scale of the previous max), then rescale ----
-      if (t > 0) {
-        cb::mbar_wait(&sm.o_full, o_phase);
+      // ---- rescale O in TMEM where a row of this warp moved its reference point (rare after the first tiles) ----
+      if (t > 0 && __any_sync(0xffffffffu, raise)) {
+        cb::mbar_wait(&sm.o_full, (t - 1) & 1);          // PV(t-1) has landed
         cb::tc_fence_after();
         uint32_t r[OPT];
         tmem_ld_32x32b_x16(lane_addr + COL_O + g * OPT, r);
         cb::tmem_ld_wait();
-        cb::tc_fence_before();
-        cb::mbar_arrive(&sm.o_empty);
-        o_phase ^= 1;
 #pragma unroll
-        for (int e = 0; e < OPT; ++e) o[e] = (o[e] + __uint_as_float(r[e])) * corr;
+        for (int e = 0; e < OPT; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * corr);
+        tmem_st_32x32b_x16(lane_addr + COL_O + g * OPT, r);
       }
       // ---- P(t) -> TMEM (bf16 pairs; this thread's 32 keys = 16 columns) ----
       tmem_st_32x32b_x16(lane_addr + COL_P + g * (CPT / 2), pk);
@@ -395,18 +394,18 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       cb::tc_fence_before();
       cb::mbar_arrive(&sm.p_full);
     }
-    // last partial O
-    cb::mbar_wait(&sm.o_full, o_phase);
+    // the accumulated O
+    cb::mbar_wait(&sm.o_full, (nt - 1) & 1);
     cb::tc_fence_after();
+    float o[OPT];
     {
       uint32_t r[OPT];
       tmem_ld_32x32b_x16(lane_addr + COL_O + g * OPT, r);
       cb::tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < OPT; ++e) o[e] += __uint_as_float(r[e]);
+      for (int e = 0; e < OPT; ++e) o[e] = __uint_as_float(r[e]);
     }
     cb::tc_fence_before();
-    cb::mbar_arrive(&sm.o_empty);
     // ---- finalize: the column quarters add their partial sums ----
     sm.xsum[g][li] = l_run;
     named_bar(2 + wq, NWG * 32);
