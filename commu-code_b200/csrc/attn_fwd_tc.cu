@@ -378,8 +378,9 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       }
       l_run = l_run * corr + rsum;
       // ---- rescale O in TMEM where a row of this warp moved its reference point (rare after the first tiles) ----
+      // (PV(t-1) must have completed before P(t) overwrites its operand columns - normally long done)
+      if (t > 0) cb::mbar_wait(&sm.o_full, (t - 1) & 1);
       if (t > 0 && __any_sync(0xffffffffu, raise)) {
-        cb::mbar_wait(&sm.o_full, (t - 1) & 1);          // PV(t-1) has landed
         cb::tc_fence_after();
         uint32_t r[OPT];
         tmem_ld_32x32b_x16(lane_addr + COL_O + g * OPT, r);
