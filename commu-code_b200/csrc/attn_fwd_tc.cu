@@ -68,7 +68,7 @@ struct Smem {
   float xsum[4][TM];  // per-row partial sums (end of kernel)
   uint64_t q_ready;
   uint64_t k_full[2], k_empty[2], v_full, v_empty, r_full[2], r_empty[2];
-  uint64_t s_full[2], s_empty[2], bd_full, bd_empty, p_full, o_full, pst_full, pst_free;
+  uint64_t s_full[2], s_empty[2], bd_full, bd_empty, p_full, o_full, pst_full[4], pst_free[4];
   uint32_t tmem_base;
 };
 
@@ -104,7 +104,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       cb::mbar_init(&sm.s_full[s], 1); cb::mbar_init(&sm.s_empty[s], SOFT);
     }
     cb::mbar_init(&sm.v_full, 1); cb::mbar_init(&sm.v_empty, 1);
-    cb::mbar_init(&sm.pst_full, SOFT); cb::mbar_init(&sm.pst_free, 1);
+    for (int s = 0; s < 4; ++s) { cb::mbar_init(&sm.pst_full[s], NWG * 32); cb::mbar_init(&sm.pst_free[s], 1); }
     cb::mbar_init(&sm.bd_full, 1); cb::mbar_init(&sm.bd_empty, SOFT);
     cb::mbar_init(&sm.p_full, SOFT);
     cb::mbar_init(&sm.o_full, 1);
@@ -214,15 +214,20 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
   } else if (warp == 3) {
     // ============================== P~ store (TMA, shared -> global) ==============================
     if (STORE && cb::elect_one()) {
+      // one 32-row slab per row group (TMEM lane quadrant): the row groups stay independent of each other (a CTA-wide
+      // hand-over would make all 16 softmax warps move in lock-step); 4 x 2 boxes of {64 keys, 32 rows} per tile
       const int row0 = (b * p.H + h) * sa.Tpad + i0;
       for (int t = 0; t < nt; ++t) {
-        cb::mbar_wait(&sm.pst_full, t & 1);
         const int j0 = (jt_first + t) * TN;
-        cb::tma_store_2d(&tm_ps, sm.pst, j0, row0);
-        cb::tma_store_2d(&tm_ps, sm.pst + TILE_BYTES, j0 + 64, row0);
-        cb::tma_store_commit();
-        cb::tma_store_wait_read<0>();
-        cb::mbar_arrive(&sm.pst_free);
+#pragma unroll 1
+        for (int rg = 0; rg < 4; ++rg) {
+          cb::mbar_wait(&sm.pst_full[rg], t & 1);
+          cb::tma_store_2d(&tm_ps, sm.pst + rg * 4096, j0, row0 + 32 * rg);
+          cb::tma_store_2d(&tm_ps, sm.pst + TILE_BYTES + rg * 4096, j0 + 64, row0 + 32 * rg);
+          cb::tma_store_commit();
+          cb::tma_store_wait_read<0>();       // 8 KB: the slab is free again well before the group's next exp phase
+          cb::mbar_arrive(&sm.pst_free[rg]);
+        }
       }
       cb::tma_store_wait<0>();
     }
@@ -345,7 +350,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       uint32_t pk[CPT / 2];
       uint32_t a_pst = 0;
       if (STORE) {
-        if (t > 0) cb::mbar_wait(&sm.pst_free, (t - 1) & 1);      // the previous tile's TMA store has read the staging tile
+        if (t > 0) cb::mbar_wait(&sm.pst_free[wq], (t - 1) & 1);  // the previous tile's TMA store has read this row group's slab
         a_pst = cb::smem_u32(sm.pst) + (g >> 1) * TILE_BYTES + li * 128;
         if (g == 0 && i < p.T) sa.mt[((long long)(b * p.H + h) * sa.nkt + (jt_first + t)) * sa.Tpad + i] = msafe;
       }
@@ -374,7 +379,7 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       }
       if (STORE) {
         cb::fence_proxy_async();
-        cb::mbar_arrive(&sm.pst_full);
+        cb::mbar_arrive(&sm.pst_full[wq]);
       }
       l_run = l_run * corr + rsum;
       // ---- rescale O in TMEM where a row of this warp moved its reference point (rare after the first tiles) ----
@@ -497,7 +502,7 @@ extern "C" int commu_relattn_fwd_tc(const void* q, int64_t ldq, const void* k, c
     int Tpad, Kp, nkt;
     psave_geometry(T, M, &Tpad, &Kp, &nkt);
     sa.mt = mt_save; sa.Tpad = Tpad; sa.nkt = nkt;
-    rc = cb_host::make_tmap_bf16_2d(&tps, p_save, (uint64_t)Kp, (uint64_t)B * H * Tpad, Kp, 64, 128);
+    rc = cb_host::make_tmap_bf16_2d(&tps, p_save, (uint64_t)Kp, (uint64_t)B * H * Tpad, Kp, 64, 32);   // one row group per box
     if (rc) return rc;
   }
   static bool attr = false;
