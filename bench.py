@@ -748,4 +748,10 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries the JSON line(s) only: native libraries that write to fd 1 (NCCL's version banner under torchrun)
+    # are pointed at stderr, Python's own stdout keeps the original descriptor
+    sys.stdout.flush()
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_json_fd, "w")
     main()

@@ -24,6 +24,15 @@ def lr_multiplier(step, warmup_step, lr, lr_min):
 
 
 def _find_nccl():
+    """The libnccl torch has already mapped into this process (so that both talk to ONE NCCL), else the bundled /
+    system copy."""
+    try:
+        with open("/proc/self/maps") as f:
+            for line in f:
+                if "libnccl.so" in line:
+                    return line.split()[-1]
+    except OSError:
+        pass
     for base in (os.path.dirname(torch.__file__) + "/../nvidia/nccl/lib", "/usr/lib/x86_64-linux-gnu"):
         hits = sorted(glob.glob(os.path.join(base, "libnccl.so*")))
         if hits:

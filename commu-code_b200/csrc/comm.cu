@@ -4,9 +4,18 @@
 // Replaces the DDP bucketed all-reduce of the reference (train.py:155, 467-473), which fires once
 // per micro-batch; accumulating locally and reducing once is mathematically identical.
 #include <dlfcn.h>
-#include <nccl.h>
 #include <string.h>
 #include "api_common.h"
+
+// The handful of NCCL types / constants this file needs, declared locally (ABI-stable since NCCL 2.0) so that the
+// library BUILDS without the NCCL development headers; the functions themselves are resolved with dlsym.
+extern "C" {
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclFloat32 = 7 } ncclDataType_t;
+typedef enum { ncclSum = 0 } ncclRedOp_t;
+}
 
 namespace {
 struct NcclApi {
