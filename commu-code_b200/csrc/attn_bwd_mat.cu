@@ -59,6 +59,7 @@ struct MatParams {
   float* du;
   float* dvb;
   float* dr;            // fp32 [kr, H*64]
+  unsigned* sync;       // merged dq_A / dq_C launch: [0] ticket counter, [1 + bh * a_blocks + ab] finished dq_A tiles
 };
 
 // ================================================================================================================
@@ -361,7 +362,23 @@ struct GSmem {
   float csum[4][64];
   uint64_t full[G_STAGES], empty[G_STAGES], acc_full;
   uint32_t tmem_base;
+  uint32_t ticket;
 };
+
+// One CTA's share of a band GEMM.  x / nx / h / b are what blockIdx.x / gridDim.x / blockIdx.y / blockIdx.z are in the
+// one-kernel-per-GEMM launches; the flags carry the dq_A -> dq_C hand-over of the merged launch (below).
+struct BandWork {
+  int x, nx, h, b;
+  const unsigned* wait_flag;   // MODE_C: the fp32 dq_A rows of this CTA are complete once *wait_flag == wait_need
+  unsigned wait_need;
+  unsigned* signal_flag;       // MODE_A: incremented once this CTA's dq_A rows are visible
+};
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* ptr) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ptr) : "memory");
+  return v;
+}
 
 struct Maps8 {
   CUtensorMap m[8];
@@ -371,40 +388,39 @@ struct Maps8 {
 __host__ __device__ inline int a_blocks(int Tpad) { return (Tpad / 8 + 127) / 128; }
 
 template <int MODE>
-__global__ void __launch_bounds__(G_THREADS, 1)
-relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a,    // MODE_A: 2-D dS view, box {64, 8}; else the residue view, box {64,1,128,1}
-                        const __grid_constant__ CUtensorMap tm_a4,   // MODE_A with p.ds4d: 4-D dS view, box {64, 8, 16, 1}
-                        const __grid_constant__ CUtensorMap tm_b,    // MODE_A: K rows3d; MODE_C: Rrev 2-D; MODE_R: unused
-                        const __grid_constant__ Maps8 tm_qv,         // MODE_R: (q+v) rows of residue r, one map per r
-                        const MatParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  GSmem& sm = *reinterpret_cast<GSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+__device__ __forceinline__ void band_body(GSmem& sm,
+                                          const CUtensorMap& tm_a,    // MODE_A: 2-D dS view, box {64, 8}; else the residue view, box {64,1,128,1}
+                                          const CUtensorMap& tm_a4,   // MODE_A with p.ds4d: 4-D dS view, box {64, 8, 16, 1}
+                                          const CUtensorMap& tm_b,    // MODE_A: K rows3d; MODE_C: Rrev 2-D; MODE_R: unused
+                                          const CUtensorMap* tm_qv,   // MODE_R: (q+v) rows of this CTA's residue
+                                          const MatParams& p, const BandWork w) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nab = a_blocks(p.Tpad);
   const int amax = p.Tpad / 8 - 1;
   // ---- work decomposition ----
-  int h = blockIdx.y, b = 0, bh = 0, i0 = 0, r = 0, a0 = 0, c0 = 0;
-  int s_first = 0, nsteps = 0, ab_first = 0;
+  int h = w.h, b = 0, bh = 0, i0 = 0, r = 0, a0 = 0, c0 = 0;
+  int s_first = 0, nsteps = 0, a_first = 0, nper = 0;
   if (MODE == MODE_A) {
-    b = blockIdx.z;
+    b = w.b;
     bh = b * p.H + h;
-    i0 = (gridDim.x - 1 - blockIdx.x) * TM;
+    i0 = (w.nx - 1 - w.x) * TM;
     nsteps = (min(p.T - 1, i0 + TM - 1) + p.M) / TN + 1;          // every causal key tile (masked ones hold zeros)
   } else if (MODE == MODE_C) {
-    b = blockIdx.z;
+    b = w.b;
     bh = b * p.H + h;
-    r = blockIdx.x & 7;
-    a0 = (nab - 1 - (blockIdx.x >> 3)) * 128;
+    r = w.x & 7;
+    a0 = (nab - 1 - (w.x >> 3)) * 128;
     const int lo = p.X - 8 * min(a0 + 127, amax);                 // first column any row of the block uses
     s_first = max(lo, 0) / 128;
     nsteps = (p.X + p.M + 7) / 128 - s_first + 1;                 // ... up to distance 0 of the largest residue
   } else {
-    r = blockIdx.x & 7;
-    c0 = (blockIdx.x >> 3) * 128;
+    r = w.x & 7;
+    c0 = (w.x >> 3) * 128;
     const int t = p.X - c0 - 127;                                  // rows a with X - 8a <= c0 + 127 hold data here
-    const int a_min = t > 0 ? (t + 7) / 8 : 0;
-    ab_first = max(0, a_min - 127) / 128;
-    nsteps = ab_first < nab ? p.B * (nab - ab_first) : 0;
+    a_first = t > 0 ? (t + 7) / 8 : 0;                            // first row a (NOT a block index): the sweep starts
+    const int rows = p.Tpad / 8;                                   // there, rows past the end are TMA zero fill (no traffic)
+    nper = a_first < rows ? (rows - a_first + 127) / 128 : 0;
+    nsteps = p.B * nper;
   }
 
   if (threadIdx.x == 0) {
@@ -448,13 +464,12 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a,    // MODE_A: 
           cb::tma_load_4d(sm.a[st] + TILE16, &tm_a, &sm.full[st], cc + 64, r, a0, bh);
           cb::tma_load_2d(sm.b[st], &tm_b, &sm.full[st], h * DH, cc + 8 - r);
         } else {
-          const int nper = nab - ab_first;
           const int bb = s / nper;
-          const int aa = (ab_first + s % nper) * 128;
+          const int aa = a_first + (s % nper) * 128;
           const int bhh = bb * p.H + h;
           cb::tma_load_4d(sm.a[st], &tm_a, &sm.full[st], c0, r, aa, bhh);
           cb::tma_load_4d(sm.a[st] + TILE16, &tm_a, &sm.full[st], c0 + 64, r, aa, bhh);
-          cb::tma_load_3d(sm.b[st], &tm_qv.m[r], &sm.full[st], h * DH, bb, aa);
+          cb::tma_load_3d(sm.b[st], tm_qv, &sm.full[st], h * DH, bb, aa);
         }
       }
     }
@@ -517,6 +532,11 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a,    // MODE_A: 
       }
     } else {
       const int i = MODE == MODE_A ? i0 + li : 8 * (a0 + li) + r;
+      if (MODE == MODE_C && w.wait_flag) {   // merged launch: the dq_A tiles of these rows come from CTAs that started earlier
+        if (threadIdx.x == 64)
+          while (ld_acquire_gpu(w.wait_flag) < w.wait_need) __nanosleep(64);
+        named_bar(1, 128);
+      }
       if (i < p.T) {
         float* da = p.da + ((long long)i * p.B + b) * (p.H * DH) + h * DH;
         if (MODE == MODE_A) {
@@ -526,8 +546,8 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a,    // MODE_A: 
           bf16* dq = p.dq + ((long long)i * p.B + b) * p.lddq + h * DH;
 #pragma unroll
           for (int e = 0; e < 64; e += 8) {
-            const float4 x = *reinterpret_cast<const float4*>(da + e);
-            const float4 y = *reinterpret_cast<const float4*>(da + e + 4);
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(da + e));       // (written by another CTA of this launch
+            const float4 y = __ldcg(reinterpret_cast<const float4*>(da + e + 4));   //  in the merged form: never through L1)
             uint4 o;
             o.x = cb::pack_bf16(acc[e] + x.x, acc[e + 1] + x.y);
             o.y = cb::pack_bf16(acc[e + 2] + x.z, acc[e + 3] + x.w);
@@ -537,6 +557,7 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a,    // MODE_A: 
           }
         }
       }
+      if (MODE == MODE_A && w.signal_flag) __threadfence();
       // column sums: d r_w_bias (MODE_A) / d r_r_bias (MODE_C); rows >= T hold exact zeros
 #pragma unroll
       for (int e = 0; e < 64; ++e) {
@@ -549,6 +570,7 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a,    // MODE_A: 
         const float sa = (sm.csum[0][t] + sm.csum[1][t]) + (sm.csum[2][t] + sm.csum[3][t]);
         atomicAdd((MODE == MODE_A ? p.du : p.dvb) + h * DH + t, sa);
       }
+      if (MODE == MODE_A && w.signal_flag && t == 64) atomicAdd(w.signal_flag, 1u);   // (after the bar: every row is fenced)
     }
   }
   cb::tc_fence_before();
@@ -559,10 +581,67 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a,    // MODE_A: 
   }
 }
 
+template <int MODE>
+__global__ void __launch_bounds__(G_THREADS, 1)
+relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a4,
+                        const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ Maps8 tm_qv,
+                        const MatParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  GSmem& sm = *reinterpret_cast<GSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const BandWork w = {(int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y, (int)blockIdx.z, nullptr, 0u, nullptr};
+  band_body<MODE>(sm, tm_a, tm_a4, tm_b, MODE == MODE_R ? &tm_qv.m[blockIdx.x & 7] : nullptr, p, w);
+}
+
+// dq_A and dq_C in ONE launch, ordered so that the two views of the same dS rows are read back to back: both GEMMs
+// stream the whole workspace (1.6 GB per layer at the benchmark shape), and as separate launches each streams it from
+// HBM.  Here a CTA takes a ticket and derives its tile from it: per (b,h), per block of 1024 query rows (from the last
+// block down, heaviest first), the <= 8 key-indexed row tiles (dq_A) and then the 8 residue classes of the same rows
+// (dq_C) - the second view finds the rows in L2.  The ticket (not blockIdx) fixes the order, so the one dependency -
+// dq_C adds the fp32 dq_A rows and writes the bf16 result - only ever waits on CTAs that already run.
+__global__ void __launch_bounds__(G_THREADS, 1)
+relattn_bwd_band_ac_kernel(const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_a4,
+                           const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_k,
+                           const __grid_constant__ CUtensorMap tm_rr, const MatParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  GSmem& sm = *reinterpret_cast<GSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (threadIdx.x == 0) sm.ticket = atomicAdd(p.sync, 1u);
+  __syncthreads();
+  const int nab = a_blocks(p.Tpad);
+  const int nta = p.Tpad / TM;
+  const int per_bh = nta + 8 * nab;
+  const int bh = (int)(sm.ticket / (unsigned)per_bh);
+  int u = (int)(sm.ticket % (unsigned)per_bh);
+  int ab = nab - 1, na = 0;
+  bool is_a = false;
+  for (; ab >= 0; --ab) {
+    na = min(8, nta - 8 * ab);
+    if (u < na) { is_a = true; break; }
+    u -= na;
+    if (u < 8) break;
+    u -= 8;
+  }
+  unsigned* flag = p.sync + 1 + bh * nab + ab;
+  BandWork w;
+  w.h = bh % p.H;
+  w.b = bh / p.H;
+  if (is_a) {
+    w.x = nta - 1 - (8 * ab + na - 1 - u);      // row tile 8ab + na-1-u, in band_body's reversed numbering
+    w.nx = nta;
+    w.wait_flag = nullptr; w.wait_need = 0u; w.signal_flag = flag;
+    band_body<MODE_A>(sm, tm_a2, tm_a4, tm_k, nullptr, p, w);
+  } else {
+    w.x = (nab - 1 - ab) * 8 + u;               // residue u of row block ab
+    w.nx = nab * 8;
+    w.wait_flag = flag; w.wait_need = (unsigned)na; w.signal_flag = nullptr;
+    band_body<MODE_C>(sm, tm_res, tm_a4, tm_rr, nullptr, p, w);
+  }
+}
+
 // Rrev[y, :] = R[Y0 - y, :] (zero outside [0, kr)), 16 bytes per thread
 __global__ void rrev_kernel(const bf16* __restrict__ r, long long ldr, int kr, int Y0, int rows, int cols8,
-                            bf16* __restrict__ out) {
+                            bf16* __restrict__ out, unsigned* __restrict__ sync, int nsync) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long j = idx; j < nsync; j += (long long)gridDim.x * blockDim.x) sync[j] = 0u;   // ticket + hand-over flags
   if (idx >= (long long)rows * cols8) return;
   const int y = (int)(idx / cols8), c = (int)(idx % cols8);
   const int d = Y0 - y;
@@ -598,7 +677,8 @@ int make_tmap(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims,
 
 struct Geo {
   int Tpad, Kp, P, X, nkt, Y0, rrev_rows;
-  int64_t ds_bytes, rrev_bytes, da_bytes, p_bytes, mt_bytes;
+  int64_t ds_bytes, rrev_bytes, da_bytes, sync_bytes, p_bytes, mt_bytes;
+  int nsync;
 };
 Geo geometry(int T, int M, int B, int H) {
   Geo g;
@@ -612,6 +692,8 @@ Geo geometry(int T, int M, int B, int H) {
   g.ds_bytes = (int64_t)B * H * g.Tpad * g.P * 2;
   g.rrev_bytes = ((int64_t)g.rrev_rows * H * 64 * 2 + 1023) / 1024 * 1024;
   g.da_bytes = ((int64_t)T * B * H * 64 * 4 + 1023) / 1024 * 1024;
+  g.nsync = 1 + B * H * a_blocks(g.Tpad);
+  g.sync_bytes = ((int64_t)g.nsync * 4 + 1023) / 1024 * 1024;
   g.p_bytes = (int64_t)B * H * g.Tpad * g.Kp * 2;
   g.mt_bytes = (int64_t)B * H * g.nkt * g.Tpad * 4;
   return g;
@@ -638,7 +720,7 @@ extern "C" int commu_relattn_bwd_sizes(int T, int M, int B, int H, int64_t* p_by
   const Geo g = geometry(T, M, B, H);
   if (p_bytes) *p_bytes = g.p_bytes;
   if (mt_bytes) *mt_bytes = g.mt_bytes;
-  if (ws_bytes) *ws_bytes = g.ds_bytes + g.rrev_bytes + g.da_bytes;
+  if (ws_bytes) *ws_bytes = g.ds_bytes + g.rrev_bytes + g.da_bytes + g.sync_bytes;
   if (ws_zero_bytes) *ws_zero_bytes = g.ds_bytes;
   return 0;
 }
@@ -658,12 +740,13 @@ extern "C" int commu_relattn_bwd_mat(const void* qu, const void* qv, int64_t ldq
   CB_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldr % 8 == 0 && lddo % 8 == 0 && lddq % 8 == 0 && lddkv % 8 == 0,
              "relattn_bwd_mat: leading dims must be multiples of 8");
   const Geo g = geometry(T, M, B, H);
-  CB_REQUIRE(ws_bytes >= g.ds_bytes + g.rrev_bytes + g.da_bytes, "relattn_bwd_mat: workspace too small (%lld < %lld)",
-             (long long)ws_bytes, (long long)(g.ds_bytes + g.rrev_bytes + g.da_bytes));
+  const int64_t ws_need = g.ds_bytes + g.rrev_bytes + g.da_bytes + g.sync_bytes;
+  CB_REQUIRE(ws_bytes >= ws_need, "relattn_bwd_mat: workspace too small (%lld < %lld)", (long long)ws_bytes, (long long)ws_need);
   CB_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 127) == 0, "relattn_bwd_mat: workspace must be 128-byte aligned");
   bf16* ds = (bf16*)ws;
   bf16* rrev = (bf16*)((uint8_t*)ws + g.ds_bytes);
   float* da = (float*)((uint8_t*)ws + g.ds_bytes + g.rrev_bytes);
+  unsigned* sync = (unsigned*)((uint8_t*)ws + g.ds_bytes + g.rrev_bytes + g.da_bytes);
   const int Ktot = T + M;
   const int BH = B * H;
 
@@ -672,7 +755,7 @@ extern "C" int commu_relattn_bwd_mat(const void* qu, const void* qv, int64_t ldq
   p.same_length = same_length; p.shift = shift; p.reset = reset; p.scale = scale;
   p.lse = lse; p.delta = delta; p.mt = mt_save;
   p.dk = (bf16*)dk; p.dv = (bf16*)dv; p.lddkv = lddkv;
-  p.da = da; p.dq = (bf16*)dq; p.lddq = lddq; p.du = du; p.dvb = dvb; p.dr = dr;
+  p.da = da; p.sync = sync; p.dq = (bf16*)dq; p.lddq = lddq; p.du = du; p.dvb = dvb; p.dr = dr;
   const DropState dst = drop_state();
   const uint32_t thr = dst.p > 0.f ? drop::thr15_of(dst.p) : 0u;
   p.drop_keep = 1.f - (float)thr / 32768.f;
@@ -738,12 +821,13 @@ extern "C" int commu_relattn_bwd_mat(const void* qu, const void* qv, int64_t ldq
     CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_band_kernel<MODE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem));
     CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_band_kernel<MODE_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem));
     CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_band_kernel<MODE_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(relattn_bwd_band_ac_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_smem));
     attr = true;
   }
   {
     const int cols8 = H * 8;
     const long long n = (long long)g.rrev_rows * cols8;
-    rrev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const bf16*)r, ldr, kr, g.Y0, g.rrev_rows, cols8, rrev);
+    rrev_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const bf16*)r, ldr, kr, g.Y0, g.rrev_rows, cols8, rrev, sync, g.nsync);
   }
   {
     dim3 grid(cb_host::ceil_div(Ktot, TN), H, B);
@@ -751,11 +835,20 @@ extern "C" int commu_relattn_bwd_mat(const void* qu, const void* qv, int64_t ldq
     else relattn_bwd_p1_kernel<false><<<grid, P1_THREADS, p1_smem, stream>>>(tv, tqu, tdo, tp, tds2, tds4, p);
   }
   const int nab = a_blocks(g.Tpad);
-  relattn_bwd_band_kernel<MODE_A><<<dim3(cb_host::ceil_div(T, TM), H, B), G_THREADS, g_smem, stream>>>(tds2, tds4, tk, tqv, p);
-  relattn_bwd_band_kernel<MODE_C><<<dim3(nab * 8, H, B), G_THREADS, g_smem, stream>>>(tdsg, tds4, trr, tqv, p);
+  static int merge = -1;          // COMMU_ATTN_BAND_MERGE=0: dq_A and dq_C as two launches (each streams dS from HBM)
+  if (merge < 0) {
+    const char* e = getenv("COMMU_ATTN_BAND_MERGE");
+    merge = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (merge) {
+    relattn_bwd_band_ac_kernel<<<dim3((unsigned)(BH * (g.Tpad / TM + 8 * nab))), G_THREADS, g_smem, stream>>>(tds2, tds4, tdsg, tk, trr, p);
+  } else {
+    relattn_bwd_band_kernel<MODE_A><<<dim3(cb_host::ceil_div(T, TM), H, B), G_THREADS, g_smem, stream>>>(tds2, tds4, tk, tqv, p);
+    relattn_bwd_band_kernel<MODE_C><<<dim3(nab * 8, H, B), G_THREADS, g_smem, stream>>>(tdsg, tds4, trr, tqv, p);
+  }
   const int ncb = (g.X + M + 7) / 128 + 1;
   relattn_bwd_band_kernel<MODE_R><<<dim3(ncb * 8, H, 1), G_THREADS, g_smem, stream>>>(tdsg, tds4, trr, tqv, p);
-  cb_host::count_launch(5);
+  cb_host::count_launch(merge ? 4 : 5);
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

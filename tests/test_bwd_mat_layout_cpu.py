@@ -115,11 +115,12 @@ def test_coarse_sheared_layout_and_band_gemms(T, M):
         c0 = cb * 128
         for r in range(8):
             t = X - c0 - 127
-            a_min = (t + 7) // 8 if t > 0 else 0
-            ab_first = max(0, a_min - 127) // 128
+            a_first = (t + 7) // 8 if t > 0 else 0         # the sweep starts at the first ROW that holds data here;
+            rows = Tpad // 8                                # rows past the end are TMA zero fill (a_tile / ct below)
+            nper = (rows - a_first + 127) // 128 if a_first < rows else 0
             acc = np.zeros((128, D))
-            for ab in range(ab_first, nab):
-                a0 = ab * 128
+            for st in range(nper):
+                a0 = a_first + st * 128
                 ct = np.zeros((128, D))                     # (q+v) rows 8(a0+k)+r, zero beyond T
                 for k in range(128):
                     i = 8 * (a0 + k) + r
