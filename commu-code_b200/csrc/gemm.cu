@@ -47,6 +47,7 @@ struct GemmKernelParams {
   int vec_ok;  // all leading dims / bases allow 16-byte vector stores
   uint32_t drop_thr2, drop_ka, drop_kb;   // drop_thr2 != 0: inverted dropout of the result (counter-based mask)
   float drop_inv;
+  int dbg;   // COMMU_GEMM_EPI_DEBUG (measurement only): 1 = no global stores on the bf16 path, 2 = no epilogue work at all
 };
 
 template <int BLOCK_N>
@@ -195,7 +196,7 @@ __device__ __forceinline__ void epilogue_store(const GemmKernelParams& p, const 
           if (!(cb::bf16_hi(w[j]) > 0.f)) qq[j] &= 0x0000FFFFu;
         }
       }
-      if (row0 + rr < p.M)
+      if (row0 + rr < p.M && !(p.dbg & 1))
         *reinterpret_cast<uint4*>(p.out_bf16 + (long long)(row0 + rr) * p.ld_out_bf16 + n0 + tc * 8) = q;
     }
     return;
@@ -234,7 +235,198 @@ __device__ __forceinline__ void epilogue_store(const GemmKernelParams& p, const 
   }
 }
 
-template <int BLOCK_N, bool DROP>
+
+// ---------------------------------------------------------------------------------------------------------------
+// Whole-tile epilogues of one warp for FULL tiles (its 32 rows < M, its CH*32 columns < N, vector-aligned buffers).
+// The general routine above re-derives every option, bound and 64-bit address per 32-column chunk: ~560 instructions
+// per chunk and warp, 18 k per 128 x 256 tile - more issue slots than the tile's MMAs take (K = 512: the GEMMs ran at
+// half the speed they reach with the epilogue switched off).  Here the options are hoisted per tile, the pointers
+// advance by constants, shared memory is addressed in its own window and the ReLU mask is applied on packed pairs.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// keep mask (0xFFFF per half) of a packed pair of saved activations: positive <=> sign clear and magnitude non-zero
+__device__ __forceinline__ uint32_t positive16x2(uint32_t w) {
+  return drop::mask16x2(((w & 0x7FFF7FFFu) + 0x7FFF7FFFu) & ~w);
+}
+
+// v = alpha * acc (+ bias) (relu) (dropout): the part of the epilogue that runs with a row per lane, NV columns from n0
+template <bool DROP, int NV>
+__device__ __forceinline__ void epilogue_rowmath(const GemmKernelParams& p, const uint32_t (&r)[NV], float (&v)[NV],
+                                                 bool scale, bool has_bias, bool relu, uint32_t st_bias, int n0,
+                                                 const drop::Keys& dk) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = __uint_as_float(r[i]);
+  if (scale) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] *= p.alpha;
+  }
+  if (has_bias) {
+#pragma unroll
+    for (int i = 0; i < NV / 4; ++i) {
+      const uint4 bq = lds128(st_bias + i * 16);
+      v[i * 4 + 0] += __uint_as_float(bq.x); v[i * 4 + 1] += __uint_as_float(bq.y);
+      v[i * 4 + 2] += __uint_as_float(bq.z); v[i * 4 + 3] += __uint_as_float(bq.w);
+    }
+  }
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (DROP) {   // same (seed, row, column) -> keep function as dropout.cu
+#pragma unroll
+    for (int c4 = 0; c4 < NV / 4; ++c4) {
+      const uint2 rnd = drop::rand64((uint32_t)((n0 >> 2) + c4), dk);
+      const uint32_t f0 = drop::keep_flags(rnd.x, p.drop_thr2), f1 = drop::keep_flags(rnd.y, p.drop_thr2);
+      v[c4 * 4 + 0] = (f0 & 0x8000u) ? v[c4 * 4 + 0] * p.drop_inv : 0.f;
+      v[c4 * 4 + 1] = (f0 & 0x80000000u) ? v[c4 * 4 + 1] * p.drop_inv : 0.f;
+      v[c4 * 4 + 2] = (f1 & 0x8000u) ? v[c4 * 4 + 2] * p.drop_inv : 0.f;
+      v[c4 * 4 + 3] = (f1 & 0x80000000u) ? v[c4 * 4 + 3] * p.drop_inv : 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+
+// bf16 result only (optional ReLU mask of a saved activation)
+template <bool DROP, int CH>
+__device__ __forceinline__ void epilogue_fast_bf16(const GemmKernelParams& p, uint32_t taddr, int row0, int nbase,
+                                                   int lane, unsigned char* stage) {
+  const int tr = lane >> 2, tc = lane & 3;   // transposed role: rows tr + 8 i, 16-byte chunk tc of a staged row
+  const uint32_t st = cb::smem_u32(stage);
+  const uint32_t st_mine = st + lane * EPI_PITCH, st_tr = st + tr * EPI_PITCH + tc * 16, st_bias = st + EPI_STAGE_BYTES;
+  bf16* optr = p.out_bf16 + (long long)(row0 + tr) * p.ld_out_bf16 + nbase + tc * 8;
+  const long long ostep = 8 * p.ld_out_bf16;
+  const bf16* mptr = p.relu_mask ? p.relu_mask + (long long)(row0 + tr) * p.ld_mask + nbase + tc * 8 : nullptr;
+  const long long mstep = 8 * p.ld_mask;
+  const bool scale = p.alpha != 1.f, has_bias = p.bias != nullptr, relu = p.relu != 0;
+  const drop::Keys dk = drop::row_keys(p.drop_ka, p.drop_kb, (uint32_t)(row0 + lane));
+  uint32_t r[2][32];
+  cb::tmem_ld_32x32b_x32(taddr, r[0]);
+  uint4 mk[2][4];                      // the saved activation of the NEXT chunk is in flight while one is processed
+  auto load_mask = [&](int c) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mk[c & 1][i] = __ldg(reinterpret_cast<const uint4*>(mptr + i * mstep + c * 32));
+  };
+  if (mptr) load_mask(0);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if (mptr && c + 1 < CH) load_mask(c + 1);
+    cb::tmem_ld_wait();
+    if (c + 1 < CH) cb::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+    float v[32];
+    epilogue_rowmath<DROP, 32>(p, r[c & 1], v, scale, has_bias, relu, st_bias + c * 128, nbase + c * 32, dk);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      sts128(st_mine + q * 16, cb::pack_bf16(v[q * 8 + 0], v[q * 8 + 1]), cb::pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+             cb::pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), cb::pack_bf16(v[q * 8 + 6], v[q * 8 + 7]));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {      // every store instruction writes 8 rows x 64 contiguous bytes
+      uint4 q = lds128(st_tr + i * 8 * EPI_PITCH);
+      if (mptr) {
+        q.x &= positive16x2(mk[c & 1][i].x); q.y &= positive16x2(mk[c & 1][i].y);
+        q.z &= positive16x2(mk[c & 1][i].z); q.w &= positive16x2(mk[c & 1][i].w);
+      }
+      if (!(p.dbg & 1)) *reinterpret_cast<uint4*>(optr + i * ostep + c * 32) = q;
+    }
+  }
+}
+
+// fp32 result (+ fp32 addend, which may be the output itself), stored or - split-K - atomically accumulated
+template <bool DROP, int CH>
+__device__ __forceinline__ void epilogue_fast_f32(const GemmKernelParams& p, uint32_t taddr, int row0, int nbase,
+                                                  int lane, unsigned char* stage) {
+  const int tr = lane >> 2, tc = lane & 3;
+  const uint32_t st = cb::smem_u32(stage);
+  const uint32_t st_mine = st + lane * EPI_PITCH, st_tr = st + tr * EPI_PITCH + tc * 16, st_bias = st + EPI_STAGE_BYTES;
+  float* optr = p.out_f32 + (long long)(row0 + tr) * p.ld_out_f32 + nbase + tc * 4;
+  const long long ostep = 8 * p.ld_out_f32;
+  const float* aptr = p.add_f32 ? p.add_f32 + (long long)(row0 + tr) * p.ld_add + nbase + tc * 4 : nullptr;
+  const long long astep = 8 * p.ld_add;
+  const bool scale = p.alpha != 1.f, has_bias = p.bias != nullptr, relu = p.relu != 0, atomic = p.f32_atomic != 0;
+  const drop::Keys dk = drop::row_keys(p.drop_ka, p.drop_kb, (uint32_t)(row0 + lane));
+  // the addend of the NEXT 32-column chunk is in flight while one chunk is processed (HBM latency; the TMEM load is
+  // short and is simply waited for: double-buffering both does not fit the register file)
+  float4 ad[2][2][4];
+  auto load_addend = [&](int c) {
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        ad[c & 1][hf][i] = __ldg(reinterpret_cast<const float4*>(aptr + i * astep + c * 32 + hf * 16));
+  };
+  if (aptr) load_addend(0);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    if (aptr && c + 1 < CH) load_addend(c + 1);
+    uint32_t r[32];
+    cb::tmem_ld_32x32b_x32(taddr + c * 32, r);
+    cb::tmem_ld_wait();
+    float v[32];
+    epilogue_rowmath<DROP, 32>(p, r, v, scale, has_bias, relu, st_bias + c * 128, nbase + c * 32, dk);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {   // two halves of 16 columns (64 B per row) through the staging tile
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        sts128(st_mine + q * 16, __float_as_uint(v[hf * 16 + q * 4]), __float_as_uint(v[hf * 16 + q * 4 + 1]),
+               __float_as_uint(v[hf * 16 + q * 4 + 2]), __float_as_uint(v[hf * 16 + q * 4 + 3]));
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {    // every store instruction writes 8 rows x 64 contiguous bytes
+        const uint4 w = lds128(st_tr + i * 8 * EPI_PITCH);
+        float4 q = make_float4(__uint_as_float(w.x), __uint_as_float(w.y), __uint_as_float(w.z), __uint_as_float(w.w));
+        if (aptr) {
+          const float4 x = ad[c & 1][hf][i];
+          q.x += x.x; q.y += x.y; q.z += x.z; q.w += x.w;
+        }
+        float* o = optr + i * ostep + c * 32 + hf * 16;
+        if (atomic) cb::red_add_v4(o, q.x, q.y, q.z, q.w);     // split-K partial sums
+        else *reinterpret_cast<float4*>(o) = q;
+      }
+    }
+  }
+}
+
+// One warp's share of a finished accumulator tile: 32 rows (row0 ..) x CH*32 columns (nbase ..) at TMEM address taddr.
+// FAST is chosen by the host (fast_epilogue_ok): every tile full, buffers vector-aligned, one of the two whole-tile
+// epilogues applies.  The general routine lives in the other instantiation only - next to the fast paths (inlined or
+// called) it made the register allocator spill in all of them.
+template <bool DROP, int CH, bool FAST>
+__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, uint32_t taddr, int row0, int nbase, int lane,
+                                              unsigned char* stage) {
+  if (p.dbg & 2) return;
+  if constexpr (FAST) {
+    if (p.out_bf16) epilogue_fast_bf16<DROP, CH>(p, taddr, row0, nbase, lane, stage);
+    else epilogue_fast_f32<DROP, CH>(p, taddr, row0, nbase, lane, stage);
+  } else {
+    uint32_t r[2][32];
+    cb::tmem_ld_32x32b_x32(taddr, r[0]);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      cb::tmem_ld_wait();
+      if (c + 1 < CH) cb::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
+      const int n0 = nbase + c * 32;
+      if (n0 < p.N) epilogue_store<DROP>(p, r[c & 1], row0, lane, n0, c, stage);
+    }
+  }
+}
+
+template <int BLOCK_N, bool DROP, bool FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmKernelParams p) {
@@ -385,15 +577,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int row = m_blk * BLOCK_M + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + half * (CH * 32);
       const int nbase = n_blk * BLOCK_N + half * (CH * 32);
-      uint32_t r[2][32];
-      cb::tmem_ld_32x32b_x32(taddr, r[0]);
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        cb::tmem_ld_wait();
-        if (c + 1 < CH) cb::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
-        const int n0 = nbase + c * 32;
-        if (n0 < p.N) epilogue_store<DROP>(p, r[c & 1], row - lane, lane, n0, c, epi_stage);
-      }
+      epilogue_tile<DROP, CH, FAST>(p, taddr, row - lane, nbase, lane, epi_stage);
       cb::tc_fence_before();
       cb::mbar_arrive(&tmem_empty[buf]);
       buf ^= 1;
@@ -471,7 +655,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cluster_addr) : "memory");
 }
 
-template <bool DROP>
+template <bool DROP, bool FAST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmKernelParams p) {
@@ -624,15 +808,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int row = m_blk * 2 * BLOCK_M + (int)rank * BLOCK_M + q * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BLOCK_N + half * (CH * 32);
       const int nbase = n_blk * BLOCK_N + half * (CH * 32);
-      uint32_t r[2][32];
-      cb::tmem_ld_32x32b_x32(taddr, r[0]);
-#pragma unroll
-      for (int c = 0; c < CH; ++c) {
-        cb::tmem_ld_wait();
-        if (c + 1 < CH) cb::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, r[(c + 1) & 1]);
-        const int n0 = nbase + c * 32;
-        if (n0 < p.N) epilogue_store<DROP>(p, r[c & 1], row - lane, lane, n0, c, epi_stage);
-      }
+      epilogue_tile<DROP, CH, FAST>(p, taddr, row - lane, nbase, lane, epi_stage);
       cb::tc_fence_before();
       mbar_arrive_cluster(mapa_rank(cb::smem_u32(&tmem_empty[buf]), 0));
       buf ^= 1;
@@ -723,7 +899,7 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_
 }
 }  // namespace cb_host
 
-template <int BLOCK_N, bool DROP>
+template <int BLOCK_N, bool DROP, bool FAST>
 static int launch_tc(const commu_gemm_args* a, const GemmKernelParams& p, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
   CUtensorMap ta, tb;
@@ -740,7 +916,7 @@ static int launch_tc(const commu_gemm_args* a, const GemmKernelParams& p, cudaSt
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, DROP>,
+    CB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, DROP, FAST>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
@@ -748,13 +924,13 @@ static int launch_tc(const commu_gemm_args* a, const GemmKernelParams& p, cudaSt
   const int items = m_tiles * n_tiles * p.split_k;
   const int grid = items < cb_host::num_sms() ? items : cb_host::num_sms();
   cb_host::ProfScope prof(cb_host::PROF_GEMM, stream);
-  gemm_tcgen05_kernel<BLOCK_N, DROP><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_tcgen05_kernel<BLOCK_N, DROP, FAST><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   cb_host::count_launch();
   CB_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-template <bool DROP>
+template <bool DROP, bool FAST>
 static int launch_tc_2cta(const commu_gemm_args* a, const GemmKernelParams& p, cudaStream_t stream) {
   using C = Cfg2;
   CUtensorMap ta, tb;
@@ -771,7 +947,7 @@ static int launch_tc_2cta(const commu_gemm_args* a, const GemmKernelParams& p, c
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    CB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<DROP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    CB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<DROP, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int m_pairs = cb_host::ceil_div(a->m, 2 * BLOCK_M), n_tiles = cb_host::ceil_div(a->n, C::BLOCK_N);
@@ -791,7 +967,7 @@ static int launch_tc_2cta(const commu_gemm_args* a, const GemmKernelParams& p, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<DROP>, ta, tb, p));
+  CB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tcgen05_2cta_kernel<DROP, FAST>, ta, tb, p));
   cb_host::count_launch();
   return 0;
 }
@@ -840,6 +1016,10 @@ extern "C" int commu_gemm_bf16(const commu_gemm_args* a, void* stream_) {
   }
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vec_ok = 1;
+  {
+    static const int dbg = []() { const char* e = getenv("COMMU_GEMM_EPI_DEBUG"); return e ? atoi(e) : 0; }();
+    p.dbg = dbg;
+  }
   if (p.out_bf16 && (!al16(p.out_bf16) || (p.ld_out_bf16 % 8))) p.vec_ok = 0;
   if (p.out_f32 && (!al16(p.out_f32) || (p.ld_out_f32 % 4))) p.vec_ok = 0;
   if (p.relu_mask && (!al16(p.relu_mask) || (p.ld_mask % 8))) p.vec_ok = 0;
@@ -864,8 +1044,20 @@ extern "C" int commu_gemm_bf16(const commu_gemm_args* a, void* stream_) {
   }();
   // (measured: +10-12 % where a split's reduction length is >= 1024, no gain on the epilogue-paced K = 512 shapes)
   const int k_per_split = a->k / split;
-  if (a->impl == 2 || (a->impl == 0 && use_2cta && a->n > 128 && a->m > BLOCK_M && k_per_split >= 1024))
-    return p.drop_thr2 ? launch_tc_2cta<true>(a, p, stream) : launch_tc_2cta<false>(a, p, stream);
-  if (a->n > 128) return p.drop_thr2 ? launch_tc<256, true>(a, p, stream) : launch_tc<256, false>(a, p, stream);
-  return p.drop_thr2 ? launch_tc<128, true>(a, p, stream) : launch_tc<128, false>(a, p, stream);
+  const bool pair = a->impl == 2 || (a->impl == 0 && use_2cta && a->n > 128 && a->m > BLOCK_M && k_per_split >= 1024);
+  const int block_n = (pair || a->n > 128) ? 256 : 128;
+  // whole-tile epilogues: every tile full, vector-aligned buffers, bf16-only result (optional ReLU mask) or fp32-only
+  // result (optional addend / atomic accumulation)
+  static const int fast_on = []() { const char* e = getenv("COMMU_GEMM_FAST_EPI"); return (e && e[0] == '0') ? 0 : 1; }();
+  const bool path_a = p.out_bf16 && !p.add_f32 && !p.out_f32;
+  const bool path_f = p.out_f32 && !p.out_bf16 && !p.relu_mask;
+  const bool fast = fast_on && p.vec_ok && (a->m % (pair ? 2 * BLOCK_M : BLOCK_M) == 0) && (a->n % block_n == 0) && (path_a || path_f);
+  const bool drop = p.drop_thr2 != 0;
+#define COMMU_GEMM_DISPATCH(FN, ...)                                                        \
+  (drop ? (fast ? FN<__VA_ARGS__ true, true>(a, p, stream) : FN<__VA_ARGS__ true, false>(a, p, stream)) \
+        : (fast ? FN<__VA_ARGS__ false, true>(a, p, stream) : FN<__VA_ARGS__ false, false>(a, p, stream)))
+  if (pair) return COMMU_GEMM_DISPATCH(launch_tc_2cta, );
+  if (block_n == 256) return COMMU_GEMM_DISPATCH(launch_tc, 256, );
+  return COMMU_GEMM_DISPATCH(launch_tc, 128, );
+#undef COMMU_GEMM_DISPATCH
 }
