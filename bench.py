@@ -266,14 +266,15 @@ def run_native(args):
                                       "+ the three band GEMMs (dq_A, dq_C, dR)",
                           "attn_fwd": "one layer's attention forward"}
             if dom == "attn_bwd":
-                # the materialised backward is HBM-bound by design: algorithmic traffic = P~ read + dS written once + dS
-                # read by the three band GEMMs = 10 bytes per causal-visible score element
+                # the materialised backward is HBM-bound by design: algorithmic HBM traffic = P~ read + dS written once +
+                # dS read back twice (by the merged dq_A / dq_C launch, whose second view of the rows is served from L2,
+                # and by the dR GEMM) = 8 bytes per causal-visible score element
                 elts = B * CFG["n_head"] * (T * CFG["mem_len"] + T * (T + 1) / 2)
-                hb = 10.0 * elts
+                hb = 8.0 * elts
                 roof = dict(kernel=dom, bound="hbm", achieved=round(hb / dur / 1e9, 1), peak=pk["hbm"], unit="GB/s",
                             frac=round(hb / dur / 1e9 / pk["hbm"], 4), traffic=traf,
                             peak_source=pk["source"].replace("sustained", "copy bandwidth"),
-                            bytes_per_launch=int(hb), bytes_per_unit="10 B per causal-visible score element",
+                            bytes_per_launch=int(hb), bytes_per_unit="8 B per causal-visible score element (bf16 P~ read, bf16 dS written, dS read twice)",
                             avg_launch_ms=round(dur * 1e3, 4), launch_unit=unit_names[dom], tensor_view=tens)
             else:
                 roof = dict(kernel=dom, bound="tensor", traffic=traf, peak_source=pk["source"],

@@ -48,7 +48,7 @@ constexpr int SOFT = 128 * NWG;           // softmax threads
 constexpr int NTHREADS = 128 + SOFT;      // 4 control warps + NWG softmax warpgroups
 constexpr int CPT = TN / NWG;             // key columns per softmax thread
 constexpr int OPT = DH / NWG;             // output dims per softmax thread
-constexpr int STAGE_ROW = 528;            // bytes per staged fp16 BD row: [block half 0 | half 1] + 16 pad
+constexpr int STAGE_ROW = 592;            // bytes per staged fp16 BD row: [half 0 | half 1 | first 64 B of half 0 again] + 16 pad
 constexpr int TILE_BYTES = TN * DH * 2;   // 16 KB
 // TMEM columns
 constexpr int COL_S = 0;      // 2 x 128
@@ -278,12 +278,17 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
       cb::mbar_arrive(&sm.bd_empty);
       bd_phase ^= 1;
       const uint32_t dst = my_row + half * 256 + g * 64;
+      uint32_t pk[16];
 #pragma unroll
-      for (int e = 0; e < 32; e += 8)
-        sts_v4(dst + e * 2, pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1])),
-               pack_f16(__uint_as_float(r0[e + 2]), __uint_as_float(r0[e + 3])),
-               pack_f16(__uint_as_float(r0[e + 4]), __uint_as_float(r0[e + 5])),
-               pack_f16(__uint_as_float(r0[e + 6]), __uint_as_float(r0[e + 7])));
+      for (int e = 0; e < 32; e += 2) pk[e / 2] = pack_f16(__uint_as_float(r0[e]), __uint_as_float(r0[e + 1]));
+#pragma unroll
+      for (int c = 0; c < 4; ++c) sts_v4(dst + 16 * c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      // the band a tile reads is [lo block | hi block]: contiguous when lo sits in half 0; when lo sits in half 1 the
+      // first 32 entries of the hi block (all the diagonal chunk reaches) are found in the copy behind half 1
+      if (half == 0 && g == 0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sts_v4(my_row + 512 + 16 * c, pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+      }
     };
     float m_run = -INFINITY, l_run = 0.f;
     const float sl2 = p.scale * 1.4426950408889634f;
@@ -310,18 +315,12 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
         cb::mbar_arrive(&sm.s_empty[rs.idx]);
         rs.advance();
         // this thread's 32-key chunk is chunk g; the warp's rows are 32*wq .. 32*wq+31, so
-        // g < wq: every lj < li -> "hi" block; g > wq: "lo" block; g == wq: per element  (warp-uniform)
+        // g < wq: every lj < li -> "hi" block; g > wq: "lo" block; g == wq: both  (warp-uniform)
 #pragma unroll
         for (int e = 0; e < 32; ++e) s[e] = __uint_as_float(r0[e]);
-        if (g != wq) {                 // packed 32-bit reads of the sheared window + FHADD (attn_tc_common.cuh)
-          shear_add32(s, (g < wq ? hi_base : lo_base) - 2 * (g * 32));
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int lj = g * 32 + e;
-            fhadd1(s[e], lds_u16((lj < li ? hi_base : lo_base) - 2 * lj));
-          }
-        }
+        // packed 32-bit reads of the sheared window + FHADD (attn_tc_common.cuh); the diagonal chunk's window runs from
+        // the lo block into the first entries of the hi block: contiguous in the staged row (see stage_bd)
+        shear_add32(s, (g < wq ? hi_base : lo_base) - 2 * (g * 32));
       }
       if (!(jc0 + CPT - 1 <= hi_i && jc0 >= lo_i)) {   // boundary tile: analytic mask
 #pragma unroll
