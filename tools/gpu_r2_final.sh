@@ -23,4 +23,9 @@ n = max(int(r[0]) for r in rows[hi+1:] if r and r[0].isdigit()) + 1
 per = n // 4
 print(subprocess.run(["python", "tools/launch_summary.py", "gpurun_out/r02_ncu_launches_bench.csv", "gpurun_out/r02_launch_shares_bench.md", str(2*per), str(3*per)], capture_output=True, text=True).stdout)
 PY
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"relattn_bwd_p1|relattn_bwd_band|relattn_fwd_tc" -s 5 -c 5 -o gpurun_out/r02_prof_attn_mat -f python tools/prof_bwd.py 16 > gpurun_out/r02_ncu.log 2>&1; tail -1 gpurun_out/r02_ncu.log
+# forward + the three kernels of one materialised backward (pass 1, merged dq_A/dq_C, dR): second iteration of prof_bwd.py
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"relattn_bwd_p1|relattn_bwd_band|relattn_fwd_tc" -s 4 -c 4 -o gpurun_out/r02_prof_attn_mat -f python tools/prof_bwd.py 16 > gpurun_out/r02_ncu.log 2>&1; tail -1 gpurun_out/r02_ncu.log
+# the K = 512 GEMM shapes (one-CTA and CTA-pair kernels, whole-tile epilogues)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"gemm_tcgen05" -c 18 -o gpurun_out/r02_prof_gemm -f python tools/prof_gemm.py > gpurun_out/r02_ncu_gemm.log 2>&1; tail -1 gpurun_out/r02_ncu_gemm.log
+timeout 300 python tools/time_gemm_shapes.py 2>/dev/null | tail -1 > gpurun_out/r02_gemm_shapes.json
+DROPATT=0.1 timeout 300 python tools/time_attn.py 16 5 2>/dev/null | tail -1 > gpurun_out/r02_time_attn.json; cat gpurun_out/r02_time_attn.json

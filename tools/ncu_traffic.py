@@ -30,8 +30,9 @@ def main():
     att = rows_of(sys.argv[1])
     bwd = [r for r in att if "relattn_bwd" in r[0]]
     fwd = [r for r in att if "relattn_fwd" in r[0]]
-    if bwd:   # one launch of bench.py's attn_bwd class = one commu_relattn_bwd call = the three passes together
-        per_call = max(1, len(bwd) // 3)
+    if bwd:   # one launch of bench.py's attn_bwd class = one commu_relattn_bwd call = every kernel of that call together
+        n_p1 = sum(1 for r in bwd if "bwd_p1" in r[0])          # materialised path: one pass-1 launch per call
+        per_call = n_p1 if n_p1 else max(1, len(bwd) // 3)       # recompute path: three passes per call
         res["attn_bwd"] = {"bytes_per_launch": round(sum(r[1] for r in bwd) / per_call), "launches": len(bwd),
                            "kernels": {r[0].split("(")[0].split("::")[-1]: round(r[1]) for r in bwd},
                            "source": os.path.basename(sys.argv[1])}
