@@ -6,7 +6,7 @@
 //     BD(b)   = (q+v) R_b^T                 [128 x 128]   one new 128-distance block of R per tile
 //     Opart   = P(t) V_t                    [128 x 64]    A = P in TMEM (bf16), B = V tile (MN-major)
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warp 2 = TMEM
-// allocator, warps 4-19 = four softmax warpgroups (thread = one query row x 32 key columns,
+// allocator (+ P~ store), warp 3 = P~ store, warps 4-19 = four softmax warpgroups (thread = one query row x 32 key columns,
 // tcgen05.ld 32x32b; the threads of a row exchange their partial max through shared memory).
 //
 // Relative shift: the distances a (query tile, key tile) pair needs are the 255-row band
@@ -211,16 +211,19 @@ relattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
         p_phase ^= 1;
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == 2 || warp == 3) {
     // ============================== P~ store (TMA, shared -> global) ==============================
     if (STORE && cb::elect_one()) {
       // one 32-row slab per row group (TMEM lane quadrant): the row groups stay independent of each other (a CTA-wide
-      // hand-over would make all 16 softmax warps move in lock-step); 4 x 2 boxes of {64 keys, 32 rows} per tile
+      // hand-over would make all 16 softmax warps move in lock-step); 4 x 2 boxes of {64 keys, 32 rows} per tile.
+      // Two store warps, two row groups each: a warp waits for its slab to be read before it signals it free, so one
+      // warp for all four serialised the groups behind each other.
       const int row0 = (b * p.H + h) * sa.Tpad + i0;
+      const int rg0 = (warp - 2) * 2;
       for (int t = 0; t < nt; ++t) {
         const int j0 = (jt_first + t) * TN;
 #pragma unroll 1
-        for (int rg = 0; rg < 4; ++rg) {
+        for (int rg = rg0; rg < rg0 + 2; ++rg) {
           cb::mbar_wait(&sm.pst_full[rg], t & 1);
           cb::tma_store_2d(&tm_ps, sm.pst + rg * 4096, j0, row0 + 32 * rg);
           cb::tma_store_2d(&tm_ps, sm.pst + TILE_BYTES + rg * 4096, j0 + 64, row0 + 32 * rg);
