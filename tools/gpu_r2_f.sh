@@ -13,4 +13,4 @@ for f in ("r2f_bench_n2", "r2f_bench_c5_n2"):
         j=json.load(open('gpurun_out/%s.json' % f)); print(f, {k:j.get(k) for k in ("metric","value","n_gpus","ms_per_step","e2e","kernel_time_ms_per_step","clocks","final_loss")})
     except Exception as e: print(f, "parse failed", e)
 PY
-tail -2 gpurun_out/r2f_bench_n2.err gpurun_out/r2f_bench_c5_n2.err
+tail -q -n 2 gpurun_out/r2f_bench_n2.err gpurun_out/r2f_bench_c5_n2.err
