@@ -192,7 +192,9 @@ int commu_dropout(const void* x, int x_is_bf16, int64_t ldx, const float* res, i
  * from the stored probabilities and written to the workspace in a coarse-sheared layout in which the relative shift
  * is a TMA stride; dq, dR and the two bias gradients are then pure TMA + tcgen05.mma streams (csrc/attn_bwd_mat.cu).
  * The first ws_zero_bytes of the workspace (commu_relattn_bwd_sizes) must be zero the first time it is used with a
- * shape (T, M, B, H); the kernels keep it valid afterwards, so one buffer serves every layer and step of that shape.
+ * shape (T, M, B, H); the kernels keep it valid afterwards, so one buffer serves every layer and step of that shape
+ * (calls that share a workspace must be ordered on one stream: it also carries the ticket counter and the hand-over
+ * flags of the merged dq launch, which every call resets; 128-byte alignment).
  * With p_save == NULL the three recompute passes run instead (no workspace). */
 int commu_relattn_bwd_sizes(int T, int M, int B, int H, int64_t* p_bytes, int64_t* mt_bytes, int64_t* ws_bytes,
                             int64_t* ws_zero_bytes);
