@@ -136,3 +136,52 @@ def test_coarse_sheared_layout_and_band_gemms(T, M):
         for j in range(min(K, i + M + 1)):
             ref_r[i + M - j] += dS[i, j] * qv[i]
     assert np.allclose(dR, ref_r)
+
+
+def merged_ticket_tile(ticket, Tpad):
+    """relattn_bwd_band_ac_kernel: ticket -> ((b,h) index, role, tile, hand-over block, number of dq_A tiles of the block)."""
+    nab = (Tpad // 8 + 127) // 128
+    nta = Tpad // 128
+    per_bh = nta + 8 * nab
+    bh, u = divmod(ticket, per_bh)
+    ab = nab - 1
+    while ab >= 0:
+        na = min(8, nta - 8 * ab)
+        if u < na:
+            return bh, "A", 8 * ab + na - 1 - u, ab, na
+        u -= na
+        if u < 8:
+            return bh, "C", (ab, u), ab, na
+        u -= 8
+        ab -= 1
+    raise AssertionError("ticket outside the grid")
+
+
+@pytest.mark.parametrize("T", [1, 100, 128, 300, 1024, 1100, 2048, 4096])
+def test_merged_dq_launch_ticket_order(T):
+    """The merged dq_A / dq_C launch: every row tile and every (row block, residue) is issued exactly once per (b,h); the
+    dq_A tiles a dq_C tile waits for cover exactly its rows and hold LOWER tickets (they run or are done when it waits)."""
+    Tpad = (T + 127) // 128 * 128
+    nab = (Tpad // 8 + 127) // 128
+    nta = Tpad // 128
+    per_bh = nta + 8 * nab
+    BH = 3
+    seen_a, seen_c, first_c_ticket, a_tickets = set(), set(), {}, {}
+    for ticket in range(BH * per_bh):
+        bh, role, tile, ab, na = merged_ticket_tile(ticket, Tpad)
+        assert bh == ticket // per_bh
+        if role == "A":
+            assert 0 <= tile < nta and (bh, tile) not in seen_a
+            assert tile // 8 == ab                      # the row tile signals the flag of ITS 1024-row block
+            seen_a.add((bh, tile))
+            a_tickets.setdefault((bh, ab), []).append(ticket)
+        else:
+            assert (bh, tile) not in seen_c
+            seen_c.add((bh, tile))
+            first_c_ticket.setdefault((bh, ab), ticket)
+            assert na == len(a_tickets[(bh, ab)])       # the count it waits for == dq_A tiles of the block, all issued earlier
+            assert max(a_tickets[(bh, ab)]) < ticket
+            # its rows 8 (128 ab + l) + r, l < 128, lie in the row tiles 8 ab .. 8 ab + 7 (those that exist)
+            lo, hi = 1024 * ab, min(1024 * ab + 1023, Tpad - 1)
+            assert {(bh, t) for t in range(lo // 128, hi // 128 + 1)} <= seen_a
+    assert len(seen_a) == BH * nta and len(seen_c) == BH * nab * 8
