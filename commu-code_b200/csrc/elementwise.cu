@@ -226,7 +226,8 @@ __global__ void ln_fwd_v4_kernel(const float* __restrict__ z, long long ldz, con
 }
 
 template <int MAXV>
-__global__ void ln_bwd_v4_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ z,
+__global__ void __launch_bounds__(THREADS, MAXV <= 4 ? 2 : 1)
+ln_bwd_v4_kernel(const float* __restrict__ dy, long long lddy, const float* __restrict__ z,
                                  long long ldz, const float* __restrict__ mean, const float* __restrict__ rstd,
                                  const float* __restrict__ gamma, int d, int dp, long long rows,
                                  float* __restrict__ dz_f32, long long lddz, bf16* __restrict__ dz_bf16,
@@ -234,20 +235,37 @@ __global__ void ln_bwd_v4_kernel(const float* __restrict__ dy, long long lddy, c
                                  uint32_t drop_thr2, uint32_t drop_ka, uint32_t drop_kb, float drop_inv) {
   __shared__ float sh_g[128 * MAXV];
   __shared__ float sh_b[128 * MAXV];
-  for (int c = threadIdx.x; c < 128 * MAXV; c += blockDim.x) sh_g[c] = sh_b[c] = 0.f;
+  __shared__ __align__(16) float sh_gamma[128 * MAXV];     // gamma is read from shared memory: 4 * MAXV registers fewer
+  for (int c = threadIdx.x; c < 128 * MAXV; c += blockDim.x) {
+    sh_g[c] = sh_b[c] = 0.f;
+    sh_gamma[c] = c < d ? gamma[c] : 0.f;
+  }
   __syncthreads();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  float4 gm[MAXV], acc_g[MAXV], acc_b[MAXV];
+  float4 acc_g[MAXV], acc_b[MAXV];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int c = 4 * (lane + 32 * i);
-    gm[i] = c < d ? __ldg(reinterpret_cast<const float4*>(gamma + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    acc_g[i] = acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+  for (int i = 0; i < MAXV; ++i) acc_g[i] = acc_b[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // software pipeline: the loads of this warp's NEXT row are issued as soon as the current row's values have been
+  // consumed, so they are in flight during the two warp reductions and the output phase (one row per warp at a time left
+  // 16 warps x 2 KB in flight per SM: 63 % of the copy bandwidth)
+  float4 dyv[MAXV], zv[MAXV];
+  float mu = 0.f, rs = 0.f;
+  auto load_row = [&](long long r) {
+    mu = mean[r]; rs = rstd[r];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int c = 4 * (lane + 32 * i);
+      if (c < d) {
+        dyv[i] = *reinterpret_cast<const float4*>(dy + r * lddy + c);
+        zv[i] = *reinterpret_cast<const float4*>(z + r * ldz + c);
+      }
+    }
+  };
+  if (warp < rows) load_row(warp);
   for (long long r = warp; r < rows; r += nwarps) {
-    const float mu = mean[r], rs = rstd[r];
+    const float rs_r = rs;
     float4 xh[MAXV], g[MAXV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -255,16 +273,17 @@ __global__ void ln_bwd_v4_kernel(const float* __restrict__ dy, long long lddy, c
       const int c = 4 * (lane + 32 * i);
       xh[i] = g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < d) {
-        const float4 dyv = *reinterpret_cast<const float4*>(dy + r * lddy + c);
-        const float4 zv = *reinterpret_cast<const float4*>(z + r * ldz + c);
-        xh[i] = make_float4((zv.x - mu) * rs, (zv.y - mu) * rs, (zv.z - mu) * rs, (zv.w - mu) * rs);
-        g[i] = make_float4(dyv.x * gm[i].x, dyv.y * gm[i].y, dyv.z * gm[i].z, dyv.w * gm[i].w);
-        acc_g[i].x += dyv.x * xh[i].x; acc_g[i].y += dyv.y * xh[i].y; acc_g[i].z += dyv.z * xh[i].z; acc_g[i].w += dyv.w * xh[i].w;
-        acc_b[i].x += dyv.x; acc_b[i].y += dyv.y; acc_b[i].z += dyv.z; acc_b[i].w += dyv.w;
+        const float4 dv = dyv[i];
+        xh[i] = make_float4((zv[i].x - mu) * rs, (zv[i].y - mu) * rs, (zv[i].z - mu) * rs, (zv[i].w - mu) * rs);
+        const float4 gmv = *reinterpret_cast<const float4*>(sh_gamma + c);
+        g[i] = make_float4(dv.x * gmv.x, dv.y * gmv.y, dv.z * gmv.z, dv.w * gmv.w);
+        acc_g[i].x += dv.x * xh[i].x; acc_g[i].y += dv.y * xh[i].y; acc_g[i].z += dv.z * xh[i].z; acc_g[i].w += dv.w * xh[i].w;
+        acc_b[i].x += dv.x; acc_b[i].y += dv.y; acc_b[i].z += dv.z; acc_b[i].w += dv.w;
         s1 += (g[i].x + g[i].y) + (g[i].z + g[i].w);
         s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
       }
     }
+    if (r + nwarps < rows) load_row(r + nwarps);
     s1 = cb::warp_sum(s1) / d;
     s2 = cb::warp_sum(s2) / d;
     const drop::Keys dk = drop::row_keys(drop_ka, drop_kb, (uint32_t)r);
@@ -274,10 +293,10 @@ __global__ void ln_bwd_v4_kernel(const float* __restrict__ dy, long long lddy, c
       if (c < dp) {
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (c < d) {
-          o.x = rs * (g[i].x - s1 - xh[i].x * s2);
-          o.y = rs * (g[i].y - s1 - xh[i].y * s2);
-          o.z = rs * (g[i].z - s1 - xh[i].z * s2);
-          o.w = rs * (g[i].w - s1 - xh[i].w * s2);
+          o.x = rs_r * (g[i].x - s1 - xh[i].x * s2);
+          o.y = rs_r * (g[i].y - s1 - xh[i].y * s2);
+          o.z = rs_r * (g[i].z - s1 - xh[i].z * s2);
+          o.w = rs_r * (g[i].w - s1 - xh[i].w * s2);
         }
         if (dz_f32) *reinterpret_cast<float4*>(dz_f32 + r * lddz + c) = o;
         if (dz_bf16) {
