@@ -14,6 +14,8 @@ except Exception as e: print("bench parse failed", e)
 PY
 tail -3 gpurun_out/r02_bench_default_final.err
 timeout 600 python bench.py --batch-chunk 4 --no-decode --no-cpu-baseline --no-reference-gpu > gpurun_out/r02_bench_batch_chunk4.json 2>/dev/null; cut -c1-300 gpurun_out/r02_bench_batch_chunk4.json
+timeout 900 python bench.py --config c5 --steps 4 --warmup 3 > gpurun_out/r02_bench_c5_n1.json 2>/dev/null; cut -c1-300 gpurun_out/r02_bench_c5_n1.json
+timeout 300 python tools/time_ln.py 2>/dev/null | tail -1 > gpurun_out/r02_time_ln.json
 COMMU_BENCH_PROFILE=1 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02_ncu_launches_bench.csv python bench.py --steps 1 --warmup 2 --no-decode --no-cpu-baseline --no-reference-gpu > gpurun_out/r02_bench_under_ncu.log 2>&1
 python - <<'PY'
 import csv, subprocess
