@@ -257,6 +257,14 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
       const float mt_n = (n & 1) ? mt_q[1] : mt_q[0];
       const float f = vis ? ex2(fminf(mt_n - lse_n * LOG2E, 0.f) - lkeep) : 0.f;
       const float ndelta = -(DROP ? del_n * p.drop_keep : del_n);
+      if (g == 0 && lane == 0) {   // ... and the lines of the tile five ahead are pulled into L2 (one 128-byte line per warp)
+        const int i5 = i + 5 * TM;
+        if (n + 5 < nq && i5 < p.T) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(lse_p + i5));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(del_p + i5));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(mt_p + i5));
+        }
+      }
       {
         const int i2 = i + 2 * TM;
         float a = 0.f, bq = 0.f, c = 0.f;

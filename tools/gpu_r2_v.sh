@@ -1,11 +1,6 @@
 #!/bin/bash
-# round 2, call V: attention forward change - parity, timing, bench line
+# round 2, call V: attention kernel change - parity, timing, bench line
 set +e
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests/test_kernels_gpu.py tests/test_dropout_gpu.py tests/test_model_gpu.py -q -m gpu -x -k "relattn or dropout or forward_backward or train" 2>&1 | tail -3
-DROPATT=0.1 timeout 300 python tools/time_attn.py 16 5 2>&1 | tail -1
-timeout 600 python bench.py --no-decode --no-cpu-baseline --no-reference-gpu > gpurun_out/r2v_bench.json 2>/dev/null
-python - <<'PY'
-import json
-j=json.load(open('gpurun_out/r2v_bench.json')); print({k:j.get(k) for k in ("value","ms_per_step","kernel_time_ms_per_step","final_loss")})
-PY
+DROPATT=0.1 timeout 300 python tools/time_attn.py 16 9 2>&1 | tail -1
