@@ -362,7 +362,7 @@ relattn_bwd_p1_kernel(const __grid_constant__ CUtensorMap tm_v, const __grid_con
 // ================================================================================================================
 constexpr int MODE_A = 0, MODE_C = 1, MODE_R = 2;
 constexpr int G_THREADS = 64 + 128;   // warp 0: TMA producer (+ TMEM alloc), warp 1: MMA issuer, warps 2-5: epilogue
-constexpr int G_STAGES = 4;
+constexpr int G_STAGES = 2;   // x 2 CTAs per SM: one CTA's epilogue overlaps the other's stream (4 stages x 1 CTA: same bytes in flight)
 
 struct GSmem {
   uint8_t a[G_STAGES][TILE32];   // dS tile: [column half][128 rows][128 B], 128B swizzle
@@ -590,7 +590,7 @@ __device__ __forceinline__ void band_body(GSmem& sm,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(G_THREADS, 1)
+__global__ void __launch_bounds__(G_THREADS, 2)
 relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_a4,
                         const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ Maps8 tm_qv,
                         const MatParams p) {
@@ -606,7 +606,7 @@ relattn_bwd_band_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 // block down, heaviest first), the <= 8 key-indexed row tiles (dq_A) and then the 8 residue classes of the same rows
 // (dq_C) - the second view finds the rows in L2.  The ticket (not blockIdx) fixes the order, so the one dependency -
 // dq_C adds the fp32 dq_A rows and writes the bf16 result - only ever waits on CTAs that already run.
-__global__ void __launch_bounds__(G_THREADS, 1)
+__global__ void __launch_bounds__(G_THREADS, 2)
 relattn_bwd_band_ac_kernel(const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_a4,
                            const __grid_constant__ CUtensorMap tm_res, const __grid_constant__ CUtensorMap tm_k,
                            const __grid_constant__ CUtensorMap tm_rr, const MatParams p) {
