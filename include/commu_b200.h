@@ -46,6 +46,9 @@ int commu_device_info(int* sm_major, int* sm_minor, int* num_sms);
  *   v = alpha*acc ; v += bias[n] ; v = relu(v) ; v *= (relu_mask[m,n] > 0) ; v = dropout(v) ; v += add_f32[m,n]
  *   out_bf16[m,n] = bf16(v) ; out_f32[m,n] = v (f32_atomic=0) or atomically += v (f32_atomic=1)
  * split_k > 1 partitions the k range over CTAs and requires f32_atomic = 1 and no bf16 output.
+ * When every output tile is full (m a multiple of 128 - 256 for the CTA-pair kernel -, n of the tile width) and the
+ * buffers allow 16-byte accesses, a whole-tile epilogue instantiation is launched for the bf16-only and the fp32-only
+ * results (same arithmetic, same order; COMMU_GEMM_FAST_EPI=0 keeps the general per-chunk epilogue).
  * impl: 0 = tcgen05 kernels (product path: the CTA-pair kernel, tcgen05 cta_group::2 on 256 x 256 tiles with the B tile
  *       split across the two SMs of a TPC, for n > 128 and m > 128; else the one-CTA kernel), 1 = naive SIMT kernel
  *       (test cross-check only), 2 / 3 = force the CTA-pair / the one-CTA tcgen05 kernel.
