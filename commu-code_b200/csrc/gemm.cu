@@ -1042,7 +1042,8 @@ extern "C" int commu_gemm_bf16(const commu_gemm_args* a, void* stream_) {
     const char* e = getenv("COMMU_GEMM_2CTA");
     return (e && e[0] == '0') ? 0 : 1;
   }();
-  // (measured: +10-12 % where a split's reduction length is >= 1024, no gain on the epilogue-paced K = 512 shapes)
+  // (measured with the whole-tile epilogues, profiles/r02_gemm_shapes.json: +10-14 % where a split's reduction length
+  //  is >= 1024; on the K = 512 shapes the one-CTA kernel is 5-8 % faster)
   const int k_per_split = a->k / split;
   const bool pair = a->impl == 2 || (a->impl == 0 && use_2cta && a->n > 128 && a->m > BLOCK_M && k_per_split >= 1024);
   const int block_n = (pair || a->n > 128) ? 256 : 128;
