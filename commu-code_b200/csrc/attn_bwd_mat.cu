@@ -11,6 +11,8 @@
 //                             dq_C = dB Rrev         (rows of one residue i mod 8, distance blocks walked)
 //                             dR  += dB^T (q+v)      (one distance block, all (b, rows) walked)
 //                             pure TMA + tcgen05.mma streams: no exp, no shear, no RNG, no score recompute.
+//                             dq_A and dq_C share ONE ticket-ordered launch (the second view of the dS rows comes from
+//                             L2); two ring stages and two CTAs per SM, so one CTA's epilogue overlaps the other's stream.
 //
 // The relative shift costs nothing in this layout.  Element (i, j) of one (b,h) lives at
 //     row i, column  c = j + X - 8*(i >> 3)            (pitch P elements, X = Tpad)
